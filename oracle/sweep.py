@@ -1,0 +1,425 @@
+"""Oracle: MPS container, environments, two sweep drivers (DMRG ground state, TDVP-PS).
+
+NumPy restatement of the reference's sweep path; see oracle/__init__.py for the rules.
+"""
+import numpy as np
+import scipy.linalg
+
+from .contract import hop_apply, hop_diag, env_update
+from .svdqn import add_outer, get_qn_mask, svd_qn, select_basis
+from .krylov import expm_krylov
+from .davidson import davidson
+
+
+class Mps:
+    """Site tensors (l, d, r) + quantum-number bookkeeping.
+
+    Reference: renormalizer/mps/mp.py:34-80 (MatrixProduct state), mps/mps.py:118.
+    """
+
+    def __init__(self, sites, qn, sigmaqn, qntot, qnidx, to_right, coeff=1.0):
+        self.sites = [np.asarray(s) for s in sites]
+        self.qn = [np.asarray(q) for q in qn]
+        self.sigmaqn = [np.asarray(s) for s in sigmaqn]
+        self.qntot = np.asarray(qntot)
+        self.qnidx = int(qnidx)
+        self.to_right = bool(to_right)
+        self.coeff = coeff
+
+    def __len__(self):
+        return len(self.sites)
+
+    def copy(self):
+        return Mps([s.copy() for s in self.sites], [q.copy() for q in self.qn], self.sigmaqn,
+                   self.qntot.copy(), self.qnidx, self.to_right, self.coeff)
+
+    def to_complex(self):
+        m = self.copy()
+        m.sites = [s.astype(np.complex128) for s in m.sites]
+        return m
+
+    @property
+    def bond_dims(self):
+        return [s.shape[0] for s in self.sites] + [self.sites[-1].shape[-1]]
+
+    # -- reference: mp.py:230-243
+    def iter_idx_list(self, full, stop_idx=None):
+        n = len(self)
+        if self.to_right:
+            last = stop_idx if stop_idx is not None else (n if full else n - 1)
+            return range(self.qnidx, last)
+        last = stop_idx if stop_idx is not None else (-1 if full else 0)
+        return range(self.qnidx, last, -1)
+
+    # -- reference: mp.py:297-306
+    def switch_direction(self):
+        if self.to_right:
+            self.qnidx = len(self) - 1
+            self.to_right = False
+        else:
+            self.qnidx = 0
+            self.to_right = True
+
+    # -- reference: mp.py:159-172
+    def move_qnidx(self, dstidx):
+        n = len(self)
+        for idx in range(self.qnidx + 1, n + 1):
+            self.qn[idx] = self.qntot - self.qn[idx]
+        for idx in range(n, dstidx, -1):
+            self.qn[idx] = self.qntot - self.qn[idx]
+        self.qnidx = dstidx
+
+    # -- reference: mp.py:308-352
+    def big_qn(self, cidx):
+        sq = [self.sigmaqn[i] for i in cidx]
+        qnl = self.qn[cidx[0]]
+        qnr = self.qn[cidx[-1] + 1]
+        if len(cidx) == 1:
+            if self.to_right:
+                qnbigl, qnbigr = add_outer(qnl, sq[0]), qnr
+            else:
+                qnbigl, qnbigr = qnl, add_outer(sq[0], qnr)
+        else:
+            qnbigl, qnbigr = add_outer(qnl, sq[0]), add_outer(sq[1], qnr)
+        return qnbigl, qnbigr, add_outer(qnbigl, qnbigr)
+
+    # -- reference: mp.py:890-908 (_push_cano) + mp.py:245-295 (_update_ms, sigma=None, MPS)
+    def push_cano(self, idx):
+        qnbigl, qnbigr, _ = self.big_qn([idx])
+        system = "L" if self.to_right else "R"
+        shape = self.sites[idx].shape
+        u, qnlset, v, qnrset = svd_qn(self.sites[idx], qnbigl, qnbigr, self.qntot, QR=True,
+                                      system=system, full_matrices=False)
+        vt = v.T
+        m = u.shape[1]
+        if self.to_right:
+            self.sites[idx + 1] = np.tensordot(vt, self.sites[idx + 1], axes=1)
+            self.sites[idx] = u.reshape(shape[:-1] + (m,))
+            self.qn[idx + 1] = np.array(qnlset)
+            self.qnidx = idx + 1
+        else:
+            self.sites[idx - 1] = np.tensordot(self.sites[idx - 1], u, axes=1)
+            self.sites[idx] = vt.reshape((m,) + shape[1:])
+            self.qn[idx] = np.array(qnrset)
+            self.qnidx = idx - 1
+
+    # -- reference: mp.py:910-922
+    def canonicalise(self):
+        idx = None
+        for idx in self.iter_idx_list(full=False):
+            self.push_cano(idx)
+        if (not self.to_right and idx == 1) or (self.to_right and idx == len(self) - 2):
+            self.switch_direction()
+        return self
+
+    def check_left_canonical(self, atol=1e-8, rtol=1e-5):
+        for s in self.sites[:-1]:
+            m = s.reshape(-1, s.shape[-1])
+            if not np.allclose(m.T.conj() @ m, np.eye(m.shape[1]), rtol=rtol, atol=atol):
+                return False
+        return True
+
+    def check_right_canonical(self, atol=1e-8, rtol=1e-5):
+        for s in self.sites[1:]:
+            m = s.reshape(s.shape[0], -1)
+            if not np.allclose(m @ m.T.conj(), np.eye(m.shape[0]), rtol=rtol, atol=atol):
+                return False
+        return True
+
+    # -- reference: mp.py:206-228
+    def ensure_left_canonical(self):
+        if self.to_right or self.qnidx != len(self) - 1 or not self.check_left_canonical():
+            self.move_qnidx(0)
+            self.to_right = True
+            return self.canonicalise()
+        return self
+
+    def ensure_right_canonical(self):
+        if (not self.to_right) or self.qnidx != 0 or not self.check_right_canonical():
+            self.move_qnidx(len(self) - 1)
+            self.to_right = False
+            return self.canonicalise()
+        return self
+
+    # -- reference: mp.py:933-958 (dot), mp.py:355-372 (mp_norm)
+    def dot_conj(self, other):
+        """<self|other>"""
+        e0 = np.eye(1)
+        for a, b in zip(self.sites, other.sites):
+            e0 = np.tensordot(e0, b, 1)
+            e0 = np.tensordot(e0, a.conj(), ([0, 1], [0, 1])).T
+        return complex(e0[0, 0])
+
+    @property
+    def mp_norm(self):
+        res = self.dot_conj(self).real
+        return float(np.sqrt(max(res, 0.0)))
+
+    # -- reference: mps.py:2025-2058 ("mps_only") + mp.py:984-994 (scale at qnidx)
+    def normalize_mps_only(self):
+        self.sites[self.qnidx] = self.sites[self.qnidx] * (1.0 / self.mp_norm)
+        return self
+
+    # -- reference: mps.py:471-525 (expectation through a right environment)
+    def expectation(self, mpo):
+        r = np.ones((1, 1, 1))
+        for i in range(len(self) - 1, -1, -1):
+            r = env_update(r, self.sites[i], mpo[i], "R")
+        val = complex(r[0, 0, 0])
+        return val.real if np.isclose(val.imag, 0) else val
+
+
+class Environ:
+    """Left/right environment store.  Reference: renormalizer/mps/lib.py:12-129."""
+
+    def __init__(self, mps, mpo, domain=None):
+        self.disk = {}
+        self.sentinel = np.ones((1, 1, 1))
+        self.disk[("L", -1)] = self.sentinel
+        self.disk[("R", len(mps))] = self.sentinel
+        for dom in (["L", "R"] if domain is None else [domain]):
+            n = len(mps)
+            rng = range(0, n - 1) if dom == "L" else range(n - 1, 0, -1)
+            t = self.sentinel
+            for i in rng:
+                t = env_update(t, mps.sites[i], mpo[i], dom)
+                self.disk[(dom, i)] = t
+
+    def read(self, domain, idx):
+        return self.disk[(domain, idx)]
+
+    def get_lr(self, domain, idx, mps, mpo, method):
+        if idx < 0 or idx >= len(mps):
+            return self.sentinel
+        if method == "Enviro":
+            return self.read(domain, idx)
+        assert method == "System"
+        prev = self.read(domain, idx + (-1 if domain == "L" else 1))
+        t = env_update(prev, mps.sites[idx], mpo[idx], domain)
+        self.disk[(domain, idx)] = t
+        return t
+
+
+def m_trunc_fixed(sigma, m_max):
+    """Reference: utils/configs.py:202-205 (_fixed_m_trunc with a uniform max bond dimension)."""
+    return min(int(m_max), len(sigma))
+
+
+def m_trunc_threshold(sigma, threshold):
+    """Reference: utils/configs.py:196-200 (_threshold_m_trunc)."""
+    return int(np.sum(sigma / scipy.linalg.norm(sigma) > threshold))
+
+
+def update_mps(mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent=0.0):
+    """Decompose the optimised centre tensor and move the centre one site on.
+
+    Reference: renormalizer/mps/mp.py:651-888 (_update_mps), single-state SVD branch (no OFS).
+    """
+    system = "L" if mps.to_right else "R"
+    u, su, qnlnew, v, sv, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, mps.qntot, system=system)
+    if mps.to_right:
+        ms, msdim, msqn, compms = select_basis(u, su, qnlnew, v, m_trunc_fixed(su, m_max), percent)
+        ms = ms.reshape(list(qnbigl.shape[:-1]) + [msdim])
+        compms = np.moveaxis(compms.reshape(list(qnbigr.shape[:-1]) + [msdim]), -1, 0)
+    else:
+        ms, msdim, msqn, compms = select_basis(v, sv, qnrnew, u, m_trunc_fixed(sv, m_max), percent)
+        ms = np.moveaxis(ms.reshape(list(qnbigr.shape[:-1]) + [msdim]), -1, 0)
+        compms = compms.reshape(list(qnbigl.shape[:-1]) + [msdim])
+    n = len(mps)
+    if len(cidx) == 1:
+        i = cidx[0]
+        mps.sites[i] = ms
+        if mps.to_right:
+            if i != n - 1:
+                mps.sites[i + 1] = np.tensordot(compms, mps.sites[i + 1], axes=1)
+                mps.qn[i + 1] = msqn
+                mps.qnidx = i + 1
+            else:
+                mps.sites[i] = np.tensordot(mps.sites[i], compms, axes=1)
+                mps.qnidx = n - 1
+        else:
+            if i != 0:
+                mps.sites[i - 1] = np.tensordot(mps.sites[i - 1], compms, axes=1)
+                mps.qn[i] = msqn
+                mps.qnidx = i - 1
+            else:
+                mps.sites[i] = np.tensordot(compms, mps.sites[i], axes=1)
+                mps.qnidx = 0
+    else:
+        if mps.to_right:
+            mps.sites[cidx[0]], mps.sites[cidx[1]] = ms, compms
+            mps.qnidx = cidx[1]
+        else:
+            mps.sites[cidx[1]], mps.sites[cidx[0]] = ms, compms
+            mps.qnidx = cidx[0]
+        mps.qn[cidx[1]] = msqn
+
+
+def _sign_fix(c):
+    """Reference: mps/gs.py:372-380."""
+    return c / np.sign(c[np.abs(c).argmax()])
+
+
+def _scatter(c, mask):
+    """Reference: mps/lib.py:438-457 (cvec2cmat, one root)."""
+    out = np.zeros(mask.shape, dtype=c.dtype)
+    out[mask] = c
+    return out
+
+
+def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, stats=None):
+    """One DMRG sweep over all sites.  Reference: renormalizer/mps/gs.py:174-304 (nroots=1,
+    omega=None, algo="davidson").  Returns (micro results [(e, cidx)], res_mps)."""
+    n = len(mps)
+    micro = []
+    res_mps = None
+    for imps in mps.iter_idx_list(full=True):
+        if method == "2site" and ((mps.to_right and imps == n - 1) or
+                                  (not mps.to_right and imps == 0)):
+            break
+        lmethod, rmethod = ("System", "Enviro") if mps.to_right else ("Enviro", "System")
+        if method == "1site":
+            lidx, cidx, ridx = imps - 1, [imps], imps + 1
+        elif mps.to_right:
+            lidx, cidx, ridx = imps - 1, [imps, imps + 1], imps + 2
+        else:
+            lidx, cidx, ridx = imps - 2, [imps - 1, imps], imps + 1
+        ltensor = environ.get_lr("L", lidx, mps, mpo, lmethod)
+        rtensor = environ.get_lr("R", ridx, mps, mpo, rmethod)
+        qnbigl, qnbigr, qnmat = mps.big_qn(cidx)
+        mask = get_qn_mask(qnmat, mps.qntot)
+        cshape = mask.shape
+        cmo = [mpo[i] for i in cidx]
+        if np.prod(cshape) < 1000:
+            # direct diagonalisation.  Reference: gs.py:307-407
+            if len(cidx) == 1:
+                ham = np.einsum("abc,bdef,lfk->adlcek", ltensor, cmo[0], rtensor, optimize=True)
+                ham = ham[:, :, :, mask][mask, :]
+            else:
+                ham = np.einsum("abc,bdef,fghj,ljk->adglcehk", ltensor, cmo[0], cmo[1], rtensor,
+                                optimize=True)
+                ham = ham[:, :, :, :, mask][mask, :]
+            w, vec = scipy.linalg.eigh(ham)
+            e, c = w[0], _sign_fix(vec[:, 0])
+            nhop = 0
+        else:
+            # Davidson.  Reference: gs.py:410-576
+            if len(cidx) == 1:
+                guess = mps.sites[cidx[0]]
+            else:
+                guess = np.tensordot(mps.sites[cidx[0]], mps.sites[cidx[1]], axes=1)
+            hdiag = hop_diag(ltensor, rtensor, cmo)[mask]
+            count = [0]
+
+            def hop(x):
+                count[0] += 1
+                return hop_apply(ltensor, rtensor, cmo, _scatter(x, mask))[mask]
+
+            def precond(x, e, *args):
+                return x / (hdiag - e + 1e-4)
+            e, c = davidson(hop, [guess[mask]], precond, max_cycle=100, nroots=1)
+            c = _sign_fix(c)
+            nhop = count[0]
+        if stats is not None:
+            stats.append(nhop)
+        micro.append((e, cidx))
+        cstruct = _scatter(c, mask)
+        if cidx == last_opt_idx:
+            res_mps = mps.copy()
+            update_mps(res_mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent)
+        update_mps(mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent)
+    mps.switch_direction()
+    return micro, res_mps
+
+
+def optimize_mps(mps, mpo, procedure, method="2site", e_rtol=1e-6, e_atol=1e-8, stats=None,
+                 micro_out=None):
+    """DMRG ground state.  Reference: renormalizer/mps/gs.py:54-171.  `mps` is overwritten.
+    Returns (energy per sweep, optimised Mps)."""
+    if mps.qnidx == len(mps) - 1:     # is_left_canonical
+        mps.ensure_right_canonical()
+        env = "R"
+    else:
+        mps.ensure_left_canonical()
+        env = "L"
+    environ = Environ(mps, mpo, env)
+    macro = []
+    opt_idx = None
+    res_mps = None
+    for isweep, (m_max, percent) in enumerate(procedure):
+        micro, res_mps, = dmrg_single_sweep(mps, mpo, environ, method, int(m_max), percent,
+                                            opt_idx, stats)
+        if micro_out is not None:
+            micro_out.append(np.array([e for e, _ in micro]))
+        opt_e = min(micro)
+        macro.append(opt_e[0])
+        opt_idx = opt_e[1]
+        if isweep > 0 and percent == 0:
+            v1, v2 = sorted(macro)[:2]
+            if np.allclose(v1, v2, rtol=e_rtol, atol=e_atol):
+                break
+    assert res_mps is not None
+    res_mps.normalize_mps_only()
+    res_mps.ensure_left_canonical()
+    res_mps.canonicalise()
+    return macro, res_mps
+
+
+def evolve_tdvp_ps(mps_in, mpo, dt, normalize=True, stats=None):
+    """One time step of one-site projector-splitting TDVP (two half sweeps, Krylov local solver).
+
+    Reference: renormalizer/mps/mps.py:1268-1404 (_evolve_tdvp_ps, ivp_solver == "krylov") and
+    mps.py:644-662 (evolve -> normalize "mps_only" for real dt).
+    """
+    mps = mps_in.to_complex() if not np.iscomplex(dt) else mps_in.copy()
+    n = len(mps)
+    environ = Environ(mps, mpo)
+    for _ in range(2):
+        for imps in mps.iter_idx_list(full=True):
+            system = "L" if mps.to_right else "R"
+            l_array = environ.read("L", imps - 1)
+            r_array = environ.read("R", imps + 1)
+            shape = list(mps.sites[imps].shape)
+            w = mpo[imps]
+            mps_t, j = expm_krylov(
+                lambda y: hop_apply(l_array, r_array, [w], y.reshape(shape)).ravel(),
+                -1j * dt / 2, mps.sites[imps].ravel())
+            if stats is not None:
+                stats.append(j)
+            mps_t = mps_t.reshape(shape)
+            qnbigl, qnbigr, _ = mps.big_qn([imps])
+            u, qnlset, v, qnrset = svd_qn(mps_t, qnbigl, qnbigr, mps.qntot, QR=True,
+                                          system=system, full_matrices=False)
+            vt = v.T
+            if not mps.to_right and imps != 0:
+                mps.sites[imps] = vt.reshape([-1] + shape[1:])
+                mps.qn[imps] = np.array(qnrset)
+                mps.qnidx = imps - 1
+                r_array = environ.get_lr("R", imps, mps, mpo, "System")
+                su = u.shape
+                back, j = expm_krylov(
+                    lambda y: hop_apply(l_array, r_array, [], y.reshape(su)).ravel(),
+                    1j * dt / 2, u.ravel())
+                if stats is not None:
+                    stats.append(j)
+                mps.sites[imps - 1] = np.tensordot(mps.sites[imps - 1], back.reshape(su),
+                                                   axes=(-1, 0))
+            elif mps.to_right and imps != n - 1:
+                mps.sites[imps] = u.reshape(shape[:-1] + [-1])
+                mps.qn[imps + 1] = np.array(qnlset)
+                mps.qnidx = imps + 1
+                l_array = environ.get_lr("L", imps, mps, mpo, "System")
+                sv = vt.shape
+                back, j = expm_krylov(
+                    lambda y: hop_apply(l_array, r_array, [], y.reshape(sv)).ravel(),
+                    1j * dt / 2, vt.ravel())
+                if stats is not None:
+                    stats.append(j)
+                mps.sites[imps + 1] = np.tensordot(back.reshape(sv), mps.sites[imps + 1],
+                                                   axes=(1, 0))
+            else:
+                mps.sites[imps] = mps_t
+        mps.switch_direction()
+    if normalize:
+        mps.normalize_mps_only()
+    return mps

@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) in the build
+container.  TEST TOOLING ONLY -- never imported by the product, never run on the GPU box.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference needs three third-party packages that this image lacks (opt_einsum, h5py,
+print_tree2); `tests/golden/_shims/` holds minimal stand-ins for them (einsum -> numpy.einsum).
+Every array below is produced by reference code paths:
+
+  kernels.npz   hop_expr (mps/hop_expr.py:7), contract_one_site (mps/lib.py:172)
+  svdqn.npz     svd_qn (mps/svd_qn.py:97) in SVD and QR modes
+  krylov.npz    expm_krylov (lib/krylov/krylov.py:28)
+  davidson.npz  davidson (lib/davidson/davidson.py:73)
+  holstein.npz  Mpo(holstein_model), Mps.random, optimize_mps (mps/gs.py:54), 1site + 2site
+  sbm.npz       SpinBosonModel MPO, expand_bond_dimension'd MPS, Mps.evolve with tdvp_ps
+                (mps/mps.py:1268), sigma_z trajectory and final MPS
+"""
+import os
+import sys
+import logging
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+
+logging.disable(logging.INFO)
+
+from renormalizer.mps.hop_expr import hop_expr  # noqa: E402
+from renormalizer.mps.lib import contract_one_site  # noqa: E402
+from renormalizer.mps import svd_qn as ref_svd_qn  # noqa: E402
+from renormalizer.lib.krylov.krylov import expm_krylov  # noqa: E402
+from renormalizer.lib import davidson  # noqa: E402
+
+
+def crand(rng, shape, cplx):
+    a = rng.standard_normal(shape)
+    if cplx:
+        a = a + 1j * rng.standard_normal(shape)
+    return a
+
+
+def gen_kernels():
+    rng = np.random.default_rng(20261017)
+    out = {}
+    for cplx in (False, True):
+        tag = "c" if cplx else "r"
+        Ml, Mr, w0, w1, w2, d1, d2, anc = 7, 9, 3, 4, 5, 3, 4, 2
+        L = crand(rng, (Ml, w0, Ml), cplx)
+        R = crand(rng, (Mr, w2, Mr), cplx)
+        W1 = crand(rng, (w0, d1, d1, w1), False)
+        W2 = crand(rng, (w1, d2, d2, w2), False)
+        # make the MPO site sparse like real ones
+        W1[rng.random(W1.shape) < 0.5] = 0
+        W2[rng.random(W2.shape) < 0.5] = 0
+        # one-site: R must carry W1's right bond
+        R1 = crand(rng, (Mr, w1, Mr), cplx)
+        C1 = crand(rng, (Ml, d1, Mr), cplx)
+        C2 = crand(rng, (Ml, d1, d2, Mr), cplx)
+        C1a = crand(rng, (Ml, d1, anc + 1, Mr), cplx)
+        C2a = crand(rng, (Ml, d1, anc + 1, d2, anc, Mr), cplx)
+        R0 = crand(rng, (Mr, w0, Mr), cplx)
+        C0 = crand(rng, (Ml, Mr), cplx)
+        out.update({f"{tag}_L": L, f"{tag}_R": R, f"{tag}_R1": R1, f"{tag}_R0": R0,
+                    f"{tag}_W1": W1, f"{tag}_W2": W2,
+                    f"{tag}_C0": C0, f"{tag}_C1": C1, f"{tag}_C2": C2,
+                    f"{tag}_C1a": C1a, f"{tag}_C2a": C2a})
+        out[f"{tag}_hop0"] = hop_expr(L, R0, [], C0.shape)(C0)
+        out[f"{tag}_hop1"] = hop_expr(L, R1, [W1.copy()], C1.shape)(C1)
+        out[f"{tag}_hop2"] = hop_expr(L, R, [W1.copy(), W2.copy()], C2.shape)(C2)
+        out[f"{tag}_hop1a"] = hop_expr(L, R1, [W1.copy()], C1a.shape)(C1a)
+        out[f"{tag}_hop2a"] = hop_expr(L, R, [W1.copy(), W2.copy()], C2a.shape)(C2a)
+        # environment updates: MPS site (ndim 3) and MPDM site (ndim 4)
+        A3 = crand(rng, (Ml, d1, Mr), cplx)
+        A4 = crand(rng, (Ml, d1, anc, Mr), cplx)
+        out[f"{tag}_A3"] = A3
+        out[f"{tag}_A4"] = A4
+        out[f"{tag}_envL3"] = contract_one_site(L, A3, W1, "L")
+        out[f"{tag}_envL4"] = contract_one_site(L, A4, W1, "L")
+        out[f"{tag}_envR3"] = contract_one_site(R1, A3, W1, "R")
+        out[f"{tag}_envR4"] = contract_one_site(R1, A4, W1, "R")
+    np.savez_compressed(os.path.join(HERE, "kernels.npz"), **out)
+
+
+def gen_svdqn():
+    rng = np.random.default_rng(7)
+    out = {}
+    # one-site tensor (l, sigma, r) with a U(1) quantum number, total qn = 1
+    ml, d, mr = 6, 3, 5
+    qnl = rng.integers(0, 2, size=(ml, 1))
+    sigmaqn = np.array([[0], [1], [0]])
+    qnr = rng.integers(0, 2, size=(mr, 1))
+    qntot = np.array([1])
+    for cplx in (False, True):
+        tag = "c" if cplx else "r"
+        for system in ("L", "R"):
+            if system == "L":
+                qnbigl = ref_svd_qn.add_outer(qnl, sigmaqn)
+                qnbigr = qnr
+            else:
+                qnbigl = qnl
+                qnbigr = ref_svd_qn.add_outer(sigmaqn, qnr)
+            qnmat = ref_svd_qn.add_outer(qnbigl, qnbigr)
+            mask = ref_svd_qn.get_qn_mask(qnmat, qntot)
+            c = crand(rng, (ml, d, mr), cplx)
+            c[~mask] = 0
+            key = f"{tag}_{system}"
+            out[key + "_c"] = c
+            out[key + "_qnbigl"] = qnbigl
+            out[key + "_qnbigr"] = qnbigr
+            u, su, qnlnew, v, sv, qnrnew = ref_svd_qn.svd_qn(
+                c, qnbigl, qnbigr, qntot, system=system, full_matrices=False)
+            out[key + "_svd_u"], out[key + "_svd_s"], out[key + "_svd_v"] = u, su, v
+            out[key + "_svd_qnl"], out[key + "_svd_qnr"] = np.array(qnlnew), np.array(qnrnew)
+            np.random.seed(11)
+            u, su, qnlnew, v, sv, qnrnew = ref_svd_qn.svd_qn(
+                c, qnbigl, qnbigr, qntot, system=system, full_matrices=True)
+            out[key + "_fsvd_u"], out[key + "_fsvd_su"], out[key + "_fsvd_v"] = u, su, v
+            out[key + "_fsvd_sv"] = sv
+            out[key + "_fsvd_qnl"], out[key + "_fsvd_qnr"] = np.array(qnlnew), np.array(qnrnew)
+            u, qnlnew, v, qnrnew = ref_svd_qn.svd_qn(
+                c, qnbigl, qnbigr, qntot, QR=True, system=system, full_matrices=False)
+            out[key + "_qr_u"], out[key + "_qr_v"] = u, v
+            out[key + "_qr_qnl"], out[key + "_qr_qnr"] = np.array(qnlnew), np.array(qnrnew)
+    out["qntot"] = qntot
+    np.savez_compressed(os.path.join(HERE, "svdqn.npz"), **out)
+
+
+def gen_krylov():
+    rng = np.random.default_rng(3)
+    n = 80
+    h = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    h = (h + h.conj().T) / 2
+    v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    out = {"h": h, "v": v}
+    for i, dt in enumerate((-0.05j, 0.3j, -0.2)):
+        res, j = expm_krylov(lambda y: h @ y, dt, v.copy())
+        out[f"dt{i}"] = np.array(dt)
+        out[f"res{i}"] = res
+        out[f"j{i}"] = np.array(j)
+    np.savez_compressed(os.path.join(HERE, "krylov.npz"), **out)
+
+
+def gen_davidson():
+    rng = np.random.default_rng(5)
+    n = 300
+    a = rng.standard_normal((n, n)) * 0.05
+    a = (a + a.T) / 2 + np.diag(np.arange(n) * 0.1)
+    hdiag = np.diag(a).copy()
+    out = {"a": a}
+    for nroots in (1, 3):
+        count = [0]
+
+        def hop(x):
+            count[0] += 1
+            return a @ x
+        x0 = [np.eye(n)[:, i] + 0.01 * rng.standard_normal(n) for i in range(nroots)]
+        out[f"x0_{nroots}"] = np.array(x0)
+        precond = lambda x, e, *args: x / (hdiag - e + 1e-4)  # noqa: E731
+        e, c = davidson(hop, [x.copy() for x in x0], precond, max_cycle=100, nroots=nroots,
+                        max_memory=64000)
+        out[f"e_{nroots}"] = np.array(e)
+        out[f"c_{nroots}"] = np.array(c)
+        out[f"nhop_{nroots}"] = np.array(count[0])
+    np.savez_compressed(os.path.join(HERE, "davidson.npz"), **out)
+
+
+def dump_mp(prefix, mp, out):
+    out[prefix + "_n"] = np.array(len(mp))
+    for i, mt in enumerate(mp):
+        out[f"{prefix}_{i}"] = np.asarray(mt.array)
+
+
+def dump_mps_meta(prefix, mps, out):
+    out[prefix + "_qntot"] = np.array(mps.qntot)
+    out[prefix + "_qnidx"] = np.array(mps.qnidx)
+    out[prefix + "_to_right"] = np.array(bool(mps.to_right))
+    for i, q in enumerate(mps.qn):
+        out[f"{prefix}_qn_{i}"] = np.array(q)
+    for i in range(len(mps)):
+        out[f"{prefix}_sigmaqn_{i}"] = np.array(mps._get_sigmaqn(i))
+
+
+def gen_holstein():
+    from renormalizer.mps.gs import construct_mps_mpo, optimize_mps
+    from renormalizer.mps import gs as ref_gs
+    from renormalizer.tests.parameter import holstein_model
+    out = {}
+    procedure = [[10, 0.4], [20, 0.2], [30, 0.1], [40, 0], [40, 0]]
+    np.random.seed(2026)
+    mps, mpo = construct_mps_mpo(holstein_model, procedure[0][0], 1)
+    dump_mp("mpo", mpo, out)
+    dump_mp("mps0", mps, out)
+    dump_mps_meta("mps0", mps, out)
+    out["gs_zpe"] = np.array(holstein_model.gs_zpe)
+    out["procedure"] = np.array(procedure, dtype=float)
+    for method in ("1site", "2site"):
+        m = mps.copy()
+        m.optimize_config.procedure = procedure
+        m.optimize_config.method = method
+        # record every micro iteration energy of every sweep
+        micro = []
+        orig = ref_gs.single_sweep
+
+        def spy(*a, **k):
+            res = orig(*a, **k)
+            micro.append(np.array([e for e, _ in res[0]]))
+            return res
+        ref_gs.single_sweep = spy
+        try:
+            np.random.seed(99)
+            energies, opt = optimize_mps(m, mpo)
+        finally:
+            ref_gs.single_sweep = orig
+        out[f"{method}_energies"] = np.array(energies)
+        for i, mi in enumerate(micro):
+            out[f"{method}_micro_{i}"] = mi
+        out[f"{method}_nsweeps"] = np.array(len(micro))
+        out[f"{method}_expectation"] = np.array(opt.expectation(mpo))
+        dump_mp(f"{method}_opt", opt, out)
+    np.savez_compressed(os.path.join(HERE, "holstein.npz"), **out)
+
+
+def gen_sbm():
+    from renormalizer.model import Phonon, SpinBosonModel
+    from renormalizer.model.op import Op
+    from renormalizer.mps import Mps, Mpo
+    from renormalizer.utils import Quantity, CompressConfig, EvolveConfig, EvolveMethod, \
+        CompressCriteria
+    out = {}
+    nphonons, ph_levels = 6, 4
+    omegas = [0.5, 0.8, 1.0, 1.3, 1.7, 2.2]
+    disp = [1.0, 0.8, 0.6, 0.5, 0.4, 0.3]
+    ph_list = [Phonon.simple_phonon(Quantity(o), Quantity(d), ph_levels)
+               for o, d in zip(omegas, disp)]
+    model = SpinBosonModel(Quantity(0.3), Quantity(1.0), ph_list)
+    mpo = Mpo(model)
+    np.random.seed(4242)
+    mps = Mps.ground_state(model, False)
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=12)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    mps = mps.expand_bond_dimension(mpo, coef=1e-6, include_ex=False)
+    dump_mp("mpo", mpo, out)
+    dump_mp("mps0", mps, out)
+    dump_mps_meta("mps0", mps, out)
+    out["mps0_coeff"] = np.array(mps.coeff)
+    sigma_z = Mpo(model, Op("sigma_z", "spin"))
+    dump_mp("sigma_z", sigma_z, out)
+    dt = 0.05
+    nsteps = 6
+    sz = [mps.expectation(sigma_z)]
+    energy = [mps.expectation(mpo)]
+    for i in range(nsteps):
+        mps = mps.evolve(mpo, dt)
+        sz.append(mps.expectation(sigma_z))
+        energy.append(mps.expectation(mpo))
+        if i == 0:
+            dump_mp("mps1", mps, out)
+    out["dt"] = np.array(dt)
+    out["nsteps"] = np.array(nsteps)
+    out["sigma_z_t"] = np.array(sz)
+    out["energy_t"] = np.array(energy)
+    dump_mp("mpsT", mps, out)
+    out["mpsT_coeff"] = np.array(mps.coeff)
+    out["mpsT_qnidx"] = np.array(mps.qnidx)
+    out["mpsT_to_right"] = np.array(bool(mps.to_right))
+    np.savez_compressed(os.path.join(HERE, "sbm.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm"]
+    for name in which:
+        print("generating", name, flush=True)
+        globals()["gen_" + name]()
+    print("done")

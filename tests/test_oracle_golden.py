@@ -1,0 +1,135 @@
+"""Pin the CPU oracle against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import contract, svdqn
+from oracle.krylov import expm_krylov
+from oracle.davidson import davidson
+from oracle.sweep import optimize_mps, evolve_tdvp_ps
+from helpers import load_mpo, load_oracle_mps, relerr
+
+TOL = 1e-13
+
+
+@pytest.mark.parametrize("t", ["r", "c"])
+def test_hop_and_env(golden, t):
+    g = golden("kernels")
+    L, R, R1, R0, W1, W2 = (g[f"{t}_{k}"] for k in ("L", "R", "R1", "R0", "W1", "W2"))
+    assert relerr(contract.hop_apply(L, R0, [], g[f"{t}_C0"]), g[f"{t}_hop0"]) < TOL
+    assert relerr(contract.hop_apply(L, R1, [W1], g[f"{t}_C1"]), g[f"{t}_hop1"]) < TOL
+    assert relerr(contract.hop_apply(L, R, [W1, W2], g[f"{t}_C2"]), g[f"{t}_hop2"]) < TOL
+    assert relerr(contract.hop_apply(L, R1, [W1], g[f"{t}_C1a"]), g[f"{t}_hop1a"]) < TOL
+    assert relerr(contract.hop_apply(L, R, [W1, W2], g[f"{t}_C2a"]), g[f"{t}_hop2a"]) < TOL
+    assert relerr(contract.env_update(L, g[f"{t}_A3"], W1, "L"), g[f"{t}_envL3"]) < TOL
+    assert relerr(contract.env_update(L, g[f"{t}_A4"], W1, "L"), g[f"{t}_envL4"]) < TOL
+    assert relerr(contract.env_update(R1, g[f"{t}_A3"], W1, "R"), g[f"{t}_envR3"]) < TOL
+    assert relerr(contract.env_update(R1, g[f"{t}_A4"], W1, "R"), g[f"{t}_envR4"]) < TOL
+
+
+def test_hop_diag_matches_dense_diagonal(golden):
+    g = golden("kernels")
+    L, R1, R, W1, W2 = g["r_L"], g["r_R1"], g["r_R"], g["r_W1"], g["r_W2"]
+    dense = np.einsum("abc,bdef,lfk->adlcek", L, W1, R1)
+    n = dense.shape[0] * dense.shape[1] * dense.shape[2]
+    assert relerr(contract.hop_diag(L, R1, [W1]).ravel(), np.diag(dense.reshape(n, n))) < TOL
+    dense = np.einsum("abc,bdef,fghj,ljk->adglcehk", L, W1, W2, R)
+    n = int(np.prod(dense.shape[:4]))
+    assert relerr(contract.hop_diag(L, R, [W1, W2]).ravel(), np.diag(dense.reshape(n, n))) < TOL
+
+
+@pytest.mark.parametrize("t", ["r", "c"])
+@pytest.mark.parametrize("system", ["L", "R"])
+def test_svd_qn(golden, t, system):
+    g = golden("svdqn")
+    k = f"{t}_{system}"
+    c, ql, qr, qntot = g[k + "_c"], g[k + "_qnbigl"], g[k + "_qnbigr"], g["qntot"]
+    u, su, qnl, v, sv, qnr = svdqn.svd_qn(c, ql, qr, qntot, system=system, full_matrices=False)
+    assert relerr(su, g[k + "_svd_s"]) < TOL
+    assert relerr(u, g[k + "_svd_u"]) < 1e-10 and relerr(v, g[k + "_svd_v"]) < 1e-10
+    assert np.array_equal(np.array(qnl), g[k + "_svd_qnl"])
+    assert np.array_equal(np.array(qnr), g[k + "_svd_qnr"])
+    np.random.seed(11)
+    u, su, qnl, v, sv, qnr = svdqn.svd_qn(c, ql, qr, qntot, system=system, full_matrices=True)
+    assert u.shape == g[k + "_fsvd_u"].shape
+    assert relerr(u, g[k + "_fsvd_u"]) < 1e-10 and relerr(v, g[k + "_fsvd_v"]) < 1e-10
+    assert relerr(su, g[k + "_fsvd_su"]) < TOL and relerr(sv, g[k + "_fsvd_sv"]) < TOL
+    assert np.array_equal(np.array(qnl), g[k + "_fsvd_qnl"])
+    u, qnl, v, qnr = svdqn.svd_qn(c, ql, qr, qntot, QR=True, system=system, full_matrices=False)
+    assert relerr(u, g[k + "_qr_u"]) < 1e-12 and relerr(v, g[k + "_qr_v"]) < 1e-12
+    assert np.array_equal(np.array(qnl), g[k + "_qr_qnl"])
+    assert np.array_equal(np.array(qnr), g[k + "_qr_qnr"])
+
+
+def test_svd_qn_invalid_qn_raises():
+    c = np.ones((2, 2, 2))
+    qnl = np.zeros((2, 1), dtype=int)
+    sig = np.zeros((2, 1), dtype=int)
+    with pytest.raises(ValueError):
+        svdqn.svd_qn(c, svdqn.add_outer(qnl, sig), qnl, np.array([5]), system="L")
+
+
+def test_expm_krylov(golden):
+    g = golden("krylov")
+    h, v = g["h"], g["v"]
+    for i in range(3):
+        res, j = expm_krylov(lambda y: h @ y, complex(g[f"dt{i}"]), v.copy())
+        assert j == int(g[f"j{i}"])
+        assert relerr(res, g[f"res{i}"]) < TOL
+
+
+@pytest.mark.parametrize("nroots", [1, 3])
+def test_davidson(golden, nroots):
+    g = golden("davidson")
+    a = g["a"]
+    hd = np.diag(a).copy()
+    count = [0]
+
+    def hop(x):
+        count[0] += 1
+        return a @ x
+    e, c = davidson(hop, [x.copy() for x in g[f"x0_{nroots}"]],
+                    lambda x, e, *args: x / (hd - e + 1e-4), max_cycle=100, nroots=nroots)
+    assert count[0] == int(g[f"nhop_{nroots}"])
+    assert np.abs(np.array(e) - g[f"e_{nroots}"]).max() < 1e-13
+    assert np.abs(np.array(c) - g[f"c_{nroots}"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_dmrg_holstein_trajectory(golden, method):
+    """Whole optimize_mps trajectory: every micro-iteration energy of every sweep."""
+    g = golden("holstein")
+    mpo = load_mpo(g)
+    mps = load_oracle_mps(g, "mps0")
+    np.random.seed(99)
+    micro = []
+    proc = [(int(a), float(b)) for a, b in g["procedure"]]
+    e, opt = optimize_mps(mps, mpo, proc, method=method, micro_out=micro)
+    assert len(e) == len(g[f"{method}_energies"])
+    assert np.abs(np.array(e) - g[f"{method}_energies"]).max() < 1e-12
+    for i, m in enumerate(micro):
+        assert np.abs(m - g[f"{method}_micro_{i}"]).max() < 1e-12
+    assert abs(opt.expectation(mpo) - float(g[f"{method}_expectation"])) < 1e-12
+    # the reference's own acceptance value (mps/tests/test_gs.py:22,36)
+    assert e[-1] == pytest.approx(0.08401412 + float(g["gs_zpe"]), rel=1e-5)
+
+
+def test_tdvp_ps_spin_boson(golden):
+    g = golden("sbm")
+    mpo = load_mpo(g)
+    sz = load_mpo(g, "sigma_z")
+    mps = load_oracle_mps(g, "mps0")
+    dt = float(g["dt"])
+    szs, es = [mps.expectation(sz)], [mps.expectation(mpo)]
+    for i in range(int(g["nsteps"])):
+        mps = evolve_tdvp_ps(mps, mpo, dt)
+        szs.append(mps.expectation(sz))
+        es.append(mps.expectation(mpo))
+        if i == 0:
+            ref1 = load_oracle_mps(g, "mps1")
+            # same physical state (site tensors differ by a gauge on rank-deficient bonds)
+            assert abs(abs(ref1.dot_conj(mps)) - 1) < 1e-12
+    assert np.abs(np.array(szs) - g["sigma_z_t"]).max() < 1e-11
+    assert np.abs(np.array(es) - g["energy_t"]).max() < 1e-12
+    refT = load_oracle_mps(g, "mpsT")
+    assert abs(abs(refT.dot_conj(mps)) - 1) < 1e-11
