@@ -1,0 +1,125 @@
+/* rn_b200.h -- C ABI of librn_b200.so: the B200 (sm_100a) sweep-site kernels behind
+ * renormalizer.mps.backend.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream handle (cudaStream_t
+ * passed as void*); none takes or returns a torch / cupy type.  All functions return 0 on
+ * success or a cudaError_t value.  Tensors are dense, row-major (C order); a complex128 tensor is
+ * the usual interleaved (re, im) pair of doubles.  `cplx` = 0 -> float64, 1 -> complex128.
+ *
+ * Each function names the reference interface it replaces (path:line in shuaigroup/Renormalizer).
+ */
+#ifndef RN_B200_H
+#define RN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* number of partial sums a reduction workspace must hold per vector: ws needs
+ * 2 * RN_REDUCE_BLOCKS * nvec doubles */
+#define RN_REDUCE_BLOCKS 296
+
+/* Library / device bring-up; returns the SM count in *sm_count and the compute capability in
+ * *cc (e.g. 100).  Fails (non-zero) when the device is not an sm_100 part. */
+int rn_init(int device, int* sm_count, int* cc);
+/* Version string of the library ("rn_b200 <n>"), for the loader's self check. */
+const char* rn_version(void);
+
+/* ---- contraction primitives ----------------------------------------------------------------
+ * xp.tensordot (renormalizer/mps/matrix.py:210) lowered to one K-major real GEMM:
+ *   C[i*ldc + j] (+)= sum_k A[i*lda + k] * B[j*ldb + k]
+ * batch > 1 runs independent problems at the given element strides. */
+int rn_dgemm_tn(void* stream, int m, int n, int k, const double* A, long lda, const double* B,
+                long ldb, double* C, long ldc, int accumulate, int batch, long strideA,
+                long strideB, long strideC);
+
+/* Strided view -> K-major GEMM operand.  Element (r, c) of the source is src[r*s_row + c*s_col]
+ * (strides in elements).  mode 0 ("A-form"): dst[r*dst_ld + c] (complex: interleaved, conj_flag
+ * conjugates).  mode 1 ("B-form", complex only): 2x2 real representation, rows (2r, 2r+1), so a
+ * complex product is a single real GEMM; conj_flag folds a conjugation of the LEFT operand in.
+ * dst_ld is in doubles. */
+int rn_pack(void* stream, int cplx, int mode, int conj_flag, int rows, int cols, const void* src,
+            long s_row, long s_col, double* dst, long dst_ld);
+
+/* MPO-site application  out[x,d,y1,f,y2] = sum_{p,q} W[p,d,q,f] in[x,p,q,y],  y = y1*Y2 + y2.
+ * W in CSR over the output pair (d*F + f): rowptr[D*F+1], ent_pq[e] = p*Q + q, ent_val[e].
+ * All strides in elements.  (Middle step of hop_expr.py:75-115 and lib.py:214-258.) */
+int rn_wapply(void* stream, int cplx, const void* in, void* out, int X, int P, int Q, int Y,
+              long isx, long isp, long isq, long isy, int D, int F, int Y2, long osx, long osd,
+              long osf, long osy1, long osy2, const int* rowptr, const int* ent_pq,
+              const double* ent_val);
+
+/* ---- H_eff * C -----------------------------------------------------------------------------
+ * Replaces renormalizer/mps/hop_expr.py:7 hop_expr(ltensor, rtensor, cmo, cshape) -> expr and the
+ * returned expr(cstruct).  L is (La,Lb,Lc) = (bra, MPO, ket) bonds, R is (Rl,Rf,Rk); nsite = 0,
+ * 1, 2 centre sites with physical dims d1,d2 and ancilla dims g1,g2 (1 when the state is an MPS,
+ * >1 for an MPDM; hop_expr.py:80-91,104-115).  MPO site i is passed as CSR of W_i[p=left bond,
+ * D=up, q=down, F=right bond].  L, R and the CSR arrays must stay alive while the plan lives.
+ * path: 0 = FP64 DMMA GEMM, 1 = tcgen05 int8 split GEMM (FP64-accurate), see DESIGN.md. */
+typedef struct rn_hop_plan rn_hop_plan;
+int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int nsite, const void* L,
+                       int La, int Lb, int Lc, const void* R, int Rl, int Rf, int Rk, int d1,
+                       int g1, int d2, int g2, int w1_F, const int* w1_rowptr, const int* w1_pq,
+                       const double* w1_val, int w2_F, const int* w2_rowptr, const int* w2_pq,
+                       const double* w2_val, int path);
+/* out = H_eff . c_in ; c_in (Lc, d1[,g1][,d2[,g2]], Rk), out (La, ..., Rl). */
+int rn_hop_apply(rn_hop_plan* plan, void* stream, const void* c_in, void* out);
+/* kernels launched through this plan so far (for bench.py's gpu_launches) */
+long rn_hop_plan_launches(const rn_hop_plan* plan);
+int rn_hop_plan_destroy(rn_hop_plan* plan, void* stream);
+
+/* ---- environment update --------------------------------------------------------------------
+ * Replaces renormalizer/mps/lib.py:172 contract_one_site(environ, ms, mo, domain, ms_conj).
+ * domain 0 = "L": env (Ea,Eb,Ec), bra (Ea,d,g,Mf), ket (Ec,d,g,Mh), W CSR as for hop.
+ * domain 1 = "R": env (Ea,Eb,Ec), bra (Mf,d,g,Ea), ket (Mh,d,g,Ec), W CSR of
+ *                 W'[p=right bond, D=up, q=down, F=left bond].
+ * bra is the UN-conjugated bra-side site (== ket for an expectation value); out is (Mf,F,Mh). */
+int rn_env_update(void* stream, int cplx, int domain, const void* env, int Ea, int Eb, int Ec,
+                  const void* bra, const void* ket, int d, int g, int Mf, int Mh, int F,
+                  const int* rowptr, const int* pq, const double* val, void* out, int path);
+
+/* ---- bond decomposition --------------------------------------------------------------------
+ * Replace the per-block scipy.linalg.qr / rq / svd calls of renormalizer/mps/svd_qn.py:170-186
+ * (and optimized_svd, svd_qn.py:13-49).  A is (m x n) row-major with leading dimension lda (in
+ * elements); k = min(m, n).
+ *   rn_qr : A = Q R,  Q (m x k) orthonormal columns, R (k x n) upper trapezoidal (LAPACK signs)
+ *   rn_lq : A = L Q,  L (m x k) lower trapezoidal,   Q (k x n) orthonormal rows
+ *   rn_svd_jacobi : A = U diag(S) Vh, U (m x k), Vh (k x n); S is NOT sorted; *sweeps_out (host
+ *                   int, may be NULL) receives the number of Jacobi sweeps. */
+int rn_qr(void* stream, int cplx, int m, int n, const void* A, long lda, void* Q, long ldq,
+          void* R, long ldr);
+int rn_lq(void* stream, int cplx, int m, int n, const void* A, long lda, void* L, long ldl,
+          void* Q, long ldq);
+int rn_svd_jacobi(void* stream, int cplx, int m, int n, const void* A, long lda, void* U,
+                  long ldu, double* S, void* Vh, long ldvh, int max_sweeps, int* sweeps_out);
+
+/* ---- Krylov / Davidson vector kernels -------------------------------------------------------
+ * (renormalizer/lib/krylov/krylov.py:55-83, renormalizer/lib/davidson/davidson.py:56-70,493-500)
+ * n counts elements, nd counts doubles (2n for complex).  Scalars stay on the device.
+ *   rn_multi_dot     out[2i..2i+1] = <V_i, x> = sum conj(V[i*ld+k]) x[k]   (ld in doubles)
+ *   rn_lanczos_update w -= alpha[0]*vj + beta_prev[0]*vjm1 ; beta_out[0] = |w|   (vjm1 may be NULL)
+ *   rn_scale_inv     out = x / s[0]
+ *   rn_lincomb       out = sum_i coef[i] V_i          (coef complex when cplx) */
+int rn_multi_dot(void* stream, int cplx, long n, int nvec, const double* V, long ld,
+                 const double* x, double* ws, double* out);
+int rn_lanczos_update(void* stream, long nd, double* w, const double* vj, const double* vjm1,
+                      const double* alpha, const double* beta_prev, double* ws, double* beta_out);
+int rn_scale_inv(void* stream, long nd, const double* x, const double* s, double* out);
+int rn_lincomb(void* stream, int cplx, long n, int nvec, const double* V, long ld,
+               const double* coef, double* out);
+
+/* ---- host-buffer entry points (what a NumPy-side caller binds) -------------------------------
+ * Same contractions with HOST pointers: inputs are copied to the device, the kernels above run,
+ * the result is copied back and the stream is synchronised.  W is the dense MPO site(s)
+ * (Wb, d, d, Wf), real.  Shapes as for the device entry points. */
+int rn_hop_apply_host(int cplx, int nsite, const void* L, int La, int Lb, int Lc, const void* R,
+                      int Rl, int Rf, int Rk, int d1, int g1, int d2, int g2, const double* W1,
+                      int w1_F, const double* W2, int w2_F, const void* c_in, void* out, int path);
+int rn_env_update_host(int cplx, int domain, const void* env, int Ea, int Eb, int Ec,
+                       const void* bra, const void* ket, int d, int g, int Mf, int Mh,
+                       const double* W, int Wb, int Wf, void* out, int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RN_B200_H */

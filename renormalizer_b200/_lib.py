@@ -1,0 +1,105 @@
+"""ctypes binding of librn_b200.so (the C ABI declared in include/rn_b200.h).
+
+The product path has NO fallback: if the shared library is missing or the device is not an
+sm_100 part, every compute entry point raises.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_long, c_void_p, c_char_p, POINTER, c_double
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librn_b200.so")
+
+_lib = None
+_inited_devices = {}
+
+_vp, _i, _l = c_void_p, c_int, c_long
+
+# name -> (restype, argtypes); must list every symbol declared in include/rn_b200.h
+SIGNATURES = {
+    "rn_init": (_i, [_i, POINTER(_i), POINTER(_i)]),
+    "rn_version": (c_char_p, []),
+    "rn_dgemm_tn": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _l, _i, _i, _l, _l, _l]),
+    "rn_pack": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _l, _l, _vp, _l]),
+    "rn_wapply": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _l, _l, _l, _l, _i, _i, _i,
+                       _l, _l, _l, _l, _l, _vp, _vp, _vp]),
+    "rn_hop_plan_create": (_i, [POINTER(_vp), _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i,
+                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i]),
+    "rn_hop_apply": (_i, [_vp, _vp, _vp, _vp]),
+    "rn_hop_plan_launches": (_l, [_vp]),
+    "rn_hop_plan_destroy": (_i, [_vp, _vp]),
+    "rn_env_update": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i,
+                           _vp, _vp, _vp, _vp, _i]),
+    "rn_qr": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _l]),
+    "rn_lq": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _l]),
+    "rn_svd_jacobi": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _vp, _l, _i, POINTER(_i)]),
+    "rn_multi_dot": (_i, [_vp, _i, _l, _i, _vp, _l, _vp, _vp, _vp]),
+    "rn_lanczos_update": (_i, [_vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rn_scale_inv": (_i, [_vp, _l, _vp, _vp, _vp]),
+    "rn_lincomb": (_i, [_vp, _i, _l, _i, _vp, _l, _vp, _vp]),
+    "rn_hop_apply_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
+                               _vp, _i, _vp, _i, _vp, _vp, _i]),
+    "rn_env_update_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i,
+                                _vp, _i, _i, _vp, _i]),
+}
+
+REDUCE_BLOCKS = 296
+
+
+class RnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library and bind every symbol (no GPU needed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RnError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  renormalizer_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def get(device_index=None):
+    """Library handle, initialised for the given (default: current) CUDA device."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RnError("renormalizer_b200 needs a CUDA device (B200, sm_100a); none is available "
+                      "and there is no CPU fallback")
+    lib = load()
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    if device_index not in _inited_devices:
+        sm, cc = c_int(0), c_int(0)
+        err = lib.rn_init(device_index, ctypes.byref(sm), ctypes.byref(cc))
+        if err:
+            raise RnError(f"rn_init failed on device {device_index} (cuda error {err})")
+        _inited_devices[device_index] = (sm.value, cc.value)
+    return lib
+
+
+def check(err, what):
+    if err:
+        raise RnError(f"{what} failed with CUDA error {err}")
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class LaunchCounter:
+    """Counts kernels launched through the C ABI (bench.py reports it as gpu_launches)."""
+    count = 0
+
+    @classmethod
+    def add(cls, n):
+        cls.count += n

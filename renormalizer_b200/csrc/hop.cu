@@ -1,0 +1,270 @@
+// H_eff * C plans and the environment update: the two contraction hot paths of a sweep site,
+// lowered onto {pack, GEMM, MPO-apply, GEMM}.
+//
+//   hop (reference renormalizer/mps/hop_expr.py:7-117)
+//     0 site : out[a,l]        = L[a,b,c] R[l,b,k] C[c,k]
+//     1 site : out[a,d,(g),l]  = L[a,b,c] W[b,d,e,f] R[l,f,k] C[c,e,(g),k]
+//     2 sites: out[a,d,(m),g,(n),l] = L[a,b,c] W1[b,d,e,f] W2[f,g,h,j] R[l,j,k] C[c,e,(m),h,(n),k]
+//   as   G1: T1[(a,b),(rest)] = L[(a,b),c] . C[c,(rest)]          (GEMM, K = |c|)
+//        W : T2 = W1 applied on (b,e)  [, T3 = W2 applied on (f,h)] (HBM-bound, wapply.cu)
+//        G3: out[(a,d..),l]   = T[(a,d..),(f,k)] . R[l,(f,k)]      (GEMM, K = |f||k|)
+//   env update (reference renormalizer/mps/lib.py:172-262, contract_one_site) reuses G1 + W and
+//   finishes with the bra-site GEMM.
+//
+// Complex tensors are contracted with REAL GEMMs: the left operand is used through its
+// interleaved real view and the right operand is packed once into its 2x2 real representation
+// (pack.cu, B-form).  L and R are constant over all Krylov / Davidson iterations of a site, so
+// their packed forms live in the plan.
+#include "common.cuh"
+#include "rn_b200.h"
+#include "internal.cuh"
+
+#include <new>
+
+namespace rn {
+
+struct WCsr {
+  int P = 0, Q = 0, D = 0, F = 0;
+  const int* rowptr = nullptr;
+  const int* pq = nullptr;
+  const double* val = nullptr;
+};
+
+static int gemm_dispatch(cudaStream_t st, int path, int m, int n, int k, const double* A, long lda,
+                         const double* B, long ldb, double* C, long ldc) {
+  (void)path;
+  return launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+struct rn_hop_plan {
+  int cplx, es, nsite, path;
+  int La, Lb, Lc, Rl, Rf, Rk;
+  int d1, g1, d2, g2;
+  WCsr w1, w2;
+  const double* L;    // caller-owned, (La*Lb) x (Lc*es)
+  double* Rb;         // packed right operand of G3: (Rl*es) x (Rf*Rk*es); == R for real dtype
+  bool own_Rb;
+  double *Cb, *T1, *T2, *T3;
+  long rest;          // product of the centre indices between c and k (physical and ancilla)
+  long launches;
+};
+
+extern "C" int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int nsite,
+                                  const void* L, int La, int Lb, int Lc, const void* R, int Rl,
+                                  int Rf, int Rk, int d1, int g1, int d2, int g2, int w1_F,
+                                  const int* w1_rowptr, const int* w1_pq, const double* w1_val,
+                                  int w2_F, const int* w2_rowptr, const int* w2_pq,
+                                  const double* w2_val, int path) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nsite < 0 || nsite > 2) return (int)cudaErrorInvalidValue;
+  rn_hop_plan* p = new (std::nothrow) rn_hop_plan();
+  if (!p) return (int)cudaErrorMemoryAllocation;
+  p->cplx = cplx; p->es = cplx ? 2 : 1; p->nsite = nsite; p->path = path;
+  p->La = La; p->Lb = Lb; p->Lc = Lc; p->Rl = Rl; p->Rf = Rf; p->Rk = Rk;
+  p->d1 = nsite >= 1 ? d1 : 1; p->g1 = nsite >= 1 ? g1 : 1;
+  p->d2 = nsite >= 2 ? d2 : 1; p->g2 = nsite >= 2 ? g2 : 1;
+  p->L = (const double*)L;
+  p->launches = 0;
+  const int es = p->es;
+  if (nsite >= 1) {
+    p->w1.P = Lb; p->w1.Q = p->d1; p->w1.D = p->d1; p->w1.F = w1_F;
+    p->w1.rowptr = w1_rowptr; p->w1.pq = w1_pq; p->w1.val = w1_val;
+  }
+  if (nsite == 2) {
+    p->w2.P = w1_F; p->w2.Q = p->d2; p->w2.D = p->d2; p->w2.F = w2_F;
+    p->w2.rowptr = w2_rowptr; p->w2.pq = w2_pq; p->w2.val = w2_val;
+  }
+  const int wlast = nsite == 0 ? Lb : (nsite == 1 ? w1_F : w2_F);
+  if (wlast != Rf) { delete p; return (int)cudaErrorInvalidValue; }
+  p->rest = (long)p->d1 * p->g1 * p->d2 * p->g2;
+  const long n1 = p->rest * Rk;  // columns of T1 (elements)
+  p->Cb = p->T1 = p->T2 = p->T3 = nullptr;
+  RN_CHECK(cudaMallocAsync((void**)&p->T1, sizeof(double) * es * (size_t)La * Lb * n1, st));
+  if (cplx) {
+    RN_CHECK(cudaMallocAsync((void**)&p->Cb, sizeof(double) * 4 * (size_t)n1 * Lc, st));
+    RN_CHECK(cudaMallocAsync((void**)&p->Rb, sizeof(double) * 4 * (size_t)Rl * Rf * Rk, st));
+    p->own_Rb = true;
+    int err = launch_pack(st, 1, 1, 0, Rl, Rf * Rk, R, (long)Rf * Rk, 1, p->Rb, (long)Rf * Rk * 2);
+    if (err) return err;
+  } else {
+    // real: "math B"[c,(rest,k)] still has to be transposed to K-major for G1
+    RN_CHECK(cudaMallocAsync((void**)&p->Cb, sizeof(double) * (size_t)n1 * Lc, st));
+    p->Rb = (double*)R;
+    p->own_Rb = false;
+  }
+  if (nsite >= 1)
+    RN_CHECK(cudaMallocAsync((void**)&p->T2, sizeof(double) * es * (size_t)La * p->d1 * p->g1 * w1_F * p->d2 * p->g2 * Rk, st));
+  if (nsite == 2)
+    RN_CHECK(cudaMallocAsync((void**)&p->T3, sizeof(double) * es * (size_t)La * p->d1 * p->g1 * p->d2 * p->g2 * w2_F * Rk, st));
+  *out = p;
+  return 0;
+}
+
+extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void* out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int es = p->es, cplx = p->cplx;
+  const long n1 = p->rest * p->Rk;
+  int err;
+  // "math B"[c, (rest,k)] -> K-major (and realified when complex)
+  err = launch_pack(st, cplx, cplx ? 1 : 0, 0, (int)n1, p->Lc, c_in, 1, n1, p->Cb, (long)p->Lc * es);
+  if (err) return err;
+  // G1: T1[(a,b), (rest,k)]
+  err = gemm_dispatch(st, p->path, p->La * p->Lb, (int)(n1 * es), p->Lc * es, p->L, (long)p->Lc * es,
+                      p->Cb, (long)p->Lc * es, p->T1, n1 * es);
+  if (err) return err;
+  const double* lastT = p->T1;
+  long rows3 = p->La;           // rows of the G3 left operand
+  p->launches += 2;
+  if (p->nsite >= 1) {
+    WApplyParams w;
+    const long Yin = (long)p->g1 * p->d2 * p->g2 * p->Rk;   // y = (g1, h, g2, k)
+    const long Y2 = (long)p->d2 * p->g2 * p->Rk;
+    w.in = p->T1; w.out = p->T2;
+    w.X = p->La; w.P = p->w1.P; w.Q = p->w1.Q; w.Y = (int)Yin;
+    w.isx = (long)p->w1.P * p->w1.Q * Yin; w.isp = (long)p->w1.Q * Yin; w.isq = Yin; w.isy = 1;
+    w.D = p->w1.D; w.F = p->w1.F; w.Y2 = (int)Y2;
+    w.osx = (long)p->d1 * p->g1 * p->w1.F * Y2; w.osd = (long)p->g1 * p->w1.F * Y2;
+    w.osy1 = (long)p->w1.F * Y2; w.osf = Y2; w.osy2 = 1;
+    w.rowptr = p->w1.rowptr; w.ent_pq = p->w1.pq; w.ent_val = p->w1.val; w.YT = 0; w.order = 0;
+    err = launch_wapply(st, cplx, w);
+    if (err) return err;
+    lastT = p->T2;
+    rows3 = (long)p->La * p->d1 * p->g1;
+    p->launches += 1;
+  }
+  if (p->nsite == 2) {
+    WApplyParams w;
+    const long Yin = (long)p->g2 * p->Rk;   // y = (g2, k)
+    w.in = p->T2; w.out = p->T3;
+    w.X = (int)((long)p->La * p->d1 * p->g1); w.P = p->w2.P; w.Q = p->w2.Q; w.Y = (int)Yin;
+    w.isx = (long)p->w2.P * p->w2.Q * Yin; w.isp = (long)p->w2.Q * Yin; w.isq = Yin; w.isy = 1;
+    w.D = p->w2.D; w.F = p->w2.F; w.Y2 = p->Rk;
+    w.osx = (long)p->d2 * p->g2 * p->w2.F * p->Rk; w.osd = (long)p->g2 * p->w2.F * p->Rk;
+    w.osy1 = (long)p->w2.F * p->Rk; w.osf = p->Rk; w.osy2 = 1;
+    w.rowptr = p->w2.rowptr; w.ent_pq = p->w2.pq; w.ent_val = p->w2.val; w.YT = 0; w.order = 0;
+    err = launch_wapply(st, cplx, w);
+    if (err) return err;
+    lastT = p->T3;
+    rows3 = (long)p->La * p->d1 * p->g1 * p->d2 * p->g2;
+    p->launches += 1;
+  }
+  // G3: out[(rows3), l] = T[(rows3), (f,k)] . R[l, (f,k)]
+  const long K3 = (long)p->Rf * p->Rk * es;
+  err = gemm_dispatch(st, p->path, (int)rows3, p->Rl * es, (int)K3, lastT, K3, p->Rb, K3,
+                      (double*)out, (long)p->Rl * es);
+  p->launches += 1;
+  return err;
+}
+
+extern "C" long rn_hop_plan_launches(const rn_hop_plan* p) { return p ? p->launches : 0; }
+
+extern "C" int rn_hop_plan_destroy(rn_hop_plan* p, void* stream) {
+  if (!p) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->Cb) cudaFreeAsync(p->Cb, st);
+  if (p->T1) cudaFreeAsync(p->T1, st);
+  if (p->T2) cudaFreeAsync(p->T2, st);
+  if (p->T3) cudaFreeAsync(p->T3, st);
+  if (p->own_Rb && p->Rb) cudaFreeAsync(p->Rb, st);
+  delete p;
+  return 0;
+}
+
+// Environment update.  domain 0 ("L"): env (Ea,Eb,Ec), bra (Ea,d,g,Mf), ket (Ec,d,g,Mh);
+// domain 1 ("R"): env (Ea,Eb,Ec), bra (Mf,d,g,Ea), ket (Mh,d,g,Ec).  out (Mf, F, Mh).
+// `bra` is the UN-conjugated bra-side site tensor (conjugated inside); W is CSR in the
+// orientation documented in rn_b200.h.
+extern "C" int rn_env_update(void* stream, int cplx, int domain, const void* env, int Ea, int Eb,
+                             int Ec, const void* bra, const void* ket, int d, int g, int Mf,
+                             int Mh, int F, const int* rowptr, const int* pq, const double* val,
+                             void* out, int path) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int es = cplx ? 2 : 1;
+  int err;
+  double *B1 = nullptr, *X1 = nullptr, *Y = nullptr, *A3 = nullptr, *B3 = nullptr;
+  const long dg = (long)d * g;
+  if (domain == 0) {
+    // G1: X1[(a,b),(e,l,h)] = env[(a,b),c] . ket[c,(e,l,h)]
+    const long n1 = dg * Mh;
+    RN_CHECK(cudaMallocAsync((void**)&B1, sizeof(double) * es * es * (size_t)n1 * Ec, st));
+    RN_CHECK(cudaMallocAsync((void**)&X1, sizeof(double) * es * (size_t)Ea * Eb * n1, st));
+    err = launch_pack(st, cplx, cplx ? 1 : 0, 0, (int)n1, Ec, ket, 1, n1, B1, (long)Ec * es);
+    if (err) return err;
+    err = gemm_dispatch(st, path, Ea * Eb, (int)(n1 * es), Ec * es, (const double*)env, (long)Ec * es,
+                        B1, (long)Ec * es, X1, n1 * es);
+    if (err) return err;
+    // W: Y[a, d, l, f, h] = W[b,d,e,f] X1[a,b,e,(l,h)]
+    RN_CHECK(cudaMallocAsync((void**)&Y, sizeof(double) * es * (size_t)Ea * dg * F * Mh, st));
+    WApplyParams w;
+    const long Yin = (long)g * Mh;
+    w.in = X1; w.out = Y; w.X = Ea; w.P = Eb; w.Q = d; w.Y = (int)Yin;
+    w.isx = (long)Eb * d * Yin; w.isp = (long)d * Yin; w.isq = Yin; w.isy = 1;
+    w.D = d; w.F = F; w.Y2 = Mh;
+    w.osx = dg * F * Mh; w.osd = (long)g * F * Mh; w.osy1 = (long)F * Mh; w.osf = Mh; w.osy2 = 1;
+    w.rowptr = rowptr; w.ent_pq = pq; w.ent_val = val; w.YT = 0; w.order = 0;
+    err = launch_wapply(st, cplx, w);
+    if (err) return err;
+    // G3: out[f,(g,h)] = sum_(a,d,l) conj(bra)[(a,d,l),f] . Y[(a,d,l),(g,h)]
+    const long K3 = (long)Ea * dg;
+    RN_CHECK(cudaMallocAsync((void**)&A3, sizeof(double) * es * (size_t)Mf * K3, st));
+    RN_CHECK(cudaMallocAsync((void**)&B3, sizeof(double) * es * es * (size_t)F * Mh * K3, st));
+    err = launch_pack(st, cplx, 0, cplx ? 1 : 0, Mf, (int)K3, bra, 1, Mf, A3, K3 * es);
+    if (err) return err;
+    err = launch_pack(st, cplx, cplx ? 1 : 0, 0, F * Mh, (int)K3, Y, 1, (long)F * Mh, B3, K3 * es);
+    if (err) return err;
+    err = gemm_dispatch(st, path, Mf, F * Mh * es, (int)(K3 * es), A3, K3 * es, B3, K3 * es,
+                        (double*)out, (long)F * Mh * es);
+    if (err) return err;
+  } else {
+    // G1: X1[(h,e,l),(a,b)] = ket[(h,e,l),c] . env[(a,b),c]
+    const long m1 = (long)Mh * dg, n1 = (long)Ea * Eb;
+    RN_CHECK(cudaMallocAsync((void**)&X1, sizeof(double) * es * (size_t)m1 * n1, st));
+    const double* Bop = (const double*)env;
+    if (cplx) {
+      RN_CHECK(cudaMallocAsync((void**)&B1, sizeof(double) * 4 * (size_t)n1 * Ec, st));
+      err = launch_pack(st, 1, 1, 0, (int)n1, Ec, env, Ec, 1, B1, (long)Ec * 2);
+      if (err) return err;
+      Bop = B1;
+    }
+    err = gemm_dispatch(st, path, (int)m1, (int)(n1 * es), Ec * es, (const double*)ket, (long)Ec * es,
+                        Bop, (long)Ec * es, X1, n1 * es);
+    if (err) return err;
+    // W: Yt[f, h, d, (l,a)] = W'[p=b, D=d, q=e, F=f] X1[h, e, (l,a), b]
+    const long K3 = dg * Ea;
+    RN_CHECK(cudaMallocAsync((void**)&Y, sizeof(double) * es * (size_t)F * Mh * K3, st));
+    WApplyParams w;
+    const long Yin = (long)g * Ea;
+    w.in = X1; w.out = Y; w.X = Mh; w.P = Eb; w.Q = d; w.Y = (int)Yin;
+    w.isx = (long)d * Yin * Eb; w.isq = Yin * Eb; w.isy = Eb; w.isp = 1;
+    w.D = d; w.F = F; w.Y2 = (int)Yin;
+    w.osf = (long)Mh * K3; w.osx = K3; w.osd = Yin; w.osy1 = 0; w.osy2 = 1;
+    w.rowptr = rowptr; w.ent_pq = pq; w.ent_val = val; w.YT = 0; w.order = 0;
+    err = launch_wapply(st, cplx, w);
+    if (err) return err;
+    // G3: out[f,(g,h)] = sum_(d,l,a) conj(bra)[f,(d,l,a)] . Yt[(g,h),(d,l,a)]
+    const double* Aop = (const double*)bra;
+    const double* B3op = Y;
+    if (cplx) {
+      RN_CHECK(cudaMallocAsync((void**)&A3, sizeof(double) * 2 * (size_t)Mf * K3, st));
+      RN_CHECK(cudaMallocAsync((void**)&B3, sizeof(double) * 4 * (size_t)F * Mh * K3, st));
+      err = launch_pack(st, 1, 0, 1, Mf, (int)K3, bra, K3, 1, A3, K3 * 2);
+      if (err) return err;
+      err = launch_pack(st, 1, 1, 0, F * Mh, (int)K3, Y, K3, 1, B3, K3 * 2);
+      if (err) return err;
+      Aop = A3; B3op = B3;
+    }
+    err = gemm_dispatch(st, path, Mf, F * Mh * es, (int)(K3 * es), Aop, K3 * es, B3op, K3 * es,
+                        (double*)out, (long)F * Mh * es);
+    if (err) return err;
+  }
+  if (B1) cudaFreeAsync(B1, st);
+  if (X1) cudaFreeAsync(X1, st);
+  if (Y) cudaFreeAsync(Y, st);
+  if (A3) cudaFreeAsync(A3, st);
+  if (B3) cudaFreeAsync(B3, st);
+  return 0;
+}

@@ -1,0 +1,28 @@
+// Internal launcher declarations shared between the translation units of librn_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace rn {
+
+struct WApplyParams {
+  const void* in;
+  void* out;
+  int X, P, Q, Y;
+  long isx, isp, isq, isy;
+  int D, F, Y2;
+  long osx, osd, osf, osy1, osy2;
+  const int* rowptr;
+  const int* ent_pq;
+  const double* ent_val;
+  int YT;
+  int order;  // innermost-in-memory input index: 0 = y, 1 = p (then y), 2 = q (then y)
+};
+
+int launch_gemm_tn_f64(cudaStream_t st, int m, int n, int k, const double* A, long lda,
+                       const double* B, long ldb, double* C, long ldc, int accumulate, int batch,
+                       long sA, long sB, long sC);
+int launch_pack(cudaStream_t st, int cplx, int mode, int conj_flag, int rows, int cols,
+                const void* src, long s_row, long s_col, double* dst, long dst_ld);
+int launch_wapply(cudaStream_t st, int cplx, const WApplyParams& p);
+
+}  // namespace rn

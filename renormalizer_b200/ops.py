@@ -1,0 +1,364 @@
+"""Thin Python wrappers over the C ABI: device tensors in, device tensors out.
+
+Everything here launches kernels from librn_b200.so; torch is used for allocation and streams.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, stream_ptr, LaunchCounter
+from .backend import backend, asxp
+
+
+def _is_cplx(t):
+    return 1 if t.dtype == torch.complex128 else 0
+
+
+def _es(t):
+    return 2 if t.dtype == torch.complex128 else 1
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check_dev(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+            raise ValueError("expected contiguous CUDA tensors")
+        if t.dtype not in (torch.float64, torch.complex128):
+            raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+def promote(*ts):
+    """Bring tensors to a common dtype (float64 unless any is complex128)."""
+    cplx = any(t.dtype == torch.complex128 for t in ts)
+    dt = torch.complex128 if cplx else torch.float64
+    return [t if t.dtype == dt else t.to(dt) for t in ts]
+
+
+def gemm_tn(a, b, m, n, k, lda, ldb, out=None, ldc=None, accumulate=False):
+    """out[i, j] (+)= sum_k a[i*lda+k] b[j*ldb+k] on float64 storage (real views)."""
+    lib = _lib.get()
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float64, device=a.device)
+        ldc = n
+    check(lib.rn_dgemm_tn(stream_ptr(), m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldc,
+                          1 if accumulate else 0, 1, 0, 0, 0), "rn_dgemm_tn")
+    LaunchCounter.add(1)
+    return out
+
+
+def pack(src, rows, cols, s_row, s_col, mode=0, conj=False):
+    """Strided 2-D view of `src` -> K-major real operand (see rn_pack)."""
+    lib = _lib.get()
+    cplx = _is_cplx(src)
+    es = 2 if cplx else 1
+    out_rows = rows * (2 if (cplx and mode == 1) else 1)
+    dst = torch.empty((out_rows, cols * es), dtype=torch.float64, device=src.device)
+    check(lib.rn_pack(stream_ptr(), cplx, mode, 1 if conj else 0, rows, cols, _ptr(src),
+                      s_row, s_col, _ptr(dst), cols * es), "rn_pack")
+    LaunchCounter.add(1)
+    return dst
+
+
+def matmul(a, b):
+    """a (M,K) @ b (K,N) for real / complex tensors through pack + the K-major GEMM
+    (xp.tensordot with one contracted axis, matrix.py:210)."""
+    a, b = promote(a.contiguous(), b.contiguous())
+    _check_dev(a, b)
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2
+    cplx = _is_cplx(a)
+    es = 2 if cplx else 1
+    out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    if M == 0 or N == 0:
+        return out
+    if K == 0:
+        return out.zero_()
+    # right operand "math B"[k, j] = b[k*N + j] -> K-major rows j
+    bp = pack(b, N, K, 1, N, mode=1 if cplx else 0)
+    gemm_tn(torch.view_as_real(a) if cplx else a, bp, M, N * es, K * es, K * es, K * es,
+            out=torch.view_as_real(out) if cplx else out, ldc=N * es)
+    return out
+
+
+def tensordot1(a, b):
+    """tensordot(a, b, axes=1): contract the last axis of a with the first axis of b."""
+    sa, sb = a.shape, b.shape
+    out = matmul(a.reshape(-1, sa[-1]), b.reshape(sb[0], -1))
+    return out.reshape(tuple(sa[:-1]) + tuple(sb[1:]))
+
+
+class MpoSite:
+    """One MPO site tensor W[b, up, down, f] (real) with its CSR forms on the device.
+
+    orientation 0 (hop, left environment):  W'[p=b, D=up, q=down, F=f]
+    orientation 1 (right environment)    :  W'[p=f, D=up, q=down, F=b]
+    """
+
+    def __init__(self, w):
+        if isinstance(w, torch.Tensor):
+            w = w.detach().cpu().numpy()
+        w = np.asarray(w)
+        if np.iscomplexobj(w):
+            if np.abs(w.imag).max() > 0:
+                raise NotImplementedError("complex MPO site tensors are outside the accelerated path")
+            w = w.real
+        self.array = np.ascontiguousarray(w, dtype=np.float64)
+        assert self.array.ndim == 4 and self.array.shape[1] == self.array.shape[2]
+        self.shape = self.array.shape
+        self._csr = {}
+        self._dense = None
+
+    @property
+    def dense(self):
+        if self._dense is None:
+            self._dense = asxp(self.array)
+        return self._dense
+
+    def csr(self, orientation):
+        if orientation not in self._csr:
+            w = self.array
+            wb, d, _, wf = w.shape
+            if orientation == 0:
+                t = w.transpose(1, 3, 0, 2)      # up, f, b, down
+            else:
+                t = w.transpose(1, 0, 3, 2)      # up, b, f, down
+            D, F, P, Q = t.shape
+            flat = t.reshape(D * F, P * Q)
+            rows, cols = np.nonzero(flat)
+            rowptr = np.zeros(D * F + 1, dtype=np.int32)
+            np.add.at(rowptr, rows + 1, 1)
+            rowptr = np.cumsum(rowptr).astype(np.int32)
+            pq = cols.astype(np.int32)
+            val = flat[rows, cols].astype(np.float64)
+            if len(pq) == 0:
+                pq = np.zeros(1, dtype=np.int32)
+                val = np.zeros(1, dtype=np.float64)
+            dev = backend.device
+            self._csr[orientation] = (F, torch.from_numpy(rowptr).to(dev),
+                                      torch.from_numpy(pq).to(dev), torch.from_numpy(val).to(dev))
+        return self._csr[orientation]
+
+
+_site_cache = {}
+
+
+def as_mpo_site(w):
+    if isinstance(w, MpoSite):
+        return w
+    if hasattr(w, "array") and isinstance(getattr(w, "array"), MpoSite):
+        return w.array
+    key = id(w)
+    hit = _site_cache.get(key)
+    if hit is not None and hit[0] is w:
+        return hit[1]
+    site = MpoSite(w)
+    if len(_site_cache) > 4096:
+        _site_cache.clear()
+    _site_cache[key] = (w, site)
+    return site
+
+
+class HopPlan:
+    """Device plan for H_eff . C (rn_hop_plan_*)."""
+
+    def __init__(self, ltensor, rtensor, sites, cshape, dtype, path=None):
+        lib = _lib.get()
+        self.lib = lib
+        nsite = len(sites)
+        cshape = tuple(int(x) for x in cshape)
+        ancilla = nsite > 0 and (2 * nsite + 2 == len(cshape))
+        if not ancilla and nsite + 2 != len(cshape):
+            raise ValueError(f"cshape {cshape} does not match {nsite} centre sites")
+        self.dtype = dtype
+        self.L = ltensor if ltensor.dtype == dtype else ltensor.to(dtype)
+        self.R = rtensor if rtensor.dtype == dtype else rtensor.to(dtype)
+        _check_dev(self.L, self.R)
+        La, Lb, Lc = self.L.shape
+        Rl, Rf, Rk = self.R.shape
+        d = [1, 1]
+        g = [1, 1]
+        for i in range(nsite):
+            if ancilla:
+                d[i], g[i] = cshape[1 + 2 * i], cshape[2 + 2 * i]
+            else:
+                d[i] = cshape[1 + i]
+        if cshape[0] != Lc or cshape[-1] != Rk:
+            raise ValueError("cshape bonds do not match the environments")
+        self.sites = sites
+        csr = [s.csr(0) for s in sites]
+        for i, s in enumerate(sites):
+            if s.shape[1] != d[i]:
+                raise ValueError("MPO physical dimension does not match cshape")
+        self._keep = csr
+        null = (0, None, None, None)
+        c1 = csr[0] if nsite >= 1 else null
+        c2 = csr[1] if nsite == 2 else null
+        self.out_shape = (La,) + cshape[1:-1] + (Rl,)
+        self.in_shape = cshape
+        handle = ctypes.c_void_p()
+        path = backend.gemm_path if path is None else path
+        check(lib.rn_hop_plan_create(ctypes.byref(handle), stream_ptr(), 1 if dtype == torch.complex128 else 0,
+                                     nsite, _ptr(self.L), La, Lb, Lc, _ptr(self.R), Rl, Rf, Rk,
+                                     d[0], g[0], d[1], g[1],
+                                     c1[0], _ptr(c1[1]), _ptr(c1[2]), _ptr(c1[3]),
+                                     c2[0], _ptr(c2[1]), _ptr(c2[2]), _ptr(c2[3]), path),
+              "rn_hop_plan_create")
+        if dtype == torch.complex128:
+            LaunchCounter.add(1)
+        self.handle = handle
+        self.nlaunch = 2 + nsite + 1
+
+    def apply(self, c, out=None):
+        if c.dtype != self.dtype:
+            c = c.to(self.dtype)
+        c = c.contiguous()
+        if out is None:
+            out = torch.empty(self.out_shape, dtype=self.dtype, device=c.device)
+        check(self.lib.rn_hop_apply(self.handle, stream_ptr(), _ptr(c), _ptr(out)), "rn_hop_apply")
+        LaunchCounter.add(self.nlaunch)
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.rn_hop_plan_destroy(self.handle, stream_ptr())
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def env_update(environ, bra, ket, site, domain, path=None):
+    """rn_env_update: absorb one site into a left/right environment (device tensors).
+    `bra` is the un-conjugated bra-side site tensor."""
+    lib = _lib.get()
+    environ, bra, ket = promote(environ, bra, ket)
+    environ, bra, ket = environ.contiguous(), bra.contiguous(), ket.contiguous()
+    _check_dev(environ, bra, ket)
+    cplx = _is_cplx(ket)
+    Ea, Eb, Ec = environ.shape
+    if ket.ndim == 3:
+        d, g = ket.shape[1], 1
+    elif ket.ndim == 4:
+        d, g = ket.shape[1], ket.shape[2]
+    else:
+        raise ValueError(f"MPS ndim is not 3 or 4, got {ket.ndim}")
+    if domain == "L":
+        dom = 0
+        Mf, Mh = bra.shape[-1], ket.shape[-1]
+        assert bra.shape[0] == Ea and ket.shape[0] == Ec and site.shape[0] == Eb
+    elif domain == "R":
+        dom = 1
+        Mf, Mh = bra.shape[0], ket.shape[0]
+        assert bra.shape[-1] == Ea and ket.shape[-1] == Ec and site.shape[-1] == Eb
+    else:
+        raise ValueError("domain must be 'L' or 'R'")
+    F, rowptr, pq, val = site.csr(dom)
+    out = torch.empty((Mf, F, Mh), dtype=ket.dtype, device=ket.device)
+    path = backend.gemm_path if path is None else path
+    check(lib.rn_env_update(stream_ptr(), cplx, dom, _ptr(environ), Ea, Eb, Ec, _ptr(bra), _ptr(ket),
+                            d, g, Mf, Mh, F, _ptr(rowptr), _ptr(pq), _ptr(val), _ptr(out), path),
+          "rn_env_update")
+    LaunchCounter.add(6 if cplx else (5 if dom == 0 else 3))
+    return out
+
+
+def qr(a, lq=False):
+    """Householder QR (or LQ) of a 2-D device tensor; returns (Q, R) or (L, Q)."""
+    lib = _lib.get()
+    a = a.contiguous()
+    _check_dev(a)
+    m, n = a.shape
+    k = min(m, n)
+    cplx = _is_cplx(a)
+    if not lq:
+        q = torch.empty((m, k), dtype=a.dtype, device=a.device)
+        r = torch.empty((k, n), dtype=a.dtype, device=a.device)
+        check(lib.rn_qr(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(q), k, _ptr(r), n), "rn_qr")
+        LaunchCounter.add(2 * k + 4)
+        return q, r
+    l = torch.empty((m, k), dtype=a.dtype, device=a.device)
+    q = torch.empty((k, n), dtype=a.dtype, device=a.device)
+    check(lib.rn_lq(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(l), k, _ptr(q), n), "rn_lq")
+    LaunchCounter.add(2 * k + 4)
+    return l, q
+
+
+def svd(a, max_sweeps=40, sort=True):
+    """One-sided Jacobi SVD; returns (U, S, Vh) with S sorted descending when sort."""
+    lib = _lib.get()
+    a = a.contiguous()
+    _check_dev(a)
+    m, n = a.shape
+    k = min(m, n)
+    cplx = _is_cplx(a)
+    u = torch.empty((m, k), dtype=a.dtype, device=a.device)
+    s = torch.empty((k,), dtype=torch.float64, device=a.device)
+    vh = torch.empty((k, n), dtype=a.dtype, device=a.device)
+    sweeps = ctypes.c_int(0)
+    check(lib.rn_svd_jacobi(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(u), k, _ptr(s), _ptr(vh), n,
+                            max_sweeps, ctypes.byref(sweeps)), "rn_svd_jacobi")
+    nn = (k + 1) // 2 * 2
+    LaunchCounter.add(sweeps.value * max(nn - 1, 0) + 5)
+    if sort:
+        order = torch.argsort(s, descending=True)
+        u, s, vh = u.index_select(1, order), s.index_select(0, order), vh.index_select(0, order)
+    return u, s, vh
+
+
+class VecWorkspace:
+    """Scratch for the reductions of the Krylov / Davidson kernels."""
+
+    def __init__(self, device, nvec_max=64):
+        self.nvec_max = nvec_max
+        self.ws = torch.empty(2 * _lib.REDUCE_BLOCKS * nvec_max, dtype=torch.float64, device=device)
+
+
+def multi_dot(V, x, nvec, n, cplx, ws, out=None):
+    """out[i] = <V[i], x> for the first nvec rows of the 2-D stack V (complex -> 2 doubles)."""
+    lib = _lib.get()
+    assert nvec <= ws.nvec_max
+    if out is None:
+        out = torch.empty(2 * nvec, dtype=torch.float64, device=x.device)
+    es = 2 if cplx else 1
+    ld = V.stride(0) * es if V.ndim == 2 else n * es
+    check(lib.rn_multi_dot(stream_ptr(), 1 if cplx else 0, n, nvec, _ptr(V), ld, _ptr(x), _ptr(ws.ws),
+                           _ptr(out)), "rn_multi_dot")
+    LaunchCounter.add(2)
+    return out
+
+
+def lincomb(V, coef, nvec, n, cplx, out):
+    """out = sum_i coef[i] V[i]; coef is a device tensor (complex when cplx)."""
+    lib = _lib.get()
+    es = 2 if cplx else 1
+    ld = V.stride(0) * es
+    check(lib.rn_lincomb(stream_ptr(), 1 if cplx else 0, n, nvec, _ptr(V), ld, _ptr(coef), _ptr(out)),
+          "rn_lincomb")
+    LaunchCounter.add(1)
+    return out
+
+
+def lanczos_update(w, vj, vjm1, alpha, beta_prev, ws, beta_out):
+    lib = _lib.get()
+    nd = w.numel() * _es(w)
+    check(lib.rn_lanczos_update(stream_ptr(), nd, _ptr(w), _ptr(vj), _ptr(vjm1), _ptr(alpha),
+                                _ptr(beta_prev), _ptr(ws.ws), _ptr(beta_out)), "rn_lanczos_update")
+    LaunchCounter.add(2)
+
+
+def scale_inv(x, s, out):
+    lib = _lib.get()
+    nd = x.numel() * _es(x)
+    check(lib.rn_scale_inv(stream_ptr(), nd, _ptr(x), _ptr(s), _ptr(out)), "rn_scale_inv")
+    LaunchCounter.add(1)

@@ -1,0 +1,193 @@
+"""Quantum-number blocked SVD / QR of a centre tensor on the device.
+
+Mirror of renormalizer/mps/svd_qn.py:97-314: same arguments and return tuples as the reference's
+svd_qn; the per-block scipy.linalg.svd / qr / rq calls become rn_svd_jacobi / rn_qr / rn_lq.
+Quantum numbers stay on the host (tiny integer arrays); matrices never leave the device --
+only the singular values are copied back, because the caller's truncation logic needs them.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .backend import asxp
+
+
+def add_outer(a: np.ndarray, b: np.ndarray):
+    """np.add.outer keeping the last (quantum number component) axis; svd_qn.py:302-310."""
+    assert a.shape[-1] == b.shape[-1]
+    sa, sb = a.shape[:-1], b.shape[:-1]
+    return a.reshape(sa + (1,) * len(sb) + (-1,)) + b.reshape((1,) * len(sa) + sb + (-1,))
+
+
+def get_qn_mask(qnmat: np.ndarray, qntot):
+    """svd_qn.py:313-314."""
+    return np.all(qnmat == np.array(qntot), axis=-1)
+
+
+def _idx(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(device)
+
+
+def _complete(q, extra):
+    """Append `extra` orthonormal columns orthogonal to the orthonormal columns of q.
+    Same construction as add_orthonormal_basis (svd_qn.py:52-66): project random vectors and QR."""
+    m, n = q.shape
+    if extra <= 0:
+        return q
+    a = torch.from_numpy(np.random.rand(m, extra)).to(q.device).to(q.dtype)
+    for _ in range(2):
+        a = a - ops.matmul(q, ops.matmul(q.conj().transpose(0, 1).contiguous(), a))
+    qa, _ = ops.qr(a)
+    return torch.cat([q, qa], dim=1)
+
+
+def _block_svd(block, full_matrices, opt_full_matrices):
+    """optimized_svd (svd_qn.py:13-49): economic Jacobi SVD, completed to the sizes the reference
+    returns under full_matrices (all of the null space, or min(m,n) extra vectors when very
+    unbalanced)."""
+    m, n = block.shape
+    if not full_matrices:
+        opt_full_matrices = False
+    opt = opt_full_matrices and not (1 / 3 < m / n < 3)
+    u, s, vh = ops.svd(block)
+    if full_matrices:
+        k = min(m, n)
+        if opt:
+            if m < n:
+                vh = _complete(vh.conj().transpose(0, 1).contiguous(), k).conj().transpose(0, 1).contiguous()
+            else:
+                u = _complete(u, k)
+        else:
+            u = _complete(u, m - k)
+            vh = _complete(vh.conj().transpose(0, 1).contiguous(), n - k).conj().transpose(0, 1).contiguous()
+    return u, s, vh
+
+
+def _scatter_rows(indices, block, nrows, trivial):
+    if trivial:
+        return block
+    out = torch.zeros((nrows, block.shape[1]), dtype=block.dtype, device=block.device)
+    out.index_copy_(0, indices, block)
+    return out
+
+
+def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray, QR: bool = False,
+           system: str = None, full_matrices: bool = True, opt_full_matrices: bool = True):
+    """Block decompose the coefficient tensor by SVD / QR according to the quantum numbers.
+
+    Returns (U, S_u, qnl, V, S_v, qnr) -- or (U, qnl, V, qnr) with QR=True -- exactly like the
+    reference (svd_qn.py:97-246): U and V are device tensors whose columns are the new basis
+    (V = Vh.T, not conjugated), S_* are NumPy arrays.  With QR=True and system "R" the factor
+    returned in U is lower instead of upper triangular (an LQ factorisation); the orthonormal
+    factor and the product U @ V.T are the same gauge class as the reference's RQ.
+    """
+    coef_array = asxp(coef_array)
+    nl = int(np.prod(qnbigl.shape[:-1]))
+    nr = int(np.prod(qnbigr.shape[:-1]))
+    mat = coef_array.reshape(nl, nr)
+    dev = mat.device
+    assert qntot.ndim == 1
+    qn_size = len(qntot)
+    lqn = qnbigl.reshape(-1, qn_size)
+    rqn = qnbigr.reshape(-1, qn_size)
+
+    u_nz, u_z, v_nz, v_z, s_nz, su_z, sv_z = [], [], [], [], [], [], []
+    ql_nz, ql_z, qr_nz, qr_z = [], [], [], []
+    for ql in set([tuple(t) for t in lqn]):
+        qr_ = qntot - ql
+        rset = np.where(get_qn_mask(rqn, qr_))[0]
+        if len(rset) == 0:
+            continue
+        lset = np.where(get_qn_mask(lqn, ql))[0]
+        trivial = len(lset) == nl and len(rset) == nr
+        if trivial:
+            block = mat
+            li = ri = None
+        else:
+            li, ri = _idx(lset, dev), _idx(rset, dev)
+            block = mat.index_select(0, li).index_select(1, ri).contiguous()
+        dim = min(block.shape)
+        if not QR:
+            bu, bs, bvh = _block_svd(block, full_matrices, opt_full_matrices)
+            s_nz.append(bs.cpu().numpy())
+            bv = bvh.transpose(0, 1)
+        else:
+            if full_matrices:
+                raise NotImplementedError("QR with full_matrices=True is not used on the sweep path")
+            if system == "R":
+                bu, bq = ops.qr(block, lq=True)
+                bv = bq.transpose(0, 1)
+            elif system == "L":
+                bu, br = ops.qr(block)
+                bv = br.transpose(0, 1)
+            else:
+                assert False
+        u_nz.append(_scatter_rows(li, bu[:, :dim].contiguous(), nl, trivial))
+        ql_nz += [ql] * dim
+        v_nz.append(_scatter_rows(ri, bv[:, :dim].contiguous(), nr, trivial))
+        qr_nz += [tuple(qr_)] * dim
+        if full_matrices:
+            u_z.append(_scatter_rows(li, bu[:, dim:].contiguous(), nl, trivial))
+            ql_z += [ql] * (bu.shape[1] - dim)
+            su_z.append(np.zeros(bu.shape[1] - dim))
+            v_z.append(_scatter_rows(ri, bv[:, dim:].contiguous(), nr, trivial))
+            qr_z += [tuple(qr_)] * (bv.shape[1] - dim)
+            sv_z.append(np.zeros(bv.shape[1] - dim))
+    if len(u_nz) + len(u_z) == 0 or len(v_nz) + len(v_z) == 0:
+        raise ValueError("Invalid quantum number")
+    u = torch.cat(u_nz + u_z, dim=1) if len(u_nz + u_z) > 1 else (u_nz + u_z)[0]
+    v = torch.cat(v_nz + v_z, dim=1) if len(v_nz + v_z) > 1 else (v_nz + v_z)[0]
+    qnl_new = ql_nz + ql_z
+    qnr_new = qr_nz + qr_z
+    if QR:
+        return u, qnl_new, v, qnr_new
+    su = np.concatenate(s_nz + su_z)
+    sv = np.concatenate(s_nz + sv_z)
+    if not full_matrices:
+        order = np.argsort(su)[::-1]
+        oi = _idx(order.copy(), dev)
+        u, v = u.index_select(1, oi), v.index_select(1, oi)
+        su = sv = su[order]
+        qnl_new = np.array(qnl_new)[order].tolist()
+        qnr_new = np.array(qnr_new)[order].tolist()
+    return u, su, qnl_new, v, sv, qnr_new
+
+
+def select_basis(vset, sset, qnlist, compset, Mmax, percent=0):
+    """Select the retained basis and the complementary tensor (reference lib.py:265-335).
+    Index selection runs on the host over the singular values; the column gathers run on device."""
+    qnlist = [tuple(qn) for qn in qnlist]
+    qnset = set(qnlist)
+    pool = {i: (qnlist[i], sset[i]) for i in range(len(qnlist))}
+
+    def block_select(qn, n):
+        members = sorted(((i, v) for i, v in pool.items() if v[0] == qn),
+                         key=lambda x: x[1][1], reverse=True)
+        got = [i for i, _ in members[:min(n, len(members))]]
+        for i in got:
+            del pool[i]
+        return got
+
+    nbasis = min(len(pool), Mmax)
+    sidx = []
+    if percent != 0:
+        nbas_block = int(nbasis * percent / len(qnset))
+        for iqn in qnset:
+            sidx += block_select(iqn, nbas_block)
+    nbasis = nbasis - len(sidx)
+    ranked = sorted(pool.items(), key=lambda x: x[1][1], reverse=True)
+    sidx += [i for i, _ in ranked[:nbasis]]
+    assert len(sidx) == len(set(sidx))
+    mpsdim = len(sidx)
+    dev = vset.device
+    sel = _idx(np.array(sidx), dev)
+    ms = vset.index_select(1, sel)
+    compmps = None
+    if compset is not None:
+        ncomp = compset.shape[1]
+        inside = np.array([i < ncomp for i in sidx])
+        scale = np.where(inside, np.asarray(sset)[sidx], 0.0)
+        safe = _idx(np.where(inside, np.array(sidx), 0), dev)
+        compmps = compset.index_select(1, safe) * torch.from_numpy(scale).to(dev).to(compset.dtype)
+    mpsqn = [qnlist[i] for i in sidx]
+    return ms, mpsdim, np.array(mpsqn), compmps

@@ -1,0 +1,243 @@
+"""GPU parity tests of the C-ABI kernels against the CPU oracle (run with -m gpu on a B200)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import contract as oc
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # float64 contractions: relative to the largest output element
+
+
+def dev(a):
+    from renormalizer_b200.backend import asxp
+    return asxp(a)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def rnd(rng, shape, cplx):
+    a = rng.standard_normal(shape)
+    if cplx:
+        a = a + 1j * rng.standard_normal(shape)
+    return a
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (7, 5, 3), (128, 128, 16), (130, 257, 33),
+                                   (300, 64, 1000), (64, 300, 17), (513, 129, 255)])
+def test_dgemm_tn(m, n, k):
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(m * 1000 + n * 10 + k)
+    a, b = rng.standard_normal((m, k)), rng.standard_normal((n, k))
+    c = ops.gemm_tn(dev(a), dev(b), m, n, k, k, k)
+    assert relerr(host(c), a @ b.T) < TOL
+    # accumulate + leading dimensions larger than the logical sizes
+    c0 = rng.standard_normal((m, n + 3))
+    cd = dev(c0)
+    ops.gemm_tn(dev(a), dev(b), m, n, k, k, k, out=cd, ldc=n + 3, accumulate=True)
+    exp = c0.copy()
+    exp[:, :n] += a @ b.T
+    assert relerr(host(cd), exp) < TOL
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("M,K,N", [(5, 7, 3), (33, 65, 40), (256, 31, 100)])
+def test_matmul_pack(cplx, M, K, N):
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(11)
+    a, b = rnd(rng, (M, K), cplx), rnd(rng, (K, N), cplx)
+    assert relerr(host(ops.matmul(dev(a), dev(b))), a @ b) < TOL
+
+
+@pytest.mark.parametrize("t", ["r", "c"])
+def test_hop_golden(golden, t):
+    """H_eff.C against vectors produced by the reference's hop_expr."""
+    from renormalizer_b200.hop_expr import hop_expr
+    g = golden("kernels")
+    L, R, R1, R0, W1, W2 = (g[f"{t}_{k}"] for k in ("L", "R", "R1", "R0", "W1", "W2"))
+    cases = [("hop0", R0, [], "C0"), ("hop1", R1, [W1], "C1"), ("hop2", R, [W1, W2], "C2"),
+             ("hop1a", R1, [W1], "C1a"), ("hop2a", R, [W1, W2], "C2a")]
+    for name, r, cmo, ck in cases:
+        c = g[f"{t}_{ck}"]
+        expr = hop_expr(dev(L), dev(r), list(cmo), c.shape)
+        got = host(expr(dev(c)))
+        assert got.shape == g[f"{t}_{name}"].shape
+        assert relerr(got, g[f"{t}_{name}"]) < TOL, name
+
+
+@pytest.mark.parametrize("t", ["r", "c"])
+def test_env_golden(golden, t):
+    from renormalizer_b200.lib import contract_one_site
+    g = golden("kernels")
+    L, R1, W1 = g[f"{t}_L"], g[f"{t}_R1"], g[f"{t}_W1"]
+    for name, env, a, dom in [("envL3", L, "A3", "L"), ("envL4", L, "A4", "L"),
+                              ("envR3", R1, "A3", "R"), ("envR4", R1, "A4", "R")]:
+        got = host(contract_one_site(dev(env), dev(g[f"{t}_{a}"]), W1, dom))
+        assert relerr(got, g[f"{t}_{name}"]) < TOL, name
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("Ml,Mr,w,d", [(1, 1, 1, 2), (13, 9, 3, 4), (64, 48, 5, 8), (130, 100, 4, 3)])
+def test_hop_env_random(cplx, Ml, Mr, w, d):
+    """Oracle comparison at ragged sizes, including different bra/ket bond dimensions."""
+    from renormalizer_b200.hop_expr import hop_expr
+    from renormalizer_b200.lib import contract_one_site
+    rng = np.random.default_rng(Ml * 7 + Mr)
+    Ml2, Mr2 = Ml + 2, max(1, Mr - 1)
+    L = rnd(rng, (Ml2, w, Ml), cplx)
+    R = rnd(rng, (Mr2, w + 1, Mr), cplx)
+    W = rng.standard_normal((w, d, d, w + 1)) * (rng.random((w, d, d, w + 1)) < 0.4)
+    W2 = rng.standard_normal((w + 1, d, d, w + 1)) * (rng.random((w + 1, d, d, w + 1)) < 0.4)
+    C1 = rnd(rng, (Ml, d, Mr), cplx)
+    got = host(hop_expr(dev(L), dev(R), [W], C1.shape)(dev(C1)))
+    assert relerr(got, oc.hop_apply(L, R, [W], C1)) < TOL
+    C2 = rnd(rng, (Ml, d, d, Mr), cplx)
+    got = host(hop_expr(dev(L), dev(R), [W, W2], C2.shape)(dev(C2)))
+    assert relerr(got, oc.hop_apply(L, R, [W, W2], C2)) < TOL
+    R0 = rnd(rng, (Mr2, w, Mr), cplx)
+    C0 = rnd(rng, (Ml, Mr), cplx)
+    got = host(hop_expr(dev(L), dev(R0), [], C0.shape)(dev(C0)))
+    assert relerr(got, oc.hop_apply(L, R0, [], C0)) < TOL
+    # environments with a bra different from the ket
+    ket = rnd(rng, (Ml, d, Mr), cplx)
+    bra = rnd(rng, (Ml2, d, Mr2), cplx)
+    got = host(contract_one_site(dev(L), dev(ket), W, "L", ms_conj=dev(bra.conj())))
+    assert relerr(got, oc.env_update(L, ket, W, "L", ms_conj=bra.conj())) < TOL
+    Wr = rng.standard_normal((w, d, d, w + 1)) * (rng.random((w, d, d, w + 1)) < 0.4)
+    got = host(contract_one_site(dev(R), dev(ket), Wr, "R", ms_conj=dev(bra.conj())))
+    assert relerr(got, oc.env_update(R, ket, Wr, "R", ms_conj=bra.conj())) < TOL
+
+
+def test_hop_linearity_full_size():
+    """Size-independent property at the bench shape (M=256): H(a x + b y) = a H x + b H y and
+    <y, H x> = conj(<x, H y>) for Hermitian environments."""
+    from renormalizer_b200.hop_expr import hop_expr
+    rng = np.random.default_rng(5)
+    M, w, d = 256, 4, 10
+    def herm_env():
+        e = rnd(rng, (M, w, M), True)
+        return e + e.conj().transpose(2, 1, 0)
+    L, R = herm_env(), herm_env()
+    W = rng.standard_normal((w, d, d, w))
+    W = W + W.transpose(0, 2, 1, 3)
+    expr = hop_expr(dev(L), dev(R), [W], (M, d, M))
+    x, y = dev(rnd(rng, (M, d, M), True)), dev(rnd(rng, (M, d, M), True))
+    hx, hy = expr(x), expr(y)
+    comb = expr(0.3 * x + (0.2 - 0.7j) * y)
+    ref = 0.3 * hx + (0.2 - 0.7j) * hy
+    assert float((comb - ref).abs().max() / ref.abs().max()) < 1e-12
+    a = torch.vdot(y.flatten(), hx.flatten())
+    b = torch.vdot(x.flatten(), hy.flatten())
+    assert abs(complex(a) - complex(b).conjugate()) / abs(complex(a)) < 1e-11
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 3), (3, 5), (40, 40), (300, 17), (64, 200), (513, 130)])
+def test_qr_lq(cplx, m, n):
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(m + 31 * n)
+    a = rnd(rng, (m, n), cplx)
+    k = min(m, n)
+    q, r = (host(x) for x in ops.qr(dev(a)))
+    assert q.shape == (m, k) and r.shape == (k, n)
+    assert np.abs(q.conj().T @ q - np.eye(k)).max() < 1e-12
+    assert relerr(q @ r, a) < 1e-12
+    assert np.abs(np.tril(r, -1)).max() == 0
+    if m >= n:
+        # same Householder convention as LAPACK: compare with numpy directly
+        qn, rn_ = np.linalg.qr(a)
+        assert relerr(r, rn_) < 1e-10 and relerr(q, qn) < 1e-10
+    l, q2 = (host(x) for x in ops.qr(dev(a), lq=True))
+    assert l.shape == (m, k) and q2.shape == (k, n)
+    assert np.abs(q2 @ q2.conj().T - np.eye(k)).max() < 1e-12
+    assert relerr(l @ q2, a) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_qr_rank_deficient(cplx):
+    """Padded bond dimensions give exactly rank-deficient matrices; Q must stay orthonormal."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(3)
+    a = rnd(rng, (60, 4), cplx) @ rnd(rng, (4, 20), cplx)
+    a[:, 7] = 0
+    q, r = (host(x) for x in ops.qr(dev(a)))
+    assert np.abs(q.conj().T @ q - np.eye(20)).max() < 1e-12
+    assert relerr(q @ r, a) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("m,n", [(1, 1), (6, 4), (4, 6), (33, 33), (200, 31), (50, 120), (256, 256)])
+def test_svd_jacobi(cplx, m, n):
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(m * 3 + n)
+    a = rnd(rng, (m, n), cplx)
+    # graded singular values over 12 decades: Jacobi keeps relative accuracy
+    k = min(m, n)
+    u0, _, v0 = np.linalg.svd(a, full_matrices=False)
+    s0 = np.logspace(0, -12, k)
+    a = (u0 * s0) @ v0
+    u, s, vh = (host(x) for x in ops.svd(dev(a)))
+    assert np.all(np.diff(s) <= 0)
+    assert np.abs(s - s0).max() < 1e-13
+    # forming `a` in floating point perturbs sigma_min = 1e-12 by ~1e-16 absolute already
+    assert np.abs(s / s0 - 1).max() < 1e-3
+    assert relerr((u * s) @ vh, a) < 1e-12
+    assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-11
+    assert np.abs(vh @ vh.conj().T - np.eye(k)).max() < 1e-11
+
+
+def test_vector_kernels():
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(0)
+    n, nvec = 100003, 5
+    for cplx in (False, True):
+        V = rnd(rng, (nvec, n), cplx)
+        x = rnd(rng, (n,), cplx)
+        ws = ops.VecWorkspace(dev(x).device)
+        out = host(ops.multi_dot(dev(V), dev(x), nvec, n, cplx, ws)).reshape(nvec, 2)
+        ref = V.conj() @ x
+        assert relerr(out[:, 0] + 1j * out[:, 1], ref) < 1e-12
+        coef = rnd(rng, (nvec,), cplx)
+        o = dev(np.zeros(n, dtype=V.dtype))
+        ops.lincomb(dev(V), dev(coef), nvec, n, cplx, o)
+        assert relerr(host(o), coef @ V) < 1e-12
+        w, vj, vm = rnd(rng, (n,), cplx), rnd(rng, (n,), cplx), rnd(rng, (n,), cplx)
+        wd = dev(w)
+        alpha, beta = dev(np.array([0.37, 0.0])), dev(np.array([1.9, 0.0]))
+        bout = dev(np.zeros(2))
+        ops.lanczos_update(wd, dev(vj), dev(vm), alpha, beta, ws, bout)
+        exp = w - 0.37 * vj - 1.9 * vm
+        assert relerr(host(wd), exp) < 1e-14
+        assert abs(host(bout)[0] - np.linalg.norm(exp)) / np.linalg.norm(exp) < 1e-13
+        o2 = dev(np.zeros(n, dtype=V.dtype))
+        ops.scale_inv(wd, bout, o2)
+        assert relerr(host(o2), exp / np.linalg.norm(exp)) < 1e-13
+
+
+def test_host_buffer_entry_points(golden):
+    """The host-pointer C-ABI calls (what a NumPy-side caller binds)."""
+    import ctypes
+    from renormalizer_b200 import _lib
+    lib = _lib.get()
+    g = golden("kernels")
+    for t, cplx in (("r", 0), ("c", 1)):
+        L, R1, W1, C1 = (np.ascontiguousarray(g[f"{t}_{k}"]) for k in ("L", "R1", "W1", "C1"))
+        out = np.zeros_like(g[f"{t}_hop1"])
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        err = lib.rn_hop_apply_host(cplx, 1, p(L), *L.shape, p(R1), *R1.shape, C1.shape[1], 1, 1, 1,
+                                    p(W1), W1.shape[3], None, 0, p(C1), p(out), 0)
+        assert err == 0
+        assert relerr(out, g[f"{t}_hop1"]) < TOL
+        A3 = np.ascontiguousarray(g[f"{t}_A3"])
+        for dom, env, name in ((0, L, "envL3"), (1, R1, "envR3")):
+            out = np.zeros_like(g[f"{t}_{name}"])
+            Mf = Mh = A3.shape[2] if dom == 0 else A3.shape[0]
+            err = lib.rn_env_update_host(cplx, dom, p(env), *env.shape, p(A3), p(A3), A3.shape[1], 1,
+                                         Mf, Mh, p(W1), W1.shape[0], W1.shape[3], p(out), 0)
+            assert err == 0
+            assert relerr(out, g[f"{t}_{name}"]) < TOL
