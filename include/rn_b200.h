@@ -119,6 +119,13 @@ int rn_env_update_host(int cplx, int domain, const void* env, int Ea, int Eb, in
                        const void* bra, const void* ket, int d, int g, int Mf, int Mh,
                        const double* W, int Wb, int Wf, void* out, int path);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------
+ * Between rn_profile_begin and rn_profile_end every contraction GEMM launch is bracketed by CUDA
+ * events on its own stream; rn_profile_end returns the summed launch time, the summed
+ * 2*m*n*k FLOPs and the launch count. */
+int rn_profile_begin(void);
+int rn_profile_end(double* total_ms, double* total_flops, long* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,8 @@ SIGNATURES = {
     "rn_lincomb": (_i, [_vp, _i, _l, _i, _vp, _l, _vp, _vp]),
     "rn_hop_apply_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
                                _vp, _i, _vp, _i, _vp, _vp, _i]),
+    "rn_profile_begin": (_i, []),
+    "rn_profile_end": (_i, [POINTER(c_double), POINTER(c_double), POINTER(c_long)]),
     "rn_env_update_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i,
                                 _vp, _i, _i, _vp, _i]),
 }

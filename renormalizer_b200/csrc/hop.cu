@@ -20,6 +20,7 @@
 #include "internal.cuh"
 
 #include <new>
+#include <vector>
 
 namespace rn {
 
@@ -30,10 +31,31 @@ struct WCsr {
   const double* val = nullptr;
 };
 
+// Optional per-launch timing of the contraction GEMMs (bench.py's roofline leg).
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  double flops = 0.0;
+};
+static GemmProfile g_prof;
+
 static int gemm_dispatch(cudaStream_t st, int path, int m, int n, int k, const double* A, long lda,
                          const double* B, long ldb, double* C, long ldc) {
   (void)path;
-  return launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    RN_CHECK(cudaEventCreate(&e0));
+    RN_CHECK(cudaEventCreate(&e1));
+    RN_CHECK(cudaEventRecord(e0, st));
+  }
+  int err = launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
+  if (g_prof.on) {
+    RN_CHECK(cudaEventRecord(e1, st));
+    g_prof.ev.push_back(e0);
+    g_prof.ev.push_back(e1);
+    g_prof.flops += 2.0 * m * n * k;
+  }
+  return err;
 }
 
 }  // namespace rn
@@ -266,5 +288,31 @@ extern "C" int rn_env_update(void* stream, int cplx, int domain, const void* env
   if (Y) cudaFreeAsync(Y, st);
   if (A3) cudaFreeAsync(A3, st);
   if (B3) cudaFreeAsync(B3, st);
+  return 0;
+}
+
+// ---- GEMM launch profiling (used by bench.py only) ---------------------------------------------
+extern "C" int rn_profile_begin(void) {
+  g_prof.on = true;
+  g_prof.ev.clear();
+  g_prof.flops = 0.0;
+  return 0;
+}
+
+extern "C" int rn_profile_end(double* total_ms, double* total_flops, long* launches) {
+  g_prof.on = false;
+  RN_CHECK(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.ev.size(); i += 2) {
+    float t = 0.f;
+    RN_CHECK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    ms += t;
+    cudaEventDestroy(g_prof.ev[i]);
+    cudaEventDestroy(g_prof.ev[i + 1]);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = g_prof.flops;
+  if (launches) *launches = (long)(g_prof.ev.size() / 2);
+  g_prof.ev.clear();
   return 0;
 }

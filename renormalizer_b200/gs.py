@@ -1,0 +1,187 @@
+"""DMRG ground-state sweeps on the device -- mirror of renormalizer/mps/gs.py:54-576 for the
+accelerated configuration (single root, no omega targeting, Davidson or direct eigensolver)."""
+import logging
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from . import ops
+from .backend import asnumpy, asxp
+from .configs import CompressConfig, CompressCriteria
+from .davidson import davidson
+from .hop_expr import hop_expr_dtype
+from .lib import Environ
+from .svd_qn import get_qn_mask
+
+logger = logging.getLogger(__name__)
+
+
+def optimize_mps(mps, mpo, omega: float = None):
+    """DMRG ground state algorithm (gs.py:54-171).  `mps` is overwritten during the optimisation;
+    returns (energies of each macro sweep, optimised mps)."""
+    if omega is not None:
+        raise NotImplementedError("omega targeting ((H-omega)^2) is outside the accelerated path")
+    if mps.optimize_config.nroots != 1:
+        raise NotImplementedError("state-averaged DMRG (nroots > 1) is outside the accelerated path")
+    assert mps.optimize_config.method in ["2site", "1site"]
+    if mps.is_left_canonical:
+        mps.ensure_right_canonical()
+        env = "R"
+    else:
+        mps.ensure_left_canonical()
+        env = "L"
+    compress_config_bk = mps.compress_config
+    environ = Environ(mps, mpo, env)
+    macro_iteration_result = []
+    opt_e_idx = None
+    res_mps = None
+    for isweep, (compress_config, percent) in enumerate(mps.optimize_config.procedure):
+        if isinstance(compress_config, CompressConfig):
+            mps.compress_config = compress_config
+        elif isinstance(compress_config, (int, np.integer)):
+            mps.compress_config = CompressConfig(criteria=CompressCriteria.fixed,
+                                                 max_bonddim=int(compress_config))
+        else:
+            assert False
+        micro_iteration_result, res_mps, mpo = single_sweep(mps, mpo, environ, omega, percent, opt_e_idx)
+        opt_e = min(micro_iteration_result)
+        macro_iteration_result.append(opt_e[0])
+        opt_e_idx = opt_e[1]
+        if isweep > 0 and percent == 0:
+            v1, v2 = sorted(macro_iteration_result)[:2]
+            if np.allclose(v1, v2, rtol=mps.optimize_config.e_rtol, atol=mps.optimize_config.e_atol):
+                logger.info("DMRG has converged!")
+                break
+    else:
+        logger.warning("DMRG did not converge! Please increase the procedure!")
+    assert res_mps is not None
+    res_mps = res_mps.normalize("mps_only").ensure_left_canonical().canonicalise()
+    res_mps.compress_config = compress_config_bk
+    return macro_iteration_result, res_mps
+
+
+def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
+    """gs.py:174-304."""
+    method = mps.optimize_config.method
+    res_mps = None
+    micro_iteration_result = []
+    hop_counts = []
+    for imps in mps.iter_idx_list(full=True):
+        if method == "2site" and ((mps.to_right and imps == mps.site_num - 1)
+                                  or ((not mps.to_right) and imps == 0)):
+            break
+        if mps.to_right:
+            lmethod, rmethod = "System", "Enviro"
+        else:
+            lmethod, rmethod = "Enviro", "System"
+        if method == "1site":
+            lidx, cidx, ridx = imps - 1, [imps], imps + 1
+        elif mps.to_right:
+            lidx, cidx, ridx = imps - 1, [imps, imps + 1], imps + 2
+        else:
+            lidx, cidx, ridx = imps - 2, [imps - 1, imps], imps + 1
+        ltensor = environ.GetLR("L", lidx, mps, mpo, itensor=None, method=lmethod)
+        rtensor = environ.GetLR("R", ridx, mps, mpo, itensor=None, method=rmethod)
+        qnbigl, qnbigr, qnmat = mps._get_big_qn(cidx)
+        qn_mask = get_qn_mask(qnmat, mps.qntot)
+        cshape = qn_mask.shape
+        cmo = [mpo[idx] for idx in cidx]
+        use_direct_eigh = np.prod(cshape) < 1000 or mps.optimize_config.algo == "direct"
+        if use_direct_eigh:
+            e, cstruct = eigh_direct(mps, qn_mask, ltensor, rtensor, cmo)
+            nhop = 0
+        else:
+            if method == "1site":
+                raw_cguess = mps[cidx[0]]
+            else:
+                raw_cguess = ops.tensordot1(mps[cidx[0]], mps[cidx[1]])
+            e, cstruct, nhop = eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess)
+        hop_counts.append(nhop)
+        micro_iteration_result.append((e, cidx))
+        if cidx == last_opt_e_idx:
+            res_mps = mps.copy()
+            res_mps._update_mps(cstruct, cidx, qnbigl, qnbigr, percent)
+        mps._update_mps(cstruct, cidx, qnbigl, qnbigr, percent)
+    mps._switch_direction()
+    mps.hop_counts = hop_counts
+    return micro_iteration_result, res_mps, mpo
+
+
+def _sign_fix(c):
+    """gs.py:372-380 on a device vector: make the largest-magnitude component positive."""
+    idx = torch.argmax(c.abs())
+    return c / torch.sgn(c[idx])
+
+
+def eigh_direct(mps, qn_mask, ltensor, rtensor, cmo):
+    """gs.py:307-407: tiny centre tensors are diagonalised densely.  The dense H_eff is assembled
+    by applying the device H_eff to the unit vectors of the symmetry-allowed subspace."""
+    cshape = qn_mask.shape
+    dtype = torch.complex128 if (ltensor.is_complex() or rtensor.is_complex()) else torch.float64
+    hop = hop_expr_dtype(ltensor, rtensor, cmo, cshape, dtype)
+    idx = np.nonzero(qn_mask.reshape(-1))[0]
+    nfull = int(np.prod(cshape))
+    dev = ltensor.device
+    cols = []
+    sel = torch.from_numpy(idx).to(dev)
+    for i in idx:
+        x = torch.zeros(nfull, dtype=dtype, device=dev)
+        x[i] = 1
+        cols.append(hop(x.reshape(cshape)).reshape(-1).index_select(0, sel))
+    hop.close()
+    ham = asnumpy(torch.stack(cols, dim=1)) * mps.optimize_config.inverse
+    w, v = scipy.linalg.eigh(ham)
+    c = v[:, 0]
+    c = c / np.sign(c[np.abs(c).argmax()])
+    cstruct = np.zeros(nfull, dtype=c.dtype)
+    cstruct[idx] = c
+    return w[0], asxp(cstruct.reshape(cshape))
+
+
+def _hdiag(ltensor, rtensor, cmo):
+    """Diagonal of H_eff for the Davidson preconditioner (gs.py:422-445).  O(M^2 d w^2) setup
+    work done with torch.einsum on the device."""
+    dl = torch.einsum("aba->ba", ltensor)
+    dr = torch.einsum("aba->ba", rtensor)
+    d0 = torch.einsum("abbc->abc", cmo[0].dense).to(dl.dtype)
+    if len(cmo) == 1:
+        return torch.einsum("ba,bcg,gf->acf", dl, d0, dr)
+    d1 = torch.einsum("abbc->abc", cmo[1].dense).to(dl.dtype)
+    return torch.einsum("ba,bce,edg,gf->acdf", dl, d0, d1, dr)
+
+
+def eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess):
+    """gs.py:486-576 with algo == "davidson".  The Davidson vectors are kept dense on the device
+    and multiplied by the quantum-number mask, which is the same subspace iteration as the
+    reference's gather / scatter (cvec2cmat) through the mask."""
+    inverse = mps.optimize_config.inverse
+    if mps.optimize_config.algo != "davidson":
+        raise NotImplementedError("only the Davidson eigensolver is accelerated")
+    cshape = qn_mask.shape
+    cplx = ltensor.is_complex() or rtensor.is_complex() or raw_cguess.is_complex()
+    dtype = torch.complex128 if cplx else torch.float64
+    dev = ltensor.device
+    mask = torch.from_numpy(qn_mask.reshape(-1)).to(dev)
+    maskf = mask.to(dtype)
+    hdiag = (_hdiag(ltensor, rtensor, cmo).real.reshape(-1) * inverse)
+    hop = hop_expr_dtype(ltensor, rtensor, cmo, cshape, dtype)
+    count = [0]
+
+    def aop(x):
+        count[0] += 1
+        y = hop(x.reshape(cshape)).reshape(-1)
+        y *= maskf
+        if inverse != 1.0:
+            y *= inverse
+        return y
+
+    # 1/(hdiag - e + 1e-4) restricted to the allowed subspace
+    def precond(x, e, *args):
+        return torch.where(mask, x / (hdiag - e + 1e-4).to(dtype), torch.zeros((), dtype=dtype, device=dev))
+
+    guess = raw_cguess.reshape(-1).to(dtype) * maskf
+    e, c = davidson(aop, [guess], precond, max_cycle=100, nroots=1)
+    hop.close()
+    c = _sign_fix(c)
+    return e, c.reshape(cshape), count[0]

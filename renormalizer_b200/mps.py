@@ -1,0 +1,524 @@
+"""Matrix product state resident in HBM, with the sweep-path methods of the reference.
+
+Mirrors the parts of renormalizer/mps/mp.py (MatrixProduct) and renormalizer/mps/mps.py (Mps)
+that the DMRG / TDVP-PS sweeps touch: quantum-number bookkeeping (_get_big_qn, move_qnidx),
+canonicalisation (_push_cano, canonicalise, ensure_*_canonical), the centre update
+(_update_mps), evolve() with the projector-splitting TDVP integrator, expectation, dot, norm.
+Site tensors are CUDA tensors (float64 or complex128); quantum numbers are small host arrays.
+"""
+from typing import List
+
+import numpy as np
+import torch
+
+from . import ops
+from .backend import backend, asxp, asnumpy
+from .configs import CompressConfig, EvolveConfig, OptimizeConfig, EvolveMethod
+from .hop_expr import hop_expr_dtype
+from .krylov import expm_krylov
+from .lib import Environ, contract_one_site
+from .svd_qn import add_outer, svd_qn, select_basis
+
+
+class Mps:
+    def __init__(self, sites, qn, sigmaqn, qntot, qnidx, to_right, coeff=1.0):
+        self._mp = [asxp(s) for s in sites]
+        self.qn = [np.asarray(q) for q in qn]
+        self.sigmaqn = [np.asarray(s) for s in sigmaqn]
+        self.qntot = np.asarray(qntot)
+        self.qnidx = int(qnidx)
+        self.to_right = bool(to_right)
+        self.coeff = coeff
+        self.compress_config = CompressConfig()
+        self.optimize_config = OptimizeConfig()
+        self.evolve_config = EvolveConfig()
+
+    # ------------------------------------------------------------------ construction / transfer
+    @classmethod
+    def from_numpy(cls, sites, qn, sigmaqn, qntot, qnidx, to_right, coeff=1.0):
+        return cls(sites, qn, sigmaqn, qntot, qnidx, to_right, coeff)
+
+    @classmethod
+    def without_qn(cls, sites, qnidx=None, to_right=False):
+        """MPS of a model with no conserved quantum number (all qn zero)."""
+        n = len(sites)
+        dims = [s.shape[0] for s in sites] + [sites[-1].shape[-1]]
+        qn = [np.zeros((d, 1), dtype=int) for d in dims]
+        sigmaqn = [np.zeros((s.shape[1], 1), dtype=int) for s in sites]
+        return cls(sites, qn, sigmaqn, np.array([0]), n - 1 if qnidx is None else qnidx, to_right)
+
+    def to_numpy(self):
+        return [asnumpy(s) for s in self._mp]
+
+    def load_sites_from_host(self, host_sites, non_blocking=True):
+        """Host (pinned) buffers -> the existing device site tensors (same shapes)."""
+        for dst, src in zip(self._mp, host_sites):
+            dst.copy_(src, non_blocking=non_blocking)
+
+    def store_sites_to_host(self, host_sites, non_blocking=True):
+        for src, dst in zip(self._mp, host_sites):
+            dst.copy_(src, non_blocking=non_blocking)
+
+    def metacopy(self):
+        new = self.__class__.__new__(self.__class__)
+        new._mp = [None] * len(self)
+        new.qn = [q.copy() for q in self.qn]
+        new.sigmaqn = self.sigmaqn
+        new.qntot = self.qntot.copy()
+        new.qnidx = self.qnidx
+        new.to_right = self.to_right
+        new.coeff = self.coeff
+        new.compress_config = self.compress_config.copy()
+        new.optimize_config = self.optimize_config.copy()
+        new.evolve_config = self.evolve_config.copy()
+        return new
+
+    def copy(self):
+        new = self.metacopy()
+        new._mp = [s.clone() for s in self._mp]
+        return new
+
+    def to_complex(self, inplace=False):
+        new = self if inplace else self.metacopy()
+        new._mp = [s.to(torch.complex128) if not s.is_complex() else (s if inplace else s.clone())
+                   for s in self._mp]
+        return new
+
+    def conj(self):
+        new = self.metacopy()
+        new._mp = [s.conj().resolve_conj() for s in self._mp]
+        return new
+
+    # ------------------------------------------------------------------ container protocol
+    def __len__(self):
+        return len(self._mp)
+
+    def __getitem__(self, i):
+        return self._mp[i]
+
+    def __setitem__(self, i, t):
+        self._mp[i] = t if isinstance(t, torch.Tensor) else asxp(t)
+
+    def __iter__(self):
+        return iter(self._mp)
+
+    @property
+    def site_num(self):
+        return len(self._mp)
+
+    @property
+    def is_complex(self):
+        return any(s.is_complex() for s in self._mp)
+
+    @property
+    def dtype(self):
+        return torch.complex128 if self.is_complex else torch.float64
+
+    @property
+    def bond_dims(self):
+        return [s.shape[0] for s in self._mp] + [self._mp[-1].shape[-1]]
+
+    @property
+    def pbond_list(self):
+        return [s.shape[1] for s in self._mp]
+
+    @property
+    def total_bytes(self):
+        return sum(s.numel() * s.element_size() for s in self._mp)
+
+    def _get_sigmaqn(self, idx):
+        return self.sigmaqn[idx]
+
+    # ------------------------------------------------------------------ qn bookkeeping
+    def move_qnidx(self, dstidx: int):
+        """mp.py:159-172."""
+        for idx in range(self.qnidx + 1, self.site_num + 1):
+            self.qn[idx] = self.qntot - self.qn[idx]
+        for idx in range(self.site_num, dstidx, -1):
+            self.qn[idx] = self.qntot - self.qn[idx]
+        self.qnidx = dstidx
+
+    def iter_idx_list(self, full: bool, stop_idx: int = None):
+        """mp.py:230-243."""
+        if self.to_right:
+            last = stop_idx if stop_idx is not None else (self.site_num if full else self.site_num - 1)
+            return range(self.qnidx, last)
+        last = stop_idx if stop_idx is not None else (-1 if full else 0)
+        return range(self.qnidx, last, -1)
+
+    def _switch_direction(self):
+        """mp.py:297-306."""
+        assert self.to_right is not None
+        if self.to_right:
+            self.qnidx = self.site_num - 1
+            self.to_right = False
+        else:
+            self.qnidx = 0
+            self.to_right = True
+
+    def _get_big_qn(self, cidx: List[int]):
+        """mp.py:308-352: quantum numbers of the super-L / super-R blocks and of the centre."""
+        if len(cidx) == 2:
+            cidx = sorted(cidx)
+            assert cidx[0] + 1 == cidx[1]
+        elif len(cidx) > 2:
+            assert False
+        assert self.qnidx in cidx
+        sigmaqn = [np.array(self._get_sigmaqn(idx)) for idx in cidx]
+        qnl = np.array(self.qn[cidx[0]])
+        qnr = np.array(self.qn[cidx[-1] + 1])
+        if len(cidx) == 1:
+            if self.to_right:
+                qnbigl, qnbigr = add_outer(qnl, sigmaqn[0]), qnr
+            else:
+                qnbigl, qnbigr = qnl, add_outer(sigmaqn[0], qnr)
+        else:
+            qnbigl, qnbigr = add_outer(qnl, sigmaqn[0]), add_outer(sigmaqn[1], qnr)
+        return qnbigl, qnbigr, add_outer(qnbigl, qnbigr)
+
+    # ------------------------------------------------------------------ canonical form
+    def check_left_canonical(self, rtol=None, atol=None):
+        """mp.py:174-181 / matrix.py:93-103."""
+        atol = backend.canonical_atol if atol is None else atol
+        rtol = backend.canonical_rtol if rtol is None else rtol
+        for s in self._mp[:-1]:
+            m = s.reshape(-1, s.shape[-1])
+            g = ops.matmul(m.conj().transpose(0, 1).contiguous(), m)
+            if not torch.allclose(g, torch.eye(g.shape[0], dtype=g.dtype, device=g.device), rtol=rtol, atol=atol):
+                return False
+        return True
+
+    def check_right_canonical(self, rtol=None, atol=None):
+        atol = backend.canonical_atol if atol is None else atol
+        rtol = backend.canonical_rtol if rtol is None else rtol
+        for s in self._mp[1:]:
+            m = s.reshape(s.shape[0], -1)
+            g = ops.matmul(m, m.conj().transpose(0, 1).contiguous())
+            if not torch.allclose(g, torch.eye(g.shape[0], dtype=g.dtype, device=g.device), rtol=rtol, atol=atol):
+                return False
+        return True
+
+    @property
+    def is_left_canonical(self):
+        return self.qnidx == self.site_num - 1
+
+    @property
+    def is_right_canonical(self):
+        return self.qnidx == 0
+
+    def ensure_left_canonical(self, rtol=None, atol=None):
+        """mp.py:206-216."""
+        if self.to_right or self.qnidx != self.site_num - 1 or not self.check_left_canonical(rtol, atol):
+            self.move_qnidx(0)
+            self.to_right = True
+            return self.canonicalise()
+        return self
+
+    def ensure_right_canonical(self, rtol=None, atol=None):
+        """mp.py:218-228."""
+        if (not self.to_right) or self.qnidx != 0 or not self.check_right_canonical(rtol, atol):
+            self.move_qnidx(self.site_num - 1)
+            self.to_right = False
+            return self.canonicalise()
+        return self
+
+    def _update_ms(self, idx, u, vt, sigma=None, qnlset=None, qnrset=None, m_trunc=None):
+        """mp.py:245-295 for an MPS (no MPO norm balancing)."""
+        if m_trunc is None:
+            m_trunc = u.shape[1]
+        u = u[:, :m_trunc]
+        vt = vt[:m_trunc, :]
+        if sigma is not None:
+            sig = torch.from_numpy(np.ascontiguousarray(sigma[:m_trunc])).to(u.device).to(u.dtype)
+            if self.to_right:
+                vt = vt * sig[:, None]
+            else:
+                u = u * sig[None, :]
+        shape = self._mp[idx].shape
+        pdim = tuple(shape[1:-1])
+        if self.to_right:
+            self._mp[idx + 1] = ops.tensordot1(vt.contiguous(), self._mp[idx + 1])
+            self._mp[idx] = u.contiguous().reshape((shape[0],) + pdim + (m_trunc,))
+            if qnlset is not None:
+                self.qn[idx + 1] = np.array(qnlset[:m_trunc])
+                self.qnidx = idx + 1
+        else:
+            self._mp[idx - 1] = ops.tensordot1(self._mp[idx - 1], u.contiguous())
+            self._mp[idx] = vt.contiguous().reshape((m_trunc,) + pdim + (shape[-1],))
+            if qnrset is not None:
+                self.qn[idx] = np.array(qnrset[:m_trunc])
+                self.qnidx = idx - 1
+
+    def _push_cano(self, idx):
+        """mp.py:890-908: move the canonical centre one site on with a QR."""
+        qnbigl, qnbigr, _ = self._get_big_qn([idx])
+        system = "L" if self.to_right else "R"
+        u, qnlset, v, qnrset = svd_qn(self._mp[idx], qnbigl, qnbigr, self.qntot, QR=True,
+                                      system=system, full_matrices=False)
+        self._update_ms(idx, u, v.transpose(0, 1), sigma=None, qnlset=qnlset, qnrset=qnrset)
+
+    def canonicalise(self, stop_idx: int = None):
+        """mp.py:910-922."""
+        if self.to_right:
+            assert self.qnidx == 0
+        else:
+            assert self.qnidx == self.site_num - 1
+        idx = None
+        for idx in self.iter_idx_list(full=False, stop_idx=stop_idx):
+            self._push_cano(idx)
+        if (not self.to_right and idx == 1) or (self.to_right and idx == self.site_num - 2):
+            self._switch_direction()
+        return self
+
+    def compress(self, temp_m_trunc=None, ret_s=False):
+        """mp.py:437-511: SVD compression sweep of a canonicalised MPS."""
+        if self.to_right:
+            assert self.qnidx == 0
+        else:
+            assert self.qnidx == self.site_num - 1
+        if self.compress_config.bonddim_should_set:
+            self.compress_config.set_bonddim(len(self) + 1)
+        system = "L" if self.to_right else "R"
+        s_list = []
+        for idx in self.iter_idx_list(full=False):
+            qnbigl, qnbigr, _ = self._get_big_qn([idx])
+            u, sigma, qnlset, v, sigma, qnrset = svd_qn(self._mp[idx], qnbigl, qnbigr, self.qntot,
+                                                        system=system, full_matrices=False)
+            s_list.append(sigma)
+            if temp_m_trunc is None:
+                m_trunc = self.compress_config.compute_m_trunc(sigma, idx, self.to_right)
+            else:
+                if isinstance(temp_m_trunc, (list, tuple, np.ndarray)):
+                    m_trunc = temp_m_trunc[idx + 1 if self.to_right else idx]
+                else:
+                    m_trunc = temp_m_trunc
+                m_trunc = min(m_trunc, len(sigma))
+            self._update_ms(idx, u, v.transpose(0, 1), sigma, qnlset, qnrset, m_trunc)
+        self._switch_direction()
+        if not ret_s:
+            return self
+        mx = max(len(s) for s in s_list)
+        return self, np.array([np.pad(s, (0, mx - len(s))) for s in s_list])
+
+    # ------------------------------------------------------------------ centre update (DMRG)
+    def _update_mps(self, cstruct, cidx, qnbigl, qnbigr, percent=0):
+        """mp.py:651-888, single-state SVD branch without on-the-fly swapping."""
+        if isinstance(cstruct, list):
+            raise NotImplementedError("state-averaged update is outside the accelerated path")
+        if self.compress_config.ofs is not None:
+            raise NotImplementedError("on-the-fly swapping is outside the accelerated path")
+        system = "L" if self.to_right else "R"
+        if self.compress_config.bonddim_should_set:
+            self.compress_config.set_bonddim(len(self) + 1)
+        Uset, SUset, qnlnew, Vset, SVset, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, self.qntot, system=system)
+        if self.to_right:
+            m_trunc = self.compress_config.compute_m_trunc(SUset, cidx[0], self.to_right)
+            ms, msdim, msqn, compms = select_basis(Uset, SUset, qnlnew, Vset, m_trunc, percent=percent)
+            ms = ms.contiguous().reshape(list(qnbigl.shape[:-1]) + [msdim])
+            compms = compms.transpose(0, 1).contiguous().reshape([msdim] + list(qnbigr.shape[:-1]))
+        else:
+            m_trunc = self.compress_config.compute_m_trunc(SVset, cidx[-1], self.to_right)
+            ms, msdim, msqn, compms = select_basis(Vset, SVset, qnrnew, Uset, m_trunc, percent=percent)
+            ms = ms.transpose(0, 1).contiguous().reshape([msdim] + list(qnbigr.shape[:-1]))
+            compms = compms.contiguous().reshape(list(qnbigl.shape[:-1]) + [msdim])
+        n = self.site_num
+        if len(cidx) == 1:
+            i = cidx[0]
+            self._mp[i] = ms
+            if self.to_right:
+                if i != n - 1:
+                    self._mp[i + 1] = ops.tensordot1(compms, self._mp[i + 1])
+                    self.qn[i + 1] = msqn
+                    self.qnidx = i + 1
+                else:
+                    self._mp[i] = ops.tensordot1(self._mp[i], compms)
+                    self.qnidx = n - 1
+            else:
+                if i != 0:
+                    self._mp[i - 1] = ops.tensordot1(self._mp[i - 1], compms)
+                    self.qn[i] = msqn
+                    self.qnidx = i - 1
+                else:
+                    self._mp[i] = ops.tensordot1(compms, self._mp[i])
+                    self.qnidx = 0
+        else:
+            if self.to_right:
+                self._mp[cidx[0]], self._mp[cidx[1]] = ms, compms
+                self.qnidx = cidx[1]
+            else:
+                self._mp[cidx[1]], self._mp[cidx[0]] = ms, compms
+                self.qnidx = cidx[0]
+            self.qn[cidx[1]] = msqn
+        return None
+
+    # ------------------------------------------------------------------ scalars
+    def dot(self, other) -> complex:
+        """<conj(self) ... > as in mp.py:933-958: sum_i self_i * other_i (no conjugation)."""
+        assert len(self) == len(other)
+        e0 = torch.ones((1, 1), dtype=torch.float64, device=self._mp[0].device)
+        for mt1, mt2 in zip(self._mp, other):
+            t = ops.tensordot1(e0, mt2)                       # (a, d.., r2)
+            a = t.reshape(-1, t.shape[-1])                     # ((a,d..), r2)
+            b = mt1.reshape(-1, mt1.shape[-1])                 # ((a,d..), r1)
+            e0 = ops.matmul(b.transpose(0, 1).contiguous(), a)  # (r1, r2)
+        return complex(e0[0, 0].item())
+
+    @property
+    def mp_norm(self) -> float:
+        """mp.py:355-372."""
+        res = self.conj().dot(self).real
+        if res < 0:
+            assert abs(res) < 1e-8
+            res = 0
+        return float(np.sqrt(res))
+
+    @property
+    def norm(self):
+        return abs(self.coeff) * self.mp_norm
+
+    def scale(self, val, inplace=False):
+        """mp.py:984-994: scale the tensor at the qn centre."""
+        new = self if inplace else self.copy()
+        if np.iscomplex(val):
+            new.to_complex(inplace=True)
+        else:
+            val = val.real if hasattr(val, "real") else val
+        new._mp[self.qnidx] = new._mp[self.qnidx] * val
+        return new
+
+    def normalize(self, kind):
+        """mps.py:2025-2058."""
+        nrm = self.mp_norm
+        if kind == "mps_only":
+            new_coeff = self.coeff
+        elif kind == "mps_and_coeff":
+            new_coeff = self.coeff / abs(self.coeff)
+        elif kind == "mps_norm_to_coeff":
+            new_coeff = self.coeff * nrm
+        else:
+            raise ValueError(f"kind={kind} is not valid.")
+        self.scale(1.0 / nrm, inplace=True)
+        self.coeff = new_coeff
+        return self
+
+    def expectation(self, mpo, self_conj=None):
+        """mps.py:471-525: <self| mpo |self> through a right environment."""
+        if self_conj is None:
+            self_conj = self.conj()
+        r = torch.ones((1, 1, 1), dtype=torch.float64, device=self._mp[0].device)
+        for i in range(len(self) - 1, -1, -1):
+            r = contract_one_site(r, self._mp[i], mpo[i], "R", ms_conj=self_conj[i])
+        val = complex(r[0, 0, 0].item())
+        if np.isclose(val.imag, 0):
+            return float(val.real)
+        return val
+
+    def distance(self, other) -> float:
+        """mp.py:1009-1023."""
+        l1 = self.conj().dot(self)
+        l2 = other.conj().dot(other)
+        l12 = self.conj().dot(other)
+        d2 = (l1 + l2 - l12 - l12.conjugate()).real
+        return float(np.sqrt(d2)) if d2 > 0 else 0.0
+
+    # ------------------------------------------------------------------ time evolution
+    def evolve(self, mpo, evolve_dt, normalize=True):
+        """mps.py:644-662.  Only the projector-splitting integrator is accelerated."""
+        if self.evolve_config.method is not EvolveMethod.tdvp_ps:
+            raise NotImplementedError(
+                f"evolve method {self.evolve_config.method} is outside the accelerated path "
+                "(TDVP-PS, mps.py:1268, is)")
+        if self.evolve_config.ivp_solver != "krylov":
+            raise NotImplementedError("only the Krylov local solver is accelerated")
+        if self.evolve_config.adaptive:
+            new_mps = self._evolve_adaptive(mpo, evolve_dt)
+        else:
+            new_mps = self._evolve_tdvp_ps(mpo, evolve_dt)
+        if normalize:
+            if np.iscomplex(evolve_dt):
+                new_mps.normalize("mps_and_coeff")
+            else:
+                new_mps.normalize("mps_only")
+        return new_mps
+
+    def _evolve_adaptive(self, mpo, evolve_target_t):
+        """mps.py:46-115 (adaptive_tdvp): step-doubling error control around _evolve_tdvp_ps."""
+        config = self.evolve_config.copy()
+        cur = self
+        p_restart, p_min, p_max = 0.5, 0.1, 2.0
+        evolved_t = 0
+        while True:
+            rest = evolve_target_t - evolved_t
+            dt = config.guess_dt if abs(config.guess_dt) < abs(rest) else rest
+            half1 = cur._evolve_tdvp_ps(mpo, dt / 2)
+            half2 = half1._evolve_tdvp_ps(mpo, dt / 2)
+            full = cur._evolve_tdvp_ps(mpo, dt)
+            dis = full.distance(half2)
+            del half1, full
+            p = (0.75 * config.adaptive_rtol / (dis / half2.mp_norm + 1e-30)) ** (1.0 / 3)
+            p = min(max(p, p_min), p_max)
+            if p < p_restart:
+                config.guess_dt = dt * p
+                continue
+            evolved_t += dt
+            if np.allclose(evolved_t, evolve_target_t):
+                half2.evolve_config.guess_dt = config.guess_dt
+                return half2
+            config.guess_dt *= p
+            cur = half2
+
+    def _evolve_tdvp_ps(self, mpo, evolve_dt):
+        """One-site projector-splitting TDVP step (mps.py:1268-1404, Krylov local solver):
+        forward half sweep and backward half sweep, each site evolved by dt/2 with H_eff and each
+        bond matrix evolved backwards with the zero-site H_eff."""
+        if np.iscomplex(evolve_dt):
+            mps = self.copy()
+        else:
+            mps = self.to_complex()
+        cdtype = mps.dtype
+        environ = Environ(mps, mpo)
+        local_steps = []
+        n = len(mps)
+        for _ in range(2):
+            for imps in mps.iter_idx_list(full=True):
+                system = "L" if mps.to_right else "R"
+                l_array = environ.read("L", imps - 1)
+                r_array = environ.read("R", imps + 1)
+                shape = list(mps[imps].shape)
+                hop = hop_expr_dtype(l_array, r_array, [mpo[imps]], shape, cdtype)
+                mps_t, j = expm_krylov(lambda y: hop(y), -1j * evolve_dt / 2, mps[imps].reshape(-1))
+                hop.close()
+                local_steps.append(j)
+                mps_t = mps_t.reshape(shape)
+                qnbigl, qnbigr, _ = mps._get_big_qn([imps])
+                u, qnlset, v, qnrset = svd_qn(mps_t, qnbigl, qnbigr, mps.qntot, QR=True,
+                                              system=system, full_matrices=False)
+                vt = v.transpose(0, 1).contiguous()
+                if not mps.to_right and imps != 0:
+                    mps[imps] = vt.reshape([-1] + shape[1:])
+                    mps.qn[imps] = np.array(qnrset)
+                    mps.qnidx = imps - 1
+                    r_array = environ.GetLR("R", imps, mps, mpo, itensor=r_array, method="System")
+                    u = u.contiguous()
+                    shape_u = list(u.shape)
+                    hop_u = hop_expr_dtype(l_array, r_array, [], shape_u, cdtype)
+                    back, j = expm_krylov(lambda y: hop_u(y), 1j * evolve_dt / 2, u.reshape(-1))
+                    hop_u.close()
+                    local_steps.append(j)
+                    mps[imps - 1] = ops.tensordot1(mps[imps - 1], back.reshape(shape_u))
+                elif mps.to_right and imps != n - 1:
+                    mps[imps] = u.contiguous().reshape(shape[:-1] + [-1])
+                    mps.qn[imps + 1] = np.array(qnlset)
+                    mps.qnidx = imps + 1
+                    l_array = environ.GetLR("L", imps, mps, mpo, itensor=l_array, method="System")
+                    shape_svt = list(vt.shape)
+                    hop_svt = hop_expr_dtype(l_array, r_array, [], shape_svt, cdtype)
+                    back, j = expm_krylov(lambda y: hop_svt(y), 1j * evolve_dt / 2, vt.reshape(-1))
+                    hop_svt.close()
+                    local_steps.append(j)
+                    mps[imps + 1] = ops.tensordot1(back.reshape(shape_svt), mps[imps + 1])
+                else:
+                    mps[imps] = mps_t
+            mps._switch_direction()
+        mps.evolve_config.stat = local_steps
+        return mps

@@ -1,0 +1,259 @@
+"""GPU parity tests of the sweep drivers (svd_qn, Krylov, Davidson, DMRG, TDVP-PS) against the
+reference's golden vectors and the CPU oracle.  Tolerances follow BASELINE.json's north_star:
+energies / observables to 1e-10, site tensors (gauge-invariant form) to 1e-8."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from helpers import load_mpo, load_oracle_mps, relerr
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-10
+T_TOL = 1e-8
+
+
+def dev(a):
+    from renormalizer_b200.backend import asxp
+    return asxp(a)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def to_device_mps(om):
+    from renormalizer_b200.mps import Mps
+    return Mps(om.sites, om.qn, om.sigmaqn, om.qntot, om.qnidx, om.to_right)
+
+
+@pytest.mark.parametrize("t", ["r", "c"])
+@pytest.mark.parametrize("system", ["L", "R"])
+def test_svd_qn_golden(golden, t, system):
+    from renormalizer_b200.svd_qn import svd_qn
+    g = golden("svdqn")
+    k = f"{t}_{system}"
+    c, ql, qr, qntot = g[k + "_c"], g[k + "_qnbigl"], g[k + "_qnbigr"], g["qntot"]
+    mat = c.reshape(int(np.prod(ql.shape[:-1])), -1)
+    # economic SVD: singular values, quantum numbers and the decomposition itself
+    u, su, qnl, v, sv, qnr = svd_qn(dev(c), ql, qr, qntot, system=system, full_matrices=False)
+    u, v = host(u), host(v)
+    assert np.abs(su - g[k + "_svd_s"]).max() < 1e-13
+    assert np.array_equal(np.array(qnl), g[k + "_svd_qnl"])
+    assert np.array_equal(np.array(qnr), g[k + "_svd_qnr"])
+    assert relerr((u * su) @ v.T, mat) < 1e-12
+    nz = su > 1e-12
+    ref_u = g[k + "_svd_u"]
+    # gauge invariant comparison of the singular subspaces (site tensors to 1e-8)
+    assert np.abs(np.abs(np.sum(u[:, nz].conj() * ref_u[:, nz], axis=0)) - 1).max() < T_TOL
+    # full matrices: orthonormal completion, same sizes and quantum numbers as the reference
+    np.random.seed(11)
+    u, su, qnl, v, sv, qnr = svd_qn(dev(c), ql, qr, qntot, system=system, full_matrices=True)
+    u, v = host(u), host(v)
+    assert u.shape == g[k + "_fsvd_u"].shape and v.shape == g[k + "_fsvd_v"].shape
+    assert np.abs(u.conj().T @ u - np.eye(u.shape[1])).max() < 1e-12
+    assert np.abs(v.conj().T @ v - np.eye(v.shape[1])).max() < 1e-12
+    assert sorted(map(tuple, qnl)) == sorted(map(tuple, g[k + "_fsvd_qnl"]))
+    assert np.abs(np.sort(su) - np.sort(g[k + "_fsvd_su"])).max() < 1e-13
+    # QR / LQ: orthonormal factor spans the same space, product reproduces the tensor
+    u, qnl, v, qnr = svd_qn(dev(c), ql, qr, qntot, QR=True, system=system, full_matrices=False)
+    u, v = host(u), host(v)
+    assert relerr(u @ v.T, mat) < 1e-12
+    assert np.array_equal(np.array(qnl), g[k + "_qr_qnl"])
+    assert np.array_equal(np.array(qnr), g[k + "_qr_qnr"])
+    q = u if system == "L" else v
+    qref = g[k + "_qr_u"] if system == "L" else g[k + "_qr_v"]
+    assert np.abs(q.conj().T @ q - np.eye(q.shape[1])).max() < 1e-12
+    assert np.abs(q @ (q.conj().T @ qref) - qref).max() < T_TOL
+
+
+def test_svd_qn_invalid_qn_raises():
+    from renormalizer_b200.svd_qn import svd_qn, add_outer
+    qnl = np.zeros((2, 1), dtype=int)
+    with pytest.raises(ValueError):
+        svd_qn(dev(np.ones((2, 2, 2))), add_outer(qnl, qnl), qnl, np.array([5]), system="L")
+
+
+def test_expm_krylov_golden(golden):
+    from renormalizer_b200.krylov import expm_krylov
+    from renormalizer_b200 import ops
+    g = golden("krylov")
+    h, v = dev(g["h"]), dev(g["v"])
+    for i in range(3):
+        res, j = expm_krylov(lambda y: ops.matmul(h, y.reshape(-1, 1)).reshape(-1), complex(g[f"dt{i}"]), v)
+        assert j == int(g[f"j{i}"])
+        assert relerr(host(res), g[f"res{i}"]) < 1e-11
+
+
+def test_expm_krylov_small_spaces():
+    """Krylov space exhausted (n <= number of steps) and breakdown on an eigenvector."""
+    from renormalizer_b200.krylov import expm_krylov
+    from renormalizer_b200 import ops
+    import scipy.linalg
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 3, 6):
+        h = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        h = h + h.conj().T
+        v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        hd = dev(h)
+        res, j = expm_krylov(lambda y: ops.matmul(hd, y.reshape(-1, 1)).reshape(-1), -0.1j, dev(v))
+        assert relerr(host(res), scipy.linalg.expm(-0.1j * h) @ v) < 1e-10
+    n = 40
+    h = np.diag(np.arange(n, dtype=float)).astype(complex)
+    v = np.zeros(n, dtype=complex)
+    v[3] = 2.0
+    hd = dev(h)
+    res, j = expm_krylov(lambda y: ops.matmul(hd, y.reshape(-1, 1)).reshape(-1), -0.5j, dev(v))
+    assert relerr(host(res), np.exp(-0.5j * 3) * v) < 1e-12
+
+
+@pytest.mark.parametrize("nroots", [1, 3])
+def test_davidson_golden(golden, nroots):
+    from renormalizer_b200.davidson import davidson
+    from renormalizer_b200 import ops
+    g = golden("davidson")
+    a = dev(g["a"])
+    hd = dev(np.diag(g["a"]).copy())
+    count = [0]
+
+    def aop(x):
+        count[0] += 1
+        return ops.matmul(a, x.reshape(-1, 1)).reshape(-1)
+    e, c = davidson(aop, [dev(x) for x in g[f"x0_{nroots}"]],
+                    lambda x, e, *args: x / (hd - e + 1e-4), max_cycle=100, nroots=nroots)
+    assert np.abs(np.atleast_1d(e) - np.atleast_1d(g[f"e_{nroots}"])).max() < E_TOL
+    cs = [c] if nroots == 1 else c
+    ref = np.atleast_2d(g[f"c_{nroots}"])
+    for ci, ri in zip(cs, ref):
+        assert abs(abs(np.vdot(host(ci), ri)) - 1) < T_TOL
+    assert abs(count[0] - int(g[f"nhop_{nroots}"])) <= 2
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_dmrg_holstein_golden(golden, method):
+    """optimize_mps on the reference's Holstein test model, same MPO and initial MPS."""
+    from renormalizer_b200.gs import optimize_mps
+    from renormalizer_b200.mpo import Mpo
+    g = golden("holstein")
+    mpo = Mpo(load_mpo(g))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    mps.optimize_config.procedure = [[int(a), float(b)] for a, b in g["procedure"]]
+    mps.optimize_config.method = method
+    np.random.seed(99)
+    energies, opt = optimize_mps(mps, mpo)
+    ref = g[f"{method}_energies"]
+    assert len(energies) == len(ref)
+    # converged sweeps agree to the energy tolerance; early sweeps (random null-space completion
+    # differs from LAPACK's) to the reference's own convergence criterion
+    assert abs(energies[-1] - ref[-1]) < 1e-9
+    assert np.abs(np.array(energies) - ref).max() < 1e-6
+    assert abs(opt.expectation(mpo) - float(g[f"{method}_expectation"])) < 1e-9
+    assert energies[-1] == pytest.approx(0.08401412 + float(g["gs_zpe"]), rel=1e-5)
+    # the reference's final ensure_left_canonical().canonicalise() leaves a right-canonical MPS
+    assert opt.check_right_canonical() and opt.qnidx == 0
+
+
+def test_dmrg_first_site_energy_matches_oracle(golden):
+    """One Davidson solve on identical inputs: energy to 1e-10, centre tensor to 1e-8."""
+    from renormalizer_b200.gs import eigh_iterative
+    from renormalizer_b200.lib import Environ
+    from renormalizer_b200.mpo import Mpo
+    from renormalizer_b200.svd_qn import get_qn_mask
+    from oracle import sweep as osw, contract as oc
+    from oracle.davidson import davidson as odav
+    g = golden("holstein")
+    mpo_np = load_mpo(g)
+    om = load_oracle_mps(g, "mps0")
+    om.ensure_right_canonical()
+    # oracle: first two-site problem of a right-moving sweep
+    env = osw.Environ(om, mpo_np, "R")
+    cidx = [0, 1]
+    ltensor, rtensor = env.sentinel, env.read("R", 2)
+    qnbigl, qnbigr, qnmat = om.big_qn(cidx)
+    mask = osw.get_qn_mask(qnmat, om.qntot)
+    guess = np.tensordot(om.sites[0], om.sites[1], axes=1)
+    cmo = [mpo_np[0], mpo_np[1]]
+    hdiag = oc.hop_diag(ltensor, rtensor, cmo)[mask]
+
+    def hop(x):
+        full = np.zeros(mask.shape)
+        full[mask] = x
+        return oc.hop_apply(ltensor, rtensor, cmo, full)[mask]
+    if mask.sum() < 4:
+        pytest.skip("degenerate sector")
+    e_ref, c_ref = odav(hop, [guess[mask]], lambda x, e, *a: x / (hdiag - e + 1e-4), max_cycle=100)
+    dm = to_device_mps(om)
+    mpo = Mpo(mpo_np)
+    e, c, nhop = eigh_iterative(dm, mask, dev(ltensor), dev(rtensor), [mpo[0], mpo[1]], dev(guess))
+    assert abs(e - e_ref) < E_TOL
+    c_ref = c_ref / np.sign(c_ref[np.abs(c_ref).argmax()])
+    assert np.abs(host(c)[mask] - c_ref).max() < T_TOL
+
+
+def test_tdvp_ps_golden(golden):
+    """Mps.evolve (TDVP-PS, Krylov) on the reference's spin-boson run."""
+    from renormalizer_b200.mpo import Mpo
+    g = golden("sbm")
+    mpo = Mpo(load_mpo(g))
+    sz = Mpo(load_mpo(g, "sigma_z"))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    dt = float(g["dt"])
+    szs, es = [mps.expectation(sz)], [mps.expectation(mpo)]
+    for i in range(int(g["nsteps"])):
+        mps = mps.evolve(mpo, dt)
+        szs.append(mps.expectation(sz))
+        es.append(mps.expectation(mpo))
+        if i == 0:
+            ref1 = to_device_mps(load_oracle_mps(g, "mps1"))
+            assert abs(abs(ref1.conj().dot(mps)) - 1) < T_TOL
+    assert np.abs(np.array(szs) - g["sigma_z_t"]).max() < E_TOL
+    assert np.abs(np.array(es) - g["energy_t"]).max() < E_TOL
+    refT = to_device_mps(load_oracle_mps(g, "mpsT"))
+    assert abs(abs(refT.conj().dot(mps)) - 1) < T_TOL
+    assert abs(mps.mp_norm - 1) < 1e-12
+
+
+def test_tdvp_ps_vs_oracle_midsize():
+    """Random full-rank complex MPS, M=24: one step against the oracle, site tensors compared
+    through the overlap and observables."""
+    from renormalizer_b200 import models
+    from renormalizer_b200.mpo import Mpo
+    from renormalizer_b200.mps import Mps
+    from oracle import sweep as osw
+    rng = np.random.default_rng(8)
+    nmodes, d, M = 7, 4, 24
+    omega, gcoup = models.ohmic_modes(nmodes, alpha=0.3, omega_c=5.0)
+    w = models.spin_boson_mpo(0.2, 1.0, omega, gcoup, d)
+    sites = models.random_mps_sites([2] + [d] * nmodes, M, rng, dtype=np.complex128)
+    n = len(sites)
+    qn = [np.zeros((s.shape[0], 1), dtype=int) for s in sites] + [np.zeros((1, 1), dtype=int)]
+    sq = [np.zeros((s.shape[1], 1), dtype=int) for s in sites]
+    om = osw.Mps(sites, qn, sq, [0], n - 1, False)
+    dm = Mps(sites, qn, sq, [0], n - 1, False)
+    o1 = osw.evolve_tdvp_ps(om, w, 0.05)
+    d1 = dm.evolve(Mpo(w), 0.05)
+    ref = Mps(o1.sites, o1.qn, o1.sigmaqn, o1.qntot, o1.qnidx, o1.to_right)
+    assert abs(abs(ref.conj().dot(d1)) - 1) < T_TOL
+    szm = models.spin_boson_sigma_z_mpo(nmodes, d)
+    assert abs(d1.expectation(Mpo(szm)) - o1.expectation(szm)) < E_TOL
+    assert abs(d1.expectation(Mpo(w)) - o1.expectation(w)) < E_TOL
+
+
+def test_tdvp_roundtrip_time_reversal():
+    """Size-independent property: evolving by +dt then -dt returns the initial state (TDVP-PS is
+    symmetric), checked at a bond dimension the oracle would not finish quickly."""
+    from renormalizer_b200 import models
+    from renormalizer_b200.mpo import Mpo
+    from renormalizer_b200.mps import Mps
+    rng = np.random.default_rng(9)
+    nmodes, d, M = 9, 6, 64
+    omega, gcoup = models.ohmic_modes(nmodes, alpha=0.2, omega_c=5.0)
+    mpo = Mpo(models.spin_boson_mpo(0.0, 1.0, omega, gcoup, d))
+    sites = models.random_mps_sites([2] + [d] * nmodes, M, rng, dtype=np.complex128)
+    m0 = Mps.without_qn(sites)
+    m1 = m0.evolve(mpo, 0.02)
+    m2 = m1.evolve(mpo, -0.02)
+    assert abs(abs(m0.conj().dot(m2)) - 1) < 1e-9
+    e0, e1 = m0.expectation(mpo), m1.expectation(mpo)
+    assert abs(e0 - e1) < 1e-9     # energy conservation of TDVP
