@@ -33,6 +33,17 @@ int rn_dgemm_tn(void* stream, int m, int n, int k, const double* A, long lda, co
                 long ldb, double* C, long ldc, int accumulate, int batch, long strideA,
                 long strideB, long strideC);
 
+/* Same contraction with FP64 accuracy on the tcgen05 tensor cores: both operands are split into
+ * `nslices` (1..8) signed 8-bit digits per element (Ozaki scheme), the digit products run as
+ * int8 tcgen05.mma with int32 TMEM accumulators and are recombined in FP64.  nslices = 7 bounds
+ * the error by ~1e-14 * K * max|A_i| * max|B_j|; nslices = 8 reaches FP64 round-off. */
+int rn_ozaki_gemm_tn(void* stream, int m, int n, int k, const double* A, long lda, const double* B,
+                     long ldb, double* C, long ldc, int nslices);
+
+/* Digits per element (1..8, default 7) used when a plan runs with path = 1, and the m*n*k below
+ * which a contraction stays on the exact DMMA kernel (negative: keep the current value). */
+int rn_set_ozaki(int nslices, double min_work);
+
 /* Strided view -> K-major GEMM operand.  Element (r, c) of the source is src[r*s_row + c*s_col]
  * (strides in elements).  mode 0 ("A-form"): dst[r*dst_ld + c] (complex: interleaved, conj_flag
  * conjugates).  mode 1 ("B-form", complex only): 2x2 real representation, rows (2r, 2r+1), so a

@@ -38,17 +38,24 @@ struct GemmProfile {
   double flops = 0.0;
 };
 static GemmProfile g_prof;
+static int g_ozaki_slices = 7;
+static double g_ozaki_min_work = 4.0e6;
 
 static int gemm_dispatch(cudaStream_t st, int path, int m, int n, int k, const double* A, long lda,
                          const double* B, long ldb, double* C, long ldc) {
-  (void)path;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     RN_CHECK(cudaEventCreate(&e0));
     RN_CHECK(cudaEventCreate(&e1));
     RN_CHECK(cudaEventRecord(e0, st));
   }
-  int err = launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
+  int err;
+  // tensor-core path for contractions large enough to fill 128x128 tiles; boundary sites stay on
+  // the exact DMMA kernel
+  if (path == 1 && (double)m * n * k >= g_ozaki_min_work && k <= 65536)
+    err = rn_ozaki_gemm_tn(st, m, n, k, A, lda, B, ldb, C, ldc, g_ozaki_slices);
+  else
+    err = launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
   if (g_prof.on) {
     RN_CHECK(cudaEventRecord(e1, st));
     g_prof.ev.push_back(e0);
@@ -314,5 +321,12 @@ extern "C" int rn_profile_end(double* total_ms, double* total_flops, long* launc
   if (total_flops) *total_flops = g_prof.flops;
   if (launches) *launches = (long)(g_prof.ev.size() / 2);
   g_prof.ev.clear();
+  return 0;
+}
+
+extern "C" int rn_set_ozaki(int nslices, double min_work) {
+  if (nslices < 1 || nslices > 8) return (int)cudaErrorInvalidValue;
+  g_ozaki_slices = nslices;
+  if (min_work >= 0) g_ozaki_min_work = min_work;
   return 0;
 }

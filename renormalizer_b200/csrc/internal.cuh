@@ -25,4 +25,10 @@ int launch_pack(cudaStream_t st, int cplx, int mode, int conj_flag, int rows, in
                 const void* src, long s_row, long s_col, double* dst, long dst_ld);
 int launch_wapply(cudaStream_t st, int cplx, const WApplyParams& p);
 
+size_t ozaki_split_bytes(int rows, int K, int nslices);
+int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int K, int nslices,
+                       signed char* q, double* scale);
+int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
+                      const double* sA, const signed char* qB, const double* sB, double* C, long ldc);
+
 }  // namespace rn

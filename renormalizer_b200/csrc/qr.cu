@@ -11,6 +11,9 @@
 #include "rn_b200.h"
 #include "internal.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace rn {
 
 constexpr int Q_THREADS = 256;
@@ -164,6 +167,117 @@ house_applyq_kernel(typename Cx<CPLX>::T* __restrict__ Qt, int m, int k, long ld
   }
 }
 
+
+// ---- single-launch variants ------------------------------------------------------------------
+// Elimination of all k reflectors in ONE cooperative launch: column c is owned by block
+// c % gridDim.x for the whole factorisation, a grid barrier separates the steps (column j+1 must
+// be final before every block derives reflector j+1 from it).
+template <bool CPLX>
+__global__ void __launch_bounds__(Q_THREADS)
+house_factor_coop_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, int k, long ldt,
+                         typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
+                         double* __restrict__ rdiag) {
+  using C = Cx<CPLX>;
+  using T = typename C::T;
+  __shared__ double scratch[2 * Q_CPB * 32];
+  cg::grid_group grid = cg::this_grid();
+  const int nb = gridDim.x, bid = blockIdx.x;
+  for (int j = 0; j < k; ++j) {
+    const T* colj = At + (long)j * ldt;
+    T tau, scale;
+    double beta;
+    make_reflector<CPLX>(colj, m, j, scratch, tau, scale, beta);
+    if (bid == (j % nb)) {
+      T* vj = V + (long)j * ldt;
+      for (int r = threadIdx.x; r < m; r += blockDim.x)
+        vj[r] = r < j ? C::zero() : (r == j ? C::one() : C::mul(colj[r], scale));
+      if (threadIdx.x == 0) { tau_out[j] = tau; rdiag[j] = beta; }
+    }
+    const T ctau = C::conj(tau);
+    // owned columns c > j, c == bid (mod nb), Q_CPB at a time
+    int c = j + 1 + ((bid - (j + 1)) % nb + nb) % nb;
+    while (c < n) {
+      int cols[Q_CPB];
+#pragma unroll
+      for (int i = 0; i < Q_CPB; ++i) { cols[i] = c < n ? c : -1; c += nb; }
+      double acc[2 * Q_CPB];
+#pragma unroll
+      for (int i = 0; i < 2 * Q_CPB; ++i) acc[i] = 0.0;
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T v = r == j ? C::one() : C::mul(colj[r], scale);
+#pragma unroll
+        for (int i = 0; i < Q_CPB; ++i)
+          if (cols[i] >= 0) {
+            const T d = C::cmul(v, At[(long)cols[i] * ldt + r]);
+            acc[2 * i] += C::re(d);
+            acc[2 * i + 1] += C::im(d);
+          }
+      }
+      block_sum<2 * Q_CPB>(acc, scratch);
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T v = r == j ? C::one() : C::mul(colj[r], scale);
+#pragma unroll
+        for (int i = 0; i < Q_CPB; ++i)
+          if (cols[i] >= 0) {
+            const T w = C::mul(ctau, C::make(acc[2 * i], acc[2 * i + 1]));
+            T* p = At + (long)cols[i] * ldt + r;
+            *p = C::sub(*p, C::mul(v, w));
+          }
+      }
+      __syncthreads();
+    }
+    grid.sync();
+  }
+}
+
+// Q = H_0 ... H_{k-1} I in ONE launch: each block owns Q_CPB columns of Q and applies the
+// reflectors j = c_max .. 0 to them (H_j leaves e_c untouched for j > c).
+template <bool CPLX>
+__global__ void __launch_bounds__(Q_THREADS)
+house_formq_kernel(typename Cx<CPLX>::T* __restrict__ Qt, int m, int k, long ldt,
+                   const typename Cx<CPLX>::T* __restrict__ V,
+                   const typename Cx<CPLX>::T* __restrict__ tau_in) {
+  using C = Cx<CPLX>;
+  using T = typename C::T;
+  __shared__ double scratch[2 * Q_CPB * 32];
+  const int c0 = blockIdx.x * Q_CPB;
+  if (c0 >= k) return;
+  const int ncol = (k - c0) < Q_CPB ? (k - c0) : Q_CPB;
+  for (int i = 0; i < ncol; ++i)
+    for (int r = threadIdx.x; r < m; r += blockDim.x)
+      Qt[(long)(c0 + i) * ldt + r] = (r == c0 + i) ? C::one() : C::zero();
+  __syncthreads();
+  for (int j = c0 + ncol - 1; j >= 0; --j) {
+    const T* vj = V + (long)j * ldt;
+    const T tau = tau_in[j];
+    double acc[2 * Q_CPB];
+#pragma unroll
+    for (int i = 0; i < 2 * Q_CPB; ++i) acc[i] = 0.0;
+    for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+      const T v = vj[r];
+#pragma unroll
+      for (int i = 0; i < Q_CPB; ++i)
+        if (i < ncol && c0 + i >= j) {
+          const T d = C::cmul(v, Qt[(long)(c0 + i) * ldt + r]);
+          acc[2 * i] += C::re(d);
+          acc[2 * i + 1] += C::im(d);
+        }
+    }
+    block_sum<2 * Q_CPB>(acc, scratch);
+    for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+      const T v = vj[r];
+#pragma unroll
+      for (int i = 0; i < Q_CPB; ++i)
+        if (i < ncol && c0 + i >= j) {
+          const T w = C::mul(tau, C::make(acc[2 * i], acc[2 * i + 1]));
+          T* p = Qt + (long)(c0 + i) * ldt + r;
+          *p = C::sub(*p, C::mul(v, w));
+        }
+    }
+    __syncthreads();
+  }
+}
+
 template <bool CPLX>
 __global__ void set_identity_rows_kernel(typename Cx<CPLX>::T* Qt, int m, int k, long ldt) {
   using C = Cx<CPLX>;
@@ -190,11 +304,34 @@ __global__ void extract_r_kernel(const typename Cx<CPLX>::T* __restrict__ At, co
   }
 }
 
+static int g_qr_coop_blocks[2] = {-1, -1};   // co-resident block budget per dtype, -1 = unknown
+
 template <bool CPLX>
 static int qr_colmajor(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, long ldt,
                        typename Cx<CPLX>::T* V, typename Cx<CPLX>::T* tau, double* rdiag,
                        typename Cx<CPLX>::T* Qt) {
   const int k = m < n ? m : n;
+  int& budget = g_qr_coop_blocks[CPLX ? 1 : 0];
+  if (budget < 0) {
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    RN_CHECK(cudaGetDevice(&dev));
+    RN_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    RN_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RN_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, house_factor_coop_kernel<CPLX>,
+                                                           Q_THREADS, 0));
+    budget = coop ? sms * (per_sm > 2 ? 2 : per_sm) : 0;
+  }
+  if (budget > 0) {
+    int nb = n < budget ? n : budget;
+    if (nb < 1) nb = 1;
+    void* args[] = {(void*)&At, (void*)&m, (void*)&n, (void*)&k, (void*)&ldt, (void*)&V, (void*)&tau,
+                    (void*)&rdiag};
+    RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_coop_kernel<CPLX>, dim3(nb), dim3(Q_THREADS),
+                                         args, 0, st));
+    house_formq_kernel<CPLX><<<(unsigned)ceil_div(k, Q_CPB), Q_THREADS, 0, st>>>(Qt, m, k, ldt, V, tau);
+    RN_LAUNCH_CHECK();
+    return 0;
+  }
   for (int j = 0; j < k; ++j) {
     int nb = (int)ceil_div(n - j - 1, Q_CPB);
     if (nb < 1) nb = 1;

@@ -53,6 +53,18 @@ def gemm_tn(a, b, m, n, k, lda, ldb, out=None, ldc=None, accumulate=False):
     return out
 
 
+def ozaki_gemm_tn(a, b, m, n, k, lda, ldb, nslices=7, out=None, ldc=None):
+    """Same product as gemm_tn on the tcgen05 int8 split path (rn_ozaki_gemm_tn)."""
+    lib = _lib.get()
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float64, device=a.device)
+        ldc = n
+    check(lib.rn_ozaki_gemm_tn(stream_ptr(), m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldc,
+                               nslices), "rn_ozaki_gemm_tn")
+    LaunchCounter.add(3)
+    return out
+
+
 def pack(src, rows, cols, s_row, s_col, mode=0, conj=False):
     """Strided 2-D view of `src` -> K-major real operand (see rn_pack)."""
     lib = _lib.get()

@@ -241,3 +241,49 @@ def test_host_buffer_entry_points(golden):
                                          Mf, Mh, p(W1), W1.shape[0], W1.shape[3], p(out), 0)
             assert err == 0
             assert relerr(out, g[f"{t}_{name}"]) < TOL
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (1, 1, 1), (100, 37, 50), (256, 384, 1000),
+                                   (300, 130, 129), (768, 4096, 512), (2048, 512, 1536)])
+@pytest.mark.parametrize("nslices", [7, 8])
+def test_ozaki_gemm_tcgen05(m, n, k, nslices):
+    """tcgen05 int8 split GEMM against NumPy FP64; rows/columns with very different scales."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(m + n + k)
+    a, b = rng.standard_normal((m, k)), rng.standard_normal((n, k))
+    a *= np.exp(rng.uniform(-20, 20, size=(m, 1)))
+    b *= np.exp(rng.uniform(-20, 20, size=(n, 1)))
+    c = host(ops.ozaki_gemm_tn(dev(a), dev(b), m, n, k, k, k, nslices=nslices))
+    ref = a @ b.T
+    bound = np.abs(a).max(axis=1)[:, None] * np.abs(b).max(axis=1)[None, :] * k
+    err = (np.abs(c - ref) / bound).max()
+    assert err < (4e-14 if nslices == 7 else 4e-16), err
+
+
+def test_ozaki_gemm_is_exact_on_small_integers():
+    """Integer inputs below 2^6 need a single digit: the result must be bit exact."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(0)
+    m, n, k = 200, 150, 300
+    a = rng.integers(-60, 60, size=(m, k)).astype(np.float64)
+    b = rng.integers(-60, 60, size=(n, k)).astype(np.float64)
+    c = host(ops.ozaki_gemm_tn(dev(a), dev(b), m, n, k, k, k, nslices=3))
+    assert np.array_equal(c, a @ b.T)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_hop_tensor_path_matches_fp64_path(cplx):
+    """H_eff.C with path=1 (tcgen05 split GEMMs) against path=0 (FP64 DMMA) and the oracle."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(4)
+    Ml, Mr, w, d = 96, 80, 4, 6
+    L, R = rnd(rng, (Ml, w, Ml), cplx), rnd(rng, (Mr, w, Mr), cplx)
+    W = rng.standard_normal((w, d, d, w)) * (rng.random((w, d, d, w)) < 0.5)
+    C = rnd(rng, (Ml, d, Mr), cplx)
+    dt = torch.complex128 if cplx else torch.float64
+    ref = oc.hop_apply(L, R, [W], C)
+    for path in (0, 1):
+        plan = ops.HopPlan(dev(L), dev(R), [ops.MpoSite(W)], C.shape, dt, path=path)
+        got = host(plan.apply(dev(C)))
+        plan.close()
+        assert relerr(got, ref) < (1e-12 if path == 0 else 1e-11), path
