@@ -450,7 +450,7 @@ def main():
     ap.add_argument("--mols", type=int, default=20)
     ap.add_argument("--levels", type=int, default=8)
     ap.add_argument("--dt", type=float, default=0.05)
-    ap.add_argument("--path", type=int, default=0)
+    ap.add_argument("--path", type=int, default=1)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--cpu-skip-sites", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

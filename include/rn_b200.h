@@ -119,6 +119,12 @@ int rn_scale_inv(void* stream, long nd, const double* x, const double* s, double
 int rn_lincomb(void* stream, int cplx, long n, int nvec, const double* V, long ld,
                const double* coef, double* out);
 
+/* One fused Lanczos iteration on the Krylov stack V (row j = v_j, n elements per row):
+ *   w = H_eff v_j; alpha[j] = Re<v_j,w>; w -= alpha[j] v_j + beta[j-1] v_{j-1}; beta[j] = |w|;
+ *   v_{j+1} = w / beta[j].   alpha / beta hold (value, 0) pairs on the device; V needs row j+1. */
+int rn_lanczos_step(rn_hop_plan* plan, void* stream, long n, double* V, int j, double* alpha,
+                    double* beta, double* w, double* ws);
+
 /* ---- host-buffer entry points (what a NumPy-side caller binds) -------------------------------
  * Same contractions with HOST pointers: inputs are copied to the device, the kernels above run,
  * the result is copied back and the stream is synchronised.  W is the dense MPO site(s)

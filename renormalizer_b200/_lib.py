@@ -39,6 +39,7 @@ SIGNATURES = {
     "rn_lanczos_update": (_i, [_vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rn_scale_inv": (_i, [_vp, _l, _vp, _vp, _vp]),
     "rn_lincomb": (_i, [_vp, _i, _l, _i, _vp, _l, _vp, _vp]),
+    "rn_lanczos_step": (_i, [_vp, _vp, _l, _vp, _i, _vp, _vp, _vp, _vp]),
     "rn_hop_apply_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
                                _vp, _i, _vp, _i, _vp, _vp, _i]),
     "rn_profile_begin": (_i, []),
@@ -72,8 +73,13 @@ def load():
     return lib
 
 
+_fast = {"lib": None, "dev": -1, "raw_stream": None}
+
+
 def get(device_index=None):
     """Library handle, initialised for the given (default: current) CUDA device."""
+    if device_index is None and _fast["lib"] is not None:
+        return _fast["lib"]
     import torch
     if not torch.cuda.is_available():
         raise RnError("renormalizer_b200 needs a CUDA device (B200, sm_100a); none is available "
@@ -87,6 +93,8 @@ def get(device_index=None):
         if err:
             raise RnError(f"rn_init failed on device {device_index} (cuda error {err})")
         _inited_devices[device_index] = (sm.value, cc.value)
+    _fast["lib"], _fast["dev"] = lib, device_index
+    _fast["raw_stream"] = getattr(torch._C, "_cuda_getCurrentRawStream", None)
     return lib
 
 
@@ -96,6 +104,11 @@ def check(err, what):
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the initialised device (fast path: no Python-side
+    device bookkeeping)."""
+    raw = _fast["raw_stream"]
+    if raw is not None:
+        return raw(_fast["dev"])
     import torch
     return torch.cuda.current_stream().cuda_stream
 

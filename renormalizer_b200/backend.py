@@ -13,8 +13,9 @@ class Backend:
         self.complex_dtype = torch.complex128
         self._canonical_atol = 1e-8      # backend.py:177-187
         self._canonical_rtol = 1e-5      # backend.py:190-200
-        # GEMM path of the contraction kernels: 0 = FP64 DMMA, 1 = tcgen05 int8 split
-        self.gemm_path = 0
+        # GEMM path of the contraction kernels: 1 = tcgen05 int8 split GEMM (FP64-accurate, default;
+        # contractions too small to fill a tile stay on the DMMA kernel), 0 = FP64 DMMA everywhere
+        self.gemm_path = 1
 
     @property
     def dtypes(self):

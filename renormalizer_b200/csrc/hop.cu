@@ -65,11 +65,60 @@ static int gemm_dispatch(cudaStream_t st, int path, int m, int n, int k, const d
   return err;
 }
 
+// A GEMM operand split into int8 digits, with its TMA descriptor (tcgen05 path).
+struct OzOperand {
+  signed char* q = nullptr;
+  double* scale = nullptr;
+  CUtensorMap map;
+  int rows = 0, K = 0, nslices = 0;
+};
+
+static int oz_alloc(cudaStream_t st, OzOperand& o, int rows, int K, int nslices) {
+  o.rows = rows; o.K = K; o.nslices = nslices;
+  RN_CHECK(cudaMallocAsync((void**)&o.q, ozaki_split_bytes(rows, K, nslices) + 16, st));
+  RN_CHECK(cudaMallocAsync((void**)&o.scale, sizeof(double) * (size_t)rows, st));
+  return ozaki_make_map(&o.map, o.q, (long)nslices * rows, (K + 15) & ~15);
+}
+
+static void oz_free(cudaStream_t st, OzOperand& o) {
+  if (o.q) cudaFreeAsync(o.q, st);
+  if (o.scale) cudaFreeAsync(o.scale, st);
+  o.q = nullptr; o.scale = nullptr;
+}
+
+static bool use_ozaki(int path, double m, double n, double k) {
+  return path == 1 && m * n * k >= g_ozaki_min_work && k <= 65536;
+}
+
+// GEMM with pre-split operands (either may be split on the fly from X when `fresh` is given)
+static int oz_gemm(cudaStream_t st, OzOperand& a, const double* a_fresh, long lda, OzOperand& b,
+                   const double* b_fresh, long ldb, double* C, long ldc) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int err;
+  if (a_fresh) { err = launch_ozaki_split(st, a_fresh, lda, a.rows, a.K, a.nslices, a.q, a.scale); if (err) return err; }
+  if (b_fresh) { err = launch_ozaki_split(st, b_fresh, ldb, b.rows, b.K, b.nslices, b.q, b.scale); if (err) return err; }
+  if (g_prof.on) {
+    RN_CHECK(cudaEventCreate(&e0));
+    RN_CHECK(cudaEventCreate(&e1));
+    RN_CHECK(cudaEventRecord(e0, st));
+  }
+  err = launch_ozaki_gemm_maps(st, a.rows, b.rows, a.K, a.nslices, &a.map, a.scale, &b.map, b.scale, C, ldc);
+  if (g_prof.on) {
+    RN_CHECK(cudaEventRecord(e1, st));
+    g_prof.ev.push_back(e0);
+    g_prof.ev.push_back(e1);
+    g_prof.flops += 2.0 * a.rows * b.rows * a.K;
+  }
+  return err;
+}
+
 }  // namespace rn
 
 using namespace rn;
 
 struct rn_hop_plan {
+  bool oz1 = false, oz3 = false;          // which GEMMs run on the tcgen05 split path
+  OzOperand ozL, ozC, ozT, ozR;
   int cplx, es, nsite, path;
   int La, Lb, Lc, Rl, Rf, Rk;
   int d1, g1, d2, g2;
@@ -129,6 +178,23 @@ extern "C" int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int
     RN_CHECK(cudaMallocAsync((void**)&p->T2, sizeof(double) * es * (size_t)La * p->d1 * p->g1 * w1_F * p->d2 * p->g2 * Rk, st));
   if (nsite == 2)
     RN_CHECK(cudaMallocAsync((void**)&p->T3, sizeof(double) * es * (size_t)La * p->d1 * p->g1 * p->d2 * p->g2 * w2_F * Rk, st));
+  {
+    const long rows3 = (long)La * p->d1 * p->g1 * p->d2 * p->g2;
+    const long K3 = (long)Rf * Rk * es;
+    p->oz1 = use_ozaki(path, (double)La * Lb, (double)n1 * es, (double)Lc * es);
+    p->oz3 = use_ozaki(path, (double)rows3, (double)Rl * es, (double)K3);
+    int err;
+    if (p->oz1) {
+      if ((err = oz_alloc(st, p->ozL, La * Lb, Lc * es, g_ozaki_slices))) return err;
+      if ((err = oz_alloc(st, p->ozC, (int)(n1 * es), Lc * es, g_ozaki_slices))) return err;
+      if ((err = launch_ozaki_split(st, p->L, (long)Lc * es, La * Lb, Lc * es, g_ozaki_slices, p->ozL.q, p->ozL.scale))) return err;
+    }
+    if (p->oz3) {
+      if ((err = oz_alloc(st, p->ozT, (int)rows3, (int)K3, g_ozaki_slices))) return err;
+      if ((err = oz_alloc(st, p->ozR, Rl * es, (int)K3, g_ozaki_slices))) return err;
+      if ((err = launch_ozaki_split(st, p->Rb, K3, Rl * es, (int)K3, g_ozaki_slices, p->ozR.q, p->ozR.scale))) return err;
+    }
+  }
   *out = p;
   return 0;
 }
@@ -142,8 +208,11 @@ extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void
   err = launch_pack(st, cplx, cplx ? 1 : 0, 0, (int)n1, p->Lc, c_in, 1, n1, p->Cb, (long)p->Lc * es);
   if (err) return err;
   // G1: T1[(a,b), (rest,k)]
-  err = gemm_dispatch(st, p->path, p->La * p->Lb, (int)(n1 * es), p->Lc * es, p->L, (long)p->Lc * es,
-                      p->Cb, (long)p->Lc * es, p->T1, n1 * es);
+  if (p->oz1)
+    err = oz_gemm(st, p->ozL, nullptr, 0, p->ozC, p->Cb, (long)p->Lc * es, p->T1, n1 * es);
+  else
+    err = gemm_dispatch(st, 0, p->La * p->Lb, (int)(n1 * es), p->Lc * es, p->L, (long)p->Lc * es,
+                        p->Cb, (long)p->Lc * es, p->T1, n1 * es);
   if (err) return err;
   const double* lastT = p->T1;
   long rows3 = p->La;           // rows of the G3 left operand
@@ -183,8 +252,11 @@ extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void
   }
   // G3: out[(rows3), l] = T[(rows3), (f,k)] . R[l, (f,k)]
   const long K3 = (long)p->Rf * p->Rk * es;
-  err = gemm_dispatch(st, p->path, (int)rows3, p->Rl * es, (int)K3, lastT, K3, p->Rb, K3,
-                      (double*)out, (long)p->Rl * es);
+  if (p->oz3)
+    err = oz_gemm(st, p->ozT, lastT, K3, p->ozR, nullptr, 0, (double*)out, (long)p->Rl * es);
+  else
+    err = gemm_dispatch(st, 0, (int)rows3, p->Rl * es, (int)K3, lastT, K3, p->Rb, K3,
+                        (double*)out, (long)p->Rl * es);
   p->launches += 1;
   return err;
 }
@@ -199,6 +271,7 @@ extern "C" int rn_hop_plan_destroy(rn_hop_plan* p, void* stream) {
   if (p->T2) cudaFreeAsync(p->T2, st);
   if (p->T3) cudaFreeAsync(p->T3, st);
   if (p->own_Rb && p->Rb) cudaFreeAsync(p->Rb, st);
+  oz_free(st, p->ozL); oz_free(st, p->ozC); oz_free(st, p->ozT); oz_free(st, p->ozR);
   delete p;
   return 0;
 }
@@ -329,4 +402,29 @@ extern "C" int rn_set_ozaki(int nslices, double min_work) {
   g_ozaki_slices = nslices;
   if (min_work >= 0) g_ozaki_min_work = min_work;
   return 0;
+}
+
+// ---- one fused Lanczos iteration (krylov.py:55-83 of the reference) ----------------------------
+//   w = H_eff v_j ; alpha_j = Re<v_j, w> ; w -= alpha_j v_j + beta_{j-1} v_{j-1} ; beta_j = |w| ;
+//   v_{j+1} = w / beta_j
+// V is the Krylov stack (row j = v_j, `n` elements per row), alpha/beta are device arrays of
+// (value, 0) pairs.  One C call per iteration keeps the host off the critical path.
+extern "C" int rn_multi_dot(void*, int, long, int, const double*, long, const double*, double*, double*);
+extern "C" int rn_lanczos_update(void*, long, double*, const double*, const double*, const double*,
+                                 const double*, double*, double*);
+extern "C" int rn_scale_inv(void*, long, const double*, const double*, double*);
+
+extern "C" int rn_lanczos_step(rn_hop_plan* plan, void* stream, long n, double* V, int j, double* alpha,
+                               double* beta, double* w, double* ws) {
+  const int es = plan->es;
+  const long ld = n * es;
+  double* vj = V + (long)j * ld;
+  int err = rn_hop_apply(plan, stream, vj, w);
+  if (err) return err;
+  err = rn_multi_dot(stream, plan->cplx, n, 1, vj, ld, w, ws, alpha + 2 * j);
+  if (err) return err;
+  err = rn_lanczos_update(stream, ld, w, vj, j > 0 ? vj - ld : nullptr, alpha + 2 * j,
+                          j > 0 ? beta + 2 * (j - 1) : nullptr, ws, beta + 2 * j);
+  if (err) return err;
+  return rn_scale_inv(stream, ld, w, beta + 2 * j, vj + ld);
 }

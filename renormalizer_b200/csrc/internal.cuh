@@ -1,5 +1,6 @@
 // Internal launcher declarations shared between the translation units of librn_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace rn {
@@ -28,6 +29,9 @@ int launch_wapply(cudaStream_t st, int cplx, const WApplyParams& p);
 size_t ozaki_split_bytes(int rows, int K, int nslices);
 int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int K, int nslices,
                        signed char* q, double* scale);
+int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp);
+int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, const CUtensorMap* tmA,
+                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc);
 int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
                       const double* sA, const signed char* qB, const double* sB, double* C, long ldc);
 

@@ -34,6 +34,7 @@ constexpr int OZ_THREADS = 320;
 constexpr int OZ_TILE_BYTES = OZ_BM * OZ_BK;             // 16 KiB per operand tile
 constexpr int OZ_SMEM = OZ_STAGES * 2 * OZ_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int OZ_MAX_SLICES = 8;
+constexpr int OZ_GROUP_M = 12;
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const double* __restrict__ sA, const double* __restrict__ sB,
                   double* __restrict__ C, int m, int n, long ldc, int rowsA, int rowsB, int kblocks,
-                  int nslices) {
+                  int nslices, int tiles_m, int tiles_n) {
   extern __shared__ unsigned char oz_smem_raw[];
   const uint32_t raw = smem_u32(oz_smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-B aligned operand ring
@@ -120,7 +121,20 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       reinterpret_cast<volatile uint32_t*>(oz_smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.y * OZ_BM, col0 = blockIdx.x * OZ_BN;
+  // grouped rasterisation: the ~148 tiles in flight form a block of OZ_GROUP_M row tiles by a
+  // dozen column tiles, so that the digit slices they share stay L2 resident and every slice is
+  // read from HBM about once
+  int tm, tn;
+  {
+    const int tile = blockIdx.x;
+    const int per_group = OZ_GROUP_M * tiles_n;
+    const int first_m = (tile / per_group) * OZ_GROUP_M;
+    const int gsize = (tiles_m - first_m) < OZ_GROUP_M ? (tiles_m - first_m) : OZ_GROUP_M;
+    const int in_group = tile % per_group;
+    tm = first_m + in_group % gsize;
+    tn = in_group / gsize;
+  }
+  const int row0 = tm * OZ_BM, col0 = tn * OZ_BN;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
@@ -275,6 +289,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
+int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp);
+
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -287,7 +303,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp) {
+int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)total_rows};
@@ -318,8 +334,8 @@ int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int 
   return 0;
 }
 
-int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
-                      const double* sA, const signed char* qB, const double* sB, double* C, long ldc) {
+int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, const CUtensorMap* tmA,
+                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc) {
   if (m <= 0 || n <= 0) return 0;
   if (nslices < 1 || nslices > OZ_MAX_SLICES) return (int)cudaErrorInvalidValue;
   static bool attr_set = false;
@@ -328,16 +344,24 @@ int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const s
     attr_set = true;
   }
   const int Kp = (K + 15) & ~15;
-  CUtensorMap tmA, tmB;
-  int err = make_map(&tmA, qA, (long)nslices * m, Kp);
-  if (err) return err;
-  err = make_map(&tmB, qB, (long)nslices * n, Kp);
-  if (err) return err;
   const int kblocks = (Kp + OZ_BK - 1) / OZ_BK;
-  dim3 grid((unsigned)ceil_div(n, OZ_BN), (unsigned)ceil_div(m, OZ_BM));
-  ozaki_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices);
+  const int tiles_m = (int)ceil_div(m, OZ_BM), tiles_n = (int)ceil_div(n, OZ_BN);
+  ozaki_gemm_kernel<<<(unsigned)(tiles_m * tiles_n), OZ_THREADS, OZ_SMEM, st>>>(
+      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n);
   RN_LAUNCH_CHECK();
   return 0;
+}
+
+int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
+                      const double* sA, const signed char* qB, const double* sB, double* C, long ldc) {
+  if (m <= 0 || n <= 0) return 0;
+  const int Kp = (K + 15) & ~15;
+  CUtensorMap tmA, tmB;
+  int err = ozaki_make_map(&tmA, qA, (long)nslices * m, Kp);
+  if (err) return err;
+  err = ozaki_make_map(&tmB, qB, (long)nslices * n, Kp);
+  if (err) return err;
+  return launch_ozaki_gemm_maps(st, m, n, K, nslices, &tmA, sA, &tmB, sB, C, ldc);
 }
 
 }  // namespace rn

@@ -52,7 +52,9 @@ class _Lanczos:
 
 def expm_krylov(Afunc, dt, vstart, block_size=50):
     """Return (expm(dt*A) @ vstart, number of A applications); A Hermitian, given as
-    Afunc(device vector) -> device vector."""
+    Afunc(device vector) -> device vector.  When Afunc is an H_eff callable of this package the
+    whole Lanczos iteration runs as one fused C call (rn_lanczos_step)."""
+    plan = getattr(Afunc, "plan", None)
     if not np.iscomplex(dt):
         dt = dt.real
     vstart = vstart.reshape(-1).contiguous()
@@ -72,24 +74,33 @@ def expm_krylov(Afunc, dt, vstart, block_size=50):
         b = beta_h[:m - 1, 0].copy()
         return st.combine(_coef(a, b, nrmv, dt), m), m
 
+    fused = plan is not None and plan.dtype == st.dtype and n > 1
+    wbuf = torch.empty(n, dtype=st.dtype, device=vstart.device) if fused else None
     for j in range(n):
-        w = Afunc(st.V[j])
-        w = w.reshape(-1)
-        if w.dtype != st.dtype:
-            w = w.to(st.dtype)
-        if not w.is_contiguous():
-            w = w.contiguous()
-        # alpha_j = Re <w, v_j>  (== Re <v_j, w>)
-        ops.multi_dot(st.V[j], w, 1, n, st.cplx, st.ws, out=st.alpha[j])
+        if fused and j < n - 1:
+            if st.V.shape[0] == j + 1:
+                st.grow()
+            ops.lanczos_step(plan, n, st.V, j, st.alpha, st.beta, wbuf, st.ws)
+            w = wbuf
+        else:
+            w = Afunc(st.V[j])
+            w = w.reshape(-1)
+            if w.dtype != st.dtype:
+                w = w.to(st.dtype)
+            if not w.is_contiguous():
+                w = w.contiguous()
+            # alpha_j = Re <w, v_j>  (== Re <v_j, w>)
+            ops.multi_dot(st.V[j], w, 1, n, st.cplx, st.ws, out=st.alpha[j])
         if j == n - 1:
             alpha_h = st.alpha[:j + 1].cpu().numpy()
             beta_h = st.beta[:j + 1].cpu().numpy()
             first_bad = _first_breakdown(beta_h[:j, 0], eps_break)
             return finish(j + 1 if first_bad is None else first_bad + 1)
-        if st.V.shape[0] == j + 1:
-            st.grow()
-        ops.lanczos_update(w, st.V[j], st.V[j - 1] if j > 0 else None, st.alpha[j],
-                           st.beta[j - 1] if j > 0 else None, st.ws, st.beta[j])
+        if not fused:
+            if st.V.shape[0] == j + 1:
+                st.grow()
+            ops.lanczos_update(w, st.V[j], st.V[j - 1] if j > 0 else None, st.alpha[j],
+                               st.beta[j - 1] if j > 0 else None, st.ws, st.beta[j])
         check = 3 < j and j % 2 == 0
         if check or j < 4 and n <= 8:
             alpha_h = st.alpha[:j + 1].cpu().numpy()
@@ -102,7 +113,8 @@ def expm_krylov(Afunc, dt, vstart, block_size=50):
             if res is not None and torch.allclose(res, new_res):
                 return new_res, j + 1
             res = new_res
-        ops.scale_inv(w, st.beta[j], st.V[j + 1])
+        if not fused:
+            ops.scale_inv(w, st.beta[j], st.V[j + 1])
     raise RuntimeError("unreachable")
 
 

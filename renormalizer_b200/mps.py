@@ -486,7 +486,7 @@ class Mps:
                 r_array = environ.read("R", imps + 1)
                 shape = list(mps[imps].shape)
                 hop = hop_expr_dtype(l_array, r_array, [mpo[imps]], shape, cdtype)
-                mps_t, j = expm_krylov(lambda y: hop(y), -1j * evolve_dt / 2, mps[imps].reshape(-1))
+                mps_t, j = expm_krylov(hop, -1j * evolve_dt / 2, mps[imps].reshape(-1))
                 hop.close()
                 local_steps.append(j)
                 mps_t = mps_t.reshape(shape)
@@ -502,7 +502,7 @@ class Mps:
                     u = u.contiguous()
                     shape_u = list(u.shape)
                     hop_u = hop_expr_dtype(l_array, r_array, [], shape_u, cdtype)
-                    back, j = expm_krylov(lambda y: hop_u(y), 1j * evolve_dt / 2, u.reshape(-1))
+                    back, j = expm_krylov(hop_u, 1j * evolve_dt / 2, u.reshape(-1))
                     hop_u.close()
                     local_steps.append(j)
                     mps[imps - 1] = ops.tensordot1(mps[imps - 1], back.reshape(shape_u))
@@ -513,7 +513,7 @@ class Mps:
                     l_array = environ.GetLR("L", imps, mps, mpo, itensor=l_array, method="System")
                     shape_svt = list(vt.shape)
                     hop_svt = hop_expr_dtype(l_array, r_array, [], shape_svt, cdtype)
-                    back, j = expm_krylov(lambda y: hop_svt(y), 1j * evolve_dt / 2, vt.reshape(-1))
+                    back, j = expm_krylov(hop_svt, 1j * evolve_dt / 2, vt.reshape(-1))
                     hop_svt.close()
                     local_steps.append(j)
                     mps[imps + 1] = ops.tensordot1(back.reshape(shape_svt), mps[imps + 1])

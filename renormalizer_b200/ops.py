@@ -374,3 +374,10 @@ def scale_inv(x, s, out):
     nd = x.numel() * _es(x)
     check(lib.rn_scale_inv(stream_ptr(), nd, _ptr(x), _ptr(s), _ptr(out)), "rn_scale_inv")
     LaunchCounter.add(1)
+
+
+def lanczos_step(plan, n, V, j, alpha, beta, w, ws):
+    """One fused Lanczos iteration on the Krylov stack V through rn_lanczos_step."""
+    check(plan.lib.rn_lanczos_step(plan.handle, stream_ptr(), n, _ptr(V), j, _ptr(alpha), _ptr(beta),
+                                   _ptr(w), _ptr(ws.ws)), "rn_lanczos_step")
+    LaunchCounter.add(plan.nlaunch + 5)

@@ -257,3 +257,50 @@ def test_tdvp_roundtrip_time_reversal():
     assert abs(abs(m0.conj().dot(m2)) - 1) < 1e-9
     e0, e1 = m0.expectation(mpo), m1.expectation(mpo)
     assert abs(e0 - e1) < 1e-9     # energy conservation of TDVP
+
+
+@pytest.fixture
+def tensor_path():
+    """Route EVERY contraction GEMM (however small) through the tcgen05 split path."""
+    from renormalizer_b200 import _lib
+    from renormalizer_b200.backend import backend
+    lib = _lib.get()
+    lib.rn_set_ozaki(7, 0.0)
+    backend.gemm_path = 1
+    yield
+    backend.gemm_path = 1
+    lib.rn_set_ozaki(7, 4.0e6)
+
+
+def test_tdvp_ps_golden_tensor_path(golden, tensor_path):
+    """Same golden TDVP-PS run with all GEMMs on tcgen05 (int8 split, 7 digits)."""
+    from renormalizer_b200.mpo import Mpo
+    g = golden("sbm")
+    mpo = Mpo(load_mpo(g))
+    sz = Mpo(load_mpo(g, "sigma_z"))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    dt = float(g["dt"])
+    szs, es = [mps.expectation(sz)], [mps.expectation(mpo)]
+    for i in range(int(g["nsteps"])):
+        mps = mps.evolve(mpo, dt)
+        szs.append(mps.expectation(sz))
+        es.append(mps.expectation(mpo))
+    assert np.abs(np.array(szs) - g["sigma_z_t"]).max() < E_TOL
+    assert np.abs(np.array(es) - g["energy_t"]).max() < E_TOL
+    refT = to_device_mps(load_oracle_mps(g, "mpsT"))
+    assert abs(abs(refT.conj().dot(mps)) - 1) < T_TOL
+
+
+def test_dmrg_holstein_golden_tensor_path(golden, tensor_path):
+    from renormalizer_b200.gs import optimize_mps
+    from renormalizer_b200.mpo import Mpo
+    g = golden("holstein")
+    mpo = Mpo(load_mpo(g))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    mps.optimize_config.procedure = [[int(a), float(b)] for a, b in g["procedure"]]
+    mps.optimize_config.method = "2site"
+    np.random.seed(99)
+    energies, opt = optimize_mps(mps, mpo)
+    ref = g["2site_energies"]
+    assert abs(energies[-1] - ref[-1]) < 1e-9
+    assert abs(opt.expectation(mpo) - float(g["2site_expectation"])) < 1e-9
