@@ -304,9 +304,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = _lib.LaunchCounter.count
+    l0 = _lib.LaunchCounter.total()
     ms = timed(step_device, args.steps)
-    launches = _lib.LaunchCounter.count - l0
+    launches = _lib.LaunchCounter.total() - l0
     clocks = sampler.stop() if rank == 0 else None
     sites_total = work["sites_per_step"] * args.steps * world
     value = sites_total / (ms * 1e-3)

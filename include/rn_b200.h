@@ -118,6 +118,10 @@ int rn_lanczos_update(void* stream, long nd, double* w, const double* vj, const 
 int rn_scale_inv(void* stream, long nd, const double* x, const double* s, double* out);
 int rn_lincomb(void* stream, int cplx, long n, int nvec, const double* V, long ld,
                const double* coef, double* out);
+/* xp.allclose(a, b) of krylov.py:79: *violations (device int) = number of thread blocks that saw an
+ * element with !(|a-b| <= atol + rtol |b|); 0 means close. */
+int rn_allclose(void* stream, int cplx, long n, const double* a, const double* b, double rtol,
+                double atol, int* violations);
 
 /* One fused Lanczos iteration on the Krylov stack V (row j = v_j, n elements per row):
  *   w = H_eff v_j; alpha[j] = Re<v_j,w>; w -= alpha[j] v_j + beta[j-1] v_{j-1}; beta[j] = |w|;
@@ -140,6 +144,8 @@ int rn_env_update_host(int cplx, int domain, const void* env, int Ea, int Eb, in
  * Between rn_profile_begin and rn_profile_end every contraction GEMM launch is bracketed by CUDA
  * events on its own stream; rn_profile_end returns the summed launch time, the summed
  * 2*m*n*k FLOPs and the launch count. */
+/* Number of kernels this library has launched so far in this process. */
+long rn_launch_count(void);
 int rn_profile_begin(void);
 int rn_profile_end(double* total_ms, double* total_flops, long* launches);
 

@@ -39,9 +39,11 @@ SIGNATURES = {
     "rn_lanczos_update": (_i, [_vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rn_scale_inv": (_i, [_vp, _l, _vp, _vp, _vp]),
     "rn_lincomb": (_i, [_vp, _i, _l, _i, _vp, _l, _vp, _vp]),
+    "rn_allclose": (_i, [_vp, _i, _l, _vp, _vp, c_double, c_double, _vp]),
     "rn_lanczos_step": (_i, [_vp, _vp, _l, _vp, _i, _vp, _vp, _vp, _vp]),
     "rn_hop_apply_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
                                _vp, _i, _vp, _i, _vp, _vp, _i]),
+    "rn_launch_count": (_l, []),
     "rn_profile_begin": (_i, []),
     "rn_profile_end": (_i, [POINTER(c_double), POINTER(c_double), POINTER(c_long)]),
     "rn_env_update_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i,
@@ -114,9 +116,13 @@ def stream_ptr():
 
 
 class LaunchCounter:
-    """Counts kernels launched through the C ABI (bench.py reports it as gpu_launches)."""
-    count = 0
+    """Kernels launched by librn_b200.so (counted inside the library at every launch site);
+    bench.py reports the difference over the timed region as gpu_launches."""
 
     @classmethod
-    def add(cls, n):
-        cls.count += n
+    def add(cls, n):          # kept for call-site compatibility; the library counts for itself
+        pass
+
+    @classmethod
+    def total(cls):
+        return int(load().rn_launch_count())

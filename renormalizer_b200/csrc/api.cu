@@ -5,7 +5,11 @@
 
 #include <vector>
 
+namespace rn { long g_launches = 0; }
+
 extern "C" const char* rn_version(void) { return "rn_b200 1"; }
+
+extern "C" long rn_launch_count(void) { return rn::g_launches; }
 
 extern "C" int rn_init(int device, int* sm_count, int* cc) {
   RN_CHECK(cudaSetDevice(device));

@@ -18,6 +18,8 @@
 
 namespace rn {
 
+extern long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+
 __host__ __device__ inline long ceil_div(long a, long b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -144,11 +144,11 @@ int launch_gemm_tn_f64(cudaStream_t st, int m, int n, int k, const double* A, lo
                      (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0);
   dim3 grid((unsigned)ceil_div(n, G_BN), (unsigned)ceil_div(m, G_BM), (unsigned)batch);
   if (vec16)
-    gemm_tn_f64_kernel<true><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(A, B, C, m, n, k, lda, ldb, ldc,
-                                                                    sA, sB, sC, accumulate);
+    { gemm_tn_f64_kernel<true><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(A, B, C, m, n, k, lda, ldb, ldc,
+                                                                    sA, sB, sC, accumulate); rn::g_launches++; }
   else
-    gemm_tn_f64_kernel<false><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(A, B, C, m, n, k, lda, ldb,
-                                                                     ldc, sA, sB, sC, accumulate);
+    { gemm_tn_f64_kernel<false><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(A, B, C, m, n, k, lda, ldb,
+                                                                     ldc, sA, sB, sC, accumulate); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }

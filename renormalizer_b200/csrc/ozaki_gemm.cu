@@ -329,7 +329,7 @@ int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int 
                        signed char* q, double* scale) {
   if (rows <= 0) return 0;
   const int Kp = (K + 15) & ~15;
-  ozaki_split_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale);
+  { ozaki_split_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -346,8 +346,8 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
   const int Kp = (K + 15) & ~15;
   const int kblocks = (Kp + OZ_BK - 1) / OZ_BK;
   const int tiles_m = (int)ceil_div(m, OZ_BM), tiles_n = (int)ceil_div(n, OZ_BN);
-  ozaki_gemm_kernel<<<(unsigned)(tiles_m * tiles_n), OZ_THREADS, OZ_SMEM, st>>>(
-      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n);
+  { ozaki_gemm_kernel<<<(unsigned)(tiles_m * tiles_n), OZ_THREADS, OZ_SMEM, st>>>(
+      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }

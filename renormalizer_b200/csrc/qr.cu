@@ -435,6 +435,233 @@ house_factor_flow_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, in
   }
 }
 
+
+// Same flag-chained elimination with the block's own columns (and the current reflector) held in
+// SHARED memory: the per-step critical path is then one L2 read of the pivot column, two
+// shared-memory passes and one global write of the freshly final column.
+template <bool CPLX>
+__global__ void __launch_bounds__(Q_THREADS)
+house_factor_flow_smem_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, int k, long ldt,
+                              typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
+                              double* __restrict__ rdiag, double* __restrict__ colinfo,
+                              int* __restrict__ ready, int cpb) {
+  using C = Cx<CPLX>;
+  using T = typename C::T;
+  extern __shared__ __align__(16) unsigned char qr_smem_raw[];
+  __shared__ double scratch[4 * 32];
+  T* own = reinterpret_cast<T*>(qr_smem_raw);          // [cpb][m]
+  T* vbuf = own + (long)cpb * m;                       // [m]
+  const int nb = gridDim.x, bid = blockIdx.x;
+  int nown = 0;
+  for (int c = bid; c < n; c += nb, ++nown)
+    for (int r = threadIdx.x; r < m; r += blockDim.x) own[(long)nown * m + r] = At[(long)c * ldt + r];
+  __syncthreads();
+  if (bid == 0) {
+    double ss[1] = {0.0};
+    for (int r = 1 + threadIdx.x; r < m; r += blockDim.x) ss[0] += C::abs2(own[r]);
+    block_sum<1>(ss, scratch);
+    publish_column<CPLX>(At, m, ldt, 0, ss[0], C::re(own[0]), C::im(own[0]), colinfo, ready, V, tau_out, rdiag);
+    __syncthreads();
+  }
+  for (int j = 0; j < k; ++j) {
+    // local index of the first owned column > j
+    int l0 = (j + 1 - bid + nb - 1) / nb;
+    if (j + 1 <= bid) l0 = 0;
+    if (l0 >= nown) break;
+    if (threadIdx.x == 0) {
+      while (ld_acquire_gpu(ready + j) == 0) { }
+    }
+    __syncthreads();
+    const T* colj = At + (long)j * ldt;
+    T tau, scale;
+    double beta;
+    reflector_from_info<CPLX>(colinfo + 4 * j, tau, scale, beta);
+    const T ctau = C::conj(tau);
+    for (int r = j + threadIdx.x; r < m; r += blockDim.x)
+      vbuf[r] = r == j ? C::one() : C::mul(ldcg_elt<CPLX>(colj + r), scale);
+    __syncthreads();
+    for (int l = l0; l < nown; ++l) {
+      const int c = bid + l * nb;
+      T* col = own + (long)l * m;
+      double acc[2] = {0.0, 0.0};
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T d = C::cmul(vbuf[r], col[r]);
+        acc[0] += C::re(d); acc[1] += C::im(d);
+      }
+      block_sum<2>(acc, scratch);
+      const T w = C::mul(ctau, C::make(acc[0], acc[1]));
+      const bool becomes_final = (c == j + 1) && (c < k);
+      double nfo[3] = {0.0, 0.0, 0.0};
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T x = C::sub(col[r], C::mul(vbuf[r], w));
+        col[r] = x;
+        if (becomes_final) {
+          if (r > c) nfo[0] += C::abs2(x);
+          else if (r == c) { nfo[1] = C::re(x); nfo[2] = C::im(x); }
+        }
+      }
+      if (becomes_final) {
+        __syncthreads();
+        T* gcol = At + (long)c * ldt;
+        for (int r = threadIdx.x; r < m; r += blockDim.x) gcol[r] = col[r];
+        block_sum<3>(nfo, scratch);
+        publish_column<CPLX>(At, m, ldt, c, nfo[0], nfo[1], nfo[2], colinfo, ready, V, tau_out, rdiag);
+      }
+      __syncthreads();
+    }
+  }
+  // columns that never become reflector sources (c >= k, wide matrices) and, for safety, every
+  // owned column: the shared copy is the truth
+  for (int l = 0; l < nown; ++l) {
+    const int c = bid + l * nb;
+    if (c >= k)
+      for (int r = threadIdx.x; r < m; r += blockDim.x) At[(long)c * ldt + r] = own[(long)l * m + r];
+  }
+}
+
+
+// ---- panel variant ----------------------------------------------------------------------------
+// Q_PB adjacent columns form a panel owned by one block and held in shared memory.  The owner
+// applies the reflectors of every earlier panel (Q_PB per flag hand-off, read from V), factors
+// its own panel locally, writes R / V / tau back and raises the panel's flag: n / Q_PB chained
+// hand-offs instead of n.
+constexpr int Q_PB = 4;
+
+template <bool CPLX>
+__global__ void __launch_bounds__(Q_THREADS)
+house_factor_panel_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, int k, long ldt,
+                          typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
+                          double* __restrict__ rdiag, int* __restrict__ ready) {
+  using C = Cx<CPLX>;
+  using T = typename C::T;
+  extern __shared__ __align__(16) unsigned char qr_smem_raw[];
+  __shared__ double scratch[2 * Q_PB * 32];
+  __shared__ T s_tau[Q_PB];
+  T* own = reinterpret_cast<T*>(qr_smem_raw);          // [Q_PB][m]
+  const int p = blockIdx.x;
+  const int c0 = p * Q_PB;
+  if (c0 >= n) return;
+  const int ncol = (n - c0) < Q_PB ? (n - c0) : Q_PB;
+  for (int a = 0; a < ncol; ++a)
+    for (int r = threadIdx.x; r < m; r += blockDim.x) own[(long)a * m + r] = At[(long)(c0 + a) * ldt + r];
+  __syncthreads();
+  // reflectors of the earlier panels
+  for (int q = 0; q < p; ++q) {
+    const int j0 = q * Q_PB;
+    if (j0 >= k) break;
+    const int nrefl = (k - j0) < Q_PB ? (k - j0) : Q_PB;
+    if (threadIdx.x == 0) {
+      while (ld_acquire_gpu(ready + q) == 0) { }
+    }
+    __syncthreads();
+    if (threadIdx.x < nrefl) s_tau[threadIdx.x] = ldcg_elt<CPLX>(tau_out + j0 + threadIdx.x);
+    for (int a = 0; a < nrefl; ++a) {
+      const int j = j0 + a;
+      const T* vj = V + (long)j * ldt;
+      double acc[2 * Q_PB];
+#pragma unroll
+      for (int i = 0; i < 2 * Q_PB; ++i) acc[i] = 0.0;
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T v = ldcg_elt<CPLX>(vj + r);
+#pragma unroll
+        for (int i = 0; i < Q_PB; ++i)
+          if (i < ncol) {
+            const T d = C::cmul(v, own[(long)i * m + r]);
+            acc[2 * i] += C::re(d);
+            acc[2 * i + 1] += C::im(d);
+          }
+      }
+      block_sum<2 * Q_PB>(acc, scratch);       // also publishes s_tau
+      const T ctau = C::conj(s_tau[a]);
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T v = ldcg_elt<CPLX>(vj + r);
+#pragma unroll
+        for (int i = 0; i < Q_PB; ++i)
+          if (i < ncol) {
+            const T w = C::mul(ctau, C::make(acc[2 * i], acc[2 * i + 1]));
+            own[(long)i * m + r] = C::sub(own[(long)i * m + r], C::mul(v, w));
+          }
+      }
+      __syncthreads();
+    }
+  }
+  // factor the own panel
+  for (int a = 0; a < ncol; ++a) {
+    const int j = c0 + a;
+    if (j >= k) break;
+    T* col = own + (long)a * m;
+    double nfo[3] = {0.0, 0.0, 0.0};
+    for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+      const T x = col[r];
+      if (r > j) nfo[0] += C::abs2(x);
+      else { nfo[1] = C::re(x); nfo[2] = C::im(x); }
+    }
+    block_sum<3>(nfo, scratch);
+    T tau, scale;
+    double beta;
+    {
+      const double ss = nfo[0], ar = nfo[1], ai = nfo[2];
+      if (ss == 0.0 && ai == 0.0) { tau = C::zero(); scale = C::zero(); beta = ar; }
+      else {
+        const double nrm = sqrt(ar * ar + ai * ai + ss);
+        beta = ar >= 0.0 ? -nrm : nrm;
+        tau = C::make((beta - ar) / beta, -ai / beta);
+        const double dr = ar - beta, di = ai, den = dr * dr + di * di;
+        scale = C::make(dr / den, -di / den);
+      }
+    }
+    // v_j -> V (global) and, scaled in place, below the diagonal of the shared column
+    T* vj = V + (long)j * ldt;
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+      T v;
+      if (r < j) v = C::zero();
+      else if (r == j) v = C::one();
+      else { v = C::mul(col[r], scale); col[r] = v; }
+      vj[r] = v;
+    }
+    if (threadIdx.x == 0) { tau_out[j] = tau; rdiag[j] = beta; }
+    __syncthreads();
+    if (a + 1 < ncol) {
+      double acc[2 * Q_PB];
+#pragma unroll
+      for (int i = 0; i < 2 * Q_PB; ++i) acc[i] = 0.0;
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T v = r == j ? C::one() : col[r];
+#pragma unroll
+        for (int i = 0; i < Q_PB; ++i)
+          if (i > a && i < ncol) {
+            const T d = C::cmul(v, own[(long)i * m + r]);
+            acc[2 * i] += C::re(d);
+            acc[2 * i + 1] += C::im(d);
+          }
+      }
+      block_sum<2 * Q_PB>(acc, scratch);
+      const T ctau = C::conj(tau);
+      for (int r = j + threadIdx.x; r < m; r += blockDim.x) {
+        const T v = r == j ? C::one() : col[r];
+#pragma unroll
+        for (int i = 0; i < Q_PB; ++i)
+          if (i > a && i < ncol) {
+            const T w = C::mul(ctau, C::make(acc[2 * i], acc[2 * i + 1]));
+            own[(long)i * m + r] = C::sub(own[(long)i * m + r], C::mul(v, w));
+          }
+      }
+      __syncthreads();
+    }
+  }
+  // R entries (rows <= column index) back to global; the part below the diagonal is not read again
+  for (int a = 0; a < ncol; ++a) {
+    const int c = c0 + a;
+    const int rmax = c < m ? c + 1 : m;
+    for (int r = threadIdx.x; r < rmax; r += blockDim.x) At[(long)c * ldt + r] = own[(long)a * m + r];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release_gpu(ready + p, 1);
+  }
+}
+
 // Q = H_0 ... H_{k-1} I, one WARP per column of Q (no block-level synchronisation): column c
 // needs reflectors c..0 only.  Reflectors are shared by all warps and stay L1/L2 resident.
 template <bool CPLX>
@@ -655,7 +882,7 @@ static int qr_colmajor(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, 
     RN_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     RN_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, house_factor_flow_kernel<CPLX>,
                                                            Q_THREADS, 0));
-    budget = coop ? sms * (per_sm > 2 ? 2 : per_sm) : 0;
+    budget = coop ? sms * (per_sm > 1 ? 1 : per_sm) : 0;
   }
   if (budget > 0) {
     int nb = n < budget ? n : budget;
@@ -667,22 +894,49 @@ static int qr_colmajor(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, 
     RN_CHECK(cudaMemsetAsync(ready, 0, sizeof(int) * (size_t)n, st));
     void* args[] = {(void*)&At, (void*)&m, (void*)&n, (void*)&k, (void*)&ldt, (void*)&V, (void*)&tau,
                     (void*)&rdiag, (void*)&colinfo, (void*)&ready};
-    if (g_qr_use_flow)
-      RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_flow_kernel<CPLX>, dim3(nb), dim3(Q_THREADS),
-                                           args, 0, st));
+    const int cpb = (int)ceil_div(n, nb);
+    const size_t smem_need = (size_t)(cpb + 1) * m * sizeof(typename Cx<CPLX>::T);
+    const int npanels = (int)ceil_div(n, Q_PB);
+    const size_t smem_panel = (size_t)Q_PB * m * sizeof(typename Cx<CPLX>::T);
+    if (g_qr_use_flow == 4 && npanels <= budget && smem_panel <= 200 * 1024) {
+      static bool attr_done[2] = {false, false};
+      if (!attr_done[CPLX ? 1 : 0]) {
+        RN_CHECK(cudaFuncSetAttribute(house_factor_panel_kernel<CPLX>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done[CPLX ? 1 : 0] = true;
+      }
+      void* args3[] = {(void*)&At, (void*)&m, (void*)&n, (void*)&k, (void*)&ldt, (void*)&V, (void*)&tau,
+                       (void*)&rdiag, (void*)&ready};
+      { RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_panel_kernel<CPLX>, dim3(npanels),
+                                             dim3(Q_THREADS), args3, smem_panel, st)); rn::g_launches++; }
+    } else if (g_qr_use_flow == 1 && smem_need <= 200 * 1024) {
+      static bool attr_done[2] = {false, false};
+      if (!attr_done[CPLX ? 1 : 0]) {
+        RN_CHECK(cudaFuncSetAttribute(house_factor_flow_smem_kernel<CPLX>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done[CPLX ? 1 : 0] = true;
+      }
+      int cpb_arg = cpb;
+      void* args2[] = {(void*)&At, (void*)&m, (void*)&n, (void*)&k, (void*)&ldt, (void*)&V, (void*)&tau,
+                       (void*)&rdiag, (void*)&colinfo, (void*)&ready, (void*)&cpb_arg};
+      { RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_flow_smem_kernel<CPLX>, dim3(nb), dim3(Q_THREADS),
+                                           args2, smem_need, st)); rn::g_launches++; }
+    } else if (g_qr_use_flow)
+      { RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_flow_kernel<CPLX>, dim3(nb), dim3(Q_THREADS),
+                                           args, 0, st)); rn::g_launches++; }
     else
-      RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_coop_kernel<CPLX>, dim3(nb), dim3(Q_THREADS),
-                                           args, 0, st));
+      { RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_coop_kernel<CPLX>, dim3(nb), dim3(Q_THREADS),
+                                           args, 0, st)); rn::g_launches++; }
     if (g_qr_warp_formq == 1)
-      house_formq_warp_kernel<CPLX><<<(unsigned)ceil_div(k, 8), 256, 0, st>>>(Qt, m, k, ldt, V, tau);
+      { house_formq_warp_kernel<CPLX><<<(unsigned)ceil_div(k, 8), 256, 0, st>>>(Qt, m, k, ldt, V, tau); rn::g_launches++; }
     else if (g_qr_warp_formq == 2)
-      house_formq_kernel<CPLX><<<(unsigned)ceil_div(k, Q_CPB), Q_THREADS, 0, st>>>(Qt, m, k, ldt, V, tau);
+      { house_formq_kernel<CPLX><<<(unsigned)ceil_div(k, Q_CPB), Q_THREADS, 0, st>>>(Qt, m, k, ldt, V, tau); rn::g_launches++; }
     else {
       typename Cx<CPLX>::T* Tall = nullptr;
       const int ngroups = (int)ceil_div(k, Q_GB);
       RN_CHECK(cudaMallocAsync((void**)&Tall, sizeof(typename Cx<CPLX>::T) * (size_t)ngroups * Q_GB * Q_GB, st));
-      house_build_t_kernel<CPLX><<<ngroups, QT_THREADS, 0, st>>>(V, tau, m, k, ldt, Tall);
-      house_formq_blocked_kernel<CPLX><<<(unsigned)ceil_div(k, Q_QCOLS), Q_THREADS, 0, st>>>(Qt, m, k, ldt, V, Tall);
+      { house_build_t_kernel<CPLX><<<ngroups, QT_THREADS, 0, st>>>(V, tau, m, k, ldt, Tall); rn::g_launches++; }
+      { house_formq_blocked_kernel<CPLX><<<(unsigned)ceil_div(k, Q_QCOLS), Q_THREADS, 0, st>>>(Qt, m, k, ldt, V, Tall); rn::g_launches++; }
       RN_CHECK(cudaFreeAsync(Tall, st));
     }
     RN_LAUNCH_CHECK();
@@ -693,15 +947,15 @@ static int qr_colmajor(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, 
   for (int j = 0; j < k; ++j) {
     int nb = (int)ceil_div(n - j - 1, Q_CPB);
     if (nb < 1) nb = 1;
-    house_step_kernel<CPLX><<<nb, Q_THREADS, 0, st>>>(At, m, n, ldt, j, V, tau, rdiag);
+    { house_step_kernel<CPLX><<<nb, Q_THREADS, 0, st>>>(At, m, n, ldt, j, V, tau, rdiag); rn::g_launches++; }
   }
   RN_LAUNCH_CHECK();
   int nbi = (int)ceil_div((long)k * m, 256);
   if (nbi > 1184) nbi = 1184;
-  set_identity_rows_kernel<CPLX><<<nbi, 256, 0, st>>>(Qt, m, k, ldt);
+  { set_identity_rows_kernel<CPLX><<<nbi, 256, 0, st>>>(Qt, m, k, ldt); rn::g_launches++; }
   for (int j = k - 1; j >= 0; --j) {
     const int nb = (int)ceil_div(k - j, Q_CPB);
-    house_applyq_kernel<CPLX><<<nb, Q_THREADS, 0, st>>>(Qt, m, k, ldt, j, V, tau);
+    { house_applyq_kernel<CPLX><<<nb, Q_THREADS, 0, st>>>(Qt, m, k, ldt, j, V, tau); rn::g_launches++; }
   }
   RN_LAUNCH_CHECK();
   return 0;
@@ -738,7 +992,7 @@ static int qr_driver(cudaStream_t st, int lq, int m, int n, const void* A, long 
   if (err) return err;
   int nbr = (int)ceil_div((long)k * nt, 256);
   if (nbr > 1184) nbr = 1184;
-  extract_r_kernel<CPLX><<<nbr, 256, 0, st>>>(At, rdiag, nt, k, ldt, (T*)R, ldr, lq);
+  { extract_r_kernel<CPLX><<<nbr, 256, 0, st>>>(At, rdiag, nt, k, ldt, (T*)R, ldr, lq); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   if (!lq) {
     // Q[r][c] = Qt[c][r]

@@ -128,7 +128,7 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
   if (err) return err;
   int nbe = (int)ceil_div((long)nt * nt, 256);
   if (nbe > 1184) nbe = 1184;
-  jacobi_eye_kernel<CPLX><<<nbe, 256, 0, st>>>(Vw, nt, ldv);
+  { jacobi_eye_kernel<CPLX><<<nbe, 256, 0, st>>>(Vw, nt, ldv); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   const int N = (nt + 1) & ~1;  // even number of players
   const double tol = sqrt((double)mt) * 2.220446049250313e-16;
@@ -137,7 +137,7 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
     for (; sweeps < max_sweeps; ++sweeps) {
       RN_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
       for (int round = 0; round < N - 1; ++round)
-        jacobi_round_kernel<CPLX><<<N / 2, J_THREADS, 0, st>>>(At, Vw, mt, nt, nt, ldt, ldv, round, N, tol, flag);
+        { jacobi_round_kernel<CPLX><<<N / 2, J_THREADS, 0, st>>>(At, Vw, mt, nt, nt, ldt, ldv, round, N, tol, flag); rn::g_launches++; }
       RN_LAUNCH_CHECK();
       int h = 0;
       RN_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -146,7 +146,7 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
     }
   }
   if (sweeps_out) *sweeps_out = sweeps;
-  jacobi_finalize_kernel<CPLX><<<nt, J_THREADS, 0, st>>>(At, mt, ldt, S);
+  { jacobi_finalize_kernel<CPLX><<<nt, J_THREADS, 0, st>>>(At, mt, ldt, S); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   if (!wide) {
     // U[r][c] = At[c][r];  Vh[c][j] = conj(V[j][c]) = conj(Vw[c][j])

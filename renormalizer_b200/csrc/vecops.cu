@@ -107,6 +107,30 @@ lincomb_kernel(long n, int nvec, const double* __restrict__ V, long ld,
   }
 }
 
+// violations += #{k : !(|a_k - b_k| <= atol + rtol |b_k|)}   (numpy.allclose semantics, NaN counts)
+template <bool CPLX>
+__global__ void __launch_bounds__(V_THREADS)
+allclose_kernel(long n, const double* __restrict__ a, const double* __restrict__ b, double rtol,
+                double atol, int* __restrict__ violations) {
+  int bad = 0;
+  const long step = (long)gridDim.x * blockDim.x;
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
+    double diff, mag;
+    if constexpr (CPLX) {
+      const double2 x = reinterpret_cast<const double2*>(a)[k];
+      const double2 y = reinterpret_cast<const double2*>(b)[k];
+      diff = hypot(x.x - y.x, x.y - y.y);
+      mag = hypot(y.x, y.y);
+    } else {
+      diff = fabs(a[k] - b[k]);
+      mag = fabs(b[k]);
+    }
+    if (!(diff <= atol + rtol * mag)) bad = 1;
+  }
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0 && bad) atomicAdd(violations, 1);
+}
+
 static inline int nblocks_for(long n) {
   long nb = ceil_div(n, (long)V_THREADS * 4);
   if (nb < 1) nb = 1;
@@ -124,10 +148,10 @@ extern "C" int rn_multi_dot(void* stream, int cplx, long n, int nvec, const doub
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = nblocks_for(n);
   dim3 grid(nb, nvec);
-  if (cplx) multi_dot_partial_kernel<true><<<grid, V_THREADS, 0, st>>>(V, ld, x, n, ws);
-  else multi_dot_partial_kernel<false><<<grid, V_THREADS, 0, st>>>(V, ld, x, n, ws);
+  if (cplx) { multi_dot_partial_kernel<true><<<grid, V_THREADS, 0, st>>>(V, ld, x, n, ws); rn::g_launches++; }
+  else { multi_dot_partial_kernel<false><<<grid, V_THREADS, 0, st>>>(V, ld, x, n, ws); rn::g_launches++; }
   RN_LAUNCH_CHECK();
-  reduce_final_kernel<<<nvec, 32, 0, st>>>(ws, nb, out, 0);
+  { reduce_final_kernel<<<nvec, 32, 0, st>>>(ws, nb, out, 0); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -137,9 +161,9 @@ extern "C" int rn_lanczos_update(void* stream, long nd, double* w, const double*
                                  double* ws, double* beta_out) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = nblocks_for(nd);
-  lanczos_update_kernel<<<nb, V_THREADS, 0, st>>>(nd, w, vj, vjm1, alpha, beta_prev, ws);
+  { lanczos_update_kernel<<<nb, V_THREADS, 0, st>>>(nd, w, vj, vjm1, alpha, beta_prev, ws); rn::g_launches++; }
   RN_LAUNCH_CHECK();
-  reduce_final_kernel<<<1, 32, 0, st>>>(ws, nb, beta_out, 1);
+  { reduce_final_kernel<<<1, 32, 0, st>>>(ws, nb, beta_out, 1); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -147,7 +171,7 @@ extern "C" int rn_lanczos_update(void* stream, long nd, double* w, const double*
 extern "C" int rn_scale_inv(void* stream, long nd, const double* x, const double* s, double* out) {
   cudaStream_t st = (cudaStream_t)stream;
   int nb = nblocks_for(nd) * 4;
-  scale_inv_kernel<<<nb, V_THREADS, 0, st>>>(nd, x, s, out);
+  { scale_inv_kernel<<<nb, V_THREADS, 0, st>>>(nd, x, s, out); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -158,8 +182,20 @@ extern "C" int rn_lincomb(void* stream, int cplx, long n, int nvec, const double
   int nb = (int)ceil_div(n, V_THREADS);
   if (nb > 148 * 8) nb = 148 * 8;
   if (nb < 1) nb = 1;
-  if (cplx) lincomb_kernel<true><<<nb, V_THREADS, 0, st>>>(n, nvec, V, ld, coef, out);
-  else lincomb_kernel<false><<<nb, V_THREADS, 0, st>>>(n, nvec, V, ld, coef, out);
+  if (cplx) { lincomb_kernel<true><<<nb, V_THREADS, 0, st>>>(n, nvec, V, ld, coef, out); rn::g_launches++; }
+  else { lincomb_kernel<false><<<nb, V_THREADS, 0, st>>>(n, nvec, V, ld, coef, out); rn::g_launches++; }
+  RN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rn_allclose(void* stream, int cplx, long n, const double* a, const double* b, double rtol,
+                           double atol, int* violations) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RN_CHECK(cudaMemsetAsync(violations, 0, sizeof(int), st));
+  if (n <= 0) return 0;
+  int nb = nblocks_for(n) * 2;
+  if (cplx) { allclose_kernel<true><<<nb, V_THREADS, 0, st>>>(n, a, b, rtol, atol, violations); rn::g_launches++; }
+  else { allclose_kernel<false><<<nb, V_THREADS, 0, st>>>(n, a, b, rtol, atol, violations); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }

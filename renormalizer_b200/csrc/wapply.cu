@@ -82,8 +82,8 @@ int launch_wapply(cudaStream_t st, int cplx, const WApplyParams& in_p) {
     max_set[cplx] = 200 * 1024;
   }
   dim3 grid((unsigned)p.X, (unsigned)ceil_div(p.Y, yt));
-  if (cplx) wapply_kernel<true><<<grid, 256, smem, st>>>(p);
-  else wapply_kernel<false><<<grid, 256, smem, st>>>(p);
+  if (cplx) { wapply_kernel<true><<<grid, 256, smem, st>>>(p); rn::g_launches++; }
+  else { wapply_kernel<false><<<grid, 256, smem, st>>>(p); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }

@@ -110,7 +110,7 @@ def expm_krylov(Afunc, dt, vstart, block_size=50):
                 return finish(first_bad + 1)
         if check:
             new_res = st.combine(_coef(alpha_h[:j + 1, 0].copy(), beta_h[:j, 0].copy(), nrmv, dt), j + 1)
-            if res is not None and torch.allclose(res, new_res):
+            if res is not None and ops.allclose(res, new_res):
                 return new_res, j + 1
             res = new_res
         if not fused:

@@ -381,3 +381,13 @@ def lanczos_step(plan, n, V, j, alpha, beta, w, ws):
     check(plan.lib.rn_lanczos_step(plan.handle, stream_ptr(), n, _ptr(V), j, _ptr(alpha), _ptr(beta),
                                    _ptr(w), _ptr(ws.ws)), "rn_lanczos_step")
     LaunchCounter.add(plan.nlaunch + 5)
+
+
+def allclose(a, b, rtol=1e-5, atol=1e-8, flag=None):
+    """numpy.allclose(a, b) for two device vectors of the same dtype (one D2H int read)."""
+    lib = _lib.get()
+    if flag is None:
+        flag = torch.empty(1, dtype=torch.int32, device=a.device)
+    check(lib.rn_allclose(stream_ptr(), _is_cplx(a), a.numel(), _ptr(a), _ptr(b), rtol, atol, _ptr(flag)),
+          "rn_allclose")
+    return int(flag.item()) == 0
