@@ -129,6 +129,18 @@ int rn_allclose(void* stream, int cplx, long n, const double* a, const double* b
 int rn_lanczos_step(rn_hop_plan* plan, void* stream, long n, double* V, int j, double* alpha,
                     double* beta, double* w, double* ws);
 
+/* The whole of expm_krylov(Afunc, dt, vstart) (renormalizer/lib/krylov/krylov.py:28-84) for an
+ * H_eff plan: out = expm(dt * H_eff) v_in with dt = dt_re + i dt_im (dt_im must be 0 for real
+ * vectors), same Lanczos recurrence and the same stopping rules as the reference (breakdown
+ * 100 n eps, numpy.allclose of successive approximations every second step from the fifth on);
+ * *nsteps_out = number of H_eff applications used.  The loop runs in C++, the tridiagonal
+ * eigenproblem and the convergence test on the device; the host reads three integers per check.
+ * Returns cudaErrorNotSupported when the Krylov dimension would exceed rn_krylov_max_dim()
+ * (the caller then uses the step-wise entry points above). */
+int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n, const void* v_in,
+                   double dt_re, double dt_im, void* out, int* nsteps_out);
+int rn_krylov_max_dim(void);
+
 /* ---- host-buffer entry points (what a NumPy-side caller binds) -------------------------------
  * Same contractions with HOST pointers: inputs are copied to the device, the kernels above run,
  * the result is copied back and the stream is synchronised.  W is the dense MPO site(s)

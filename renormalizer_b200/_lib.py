@@ -41,6 +41,8 @@ SIGNATURES = {
     "rn_lincomb": (_i, [_vp, _i, _l, _i, _vp, _l, _vp, _vp]),
     "rn_allclose": (_i, [_vp, _i, _l, _vp, _vp, c_double, c_double, _vp]),
     "rn_lanczos_step": (_i, [_vp, _vp, _l, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rn_expm_krylov": (_i, [_vp, _vp, _i, _l, _vp, c_double, c_double, _vp, POINTER(_i)]),
+    "rn_krylov_max_dim": (_i, []),
     "rn_hop_apply_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
                                _vp, _i, _vp, _i, _vp, _vp, _i]),
     "rn_launch_count": (_l, []),

@@ -118,6 +118,7 @@ using namespace rn;
 
 struct rn_hop_plan {
   bool oz1 = false, oz3 = false;          // which GEMMs run on the tcgen05 split path
+  bool fuse_w = false;                    // last MPO application writes G3's digits directly
   OzOperand ozL, ozC, ozT, ozR;
   int cplx, es, nsite, path;
   int La, Lb, Lc, Rl, Rf, Rk;
@@ -160,65 +161,52 @@ extern "C" int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int
   if (wlast != Rf) { delete p; return (int)cudaErrorInvalidValue; }
   p->rest = (long)p->d1 * p->g1 * p->d2 * p->g2;
   const long n1 = p->rest * Rk;  // columns of T1 (elements)
-  p->Cb = p->T1 = p->T2 = p->T3 = nullptr;
+  p->Cb = p->T1 = p->T2 = p->T3 = nullptr; p->Rb = nullptr; p->own_Rb = false;
+  const long rows3 = (long)La * p->d1 * p->g1 * p->d2 * p->g2;
+  const long K3 = (long)Rf * Rk * es;
+  p->oz1 = use_ozaki(path, (double)La * Lb, (double)n1 * es, (double)Lc * es);
+  p->oz3 = use_ozaki(path, (double)rows3, (double)Rl * es, (double)K3);
   RN_CHECK(cudaMallocAsync((void**)&p->T1, sizeof(double) * es * (size_t)La * Lb * n1, st));
-  if (cplx) {
-    RN_CHECK(cudaMallocAsync((void**)&p->Cb, sizeof(double) * 4 * (size_t)n1 * Lc, st));
-    RN_CHECK(cudaMallocAsync((void**)&p->Rb, sizeof(double) * 4 * (size_t)Rl * Rf * Rk, st));
-    p->own_Rb = true;
-    int err = launch_pack(st, 1, 1, 0, Rl, Rf * Rk, R, (long)Rf * Rk, 1, p->Rb, (long)Rf * Rk * 2);
-    if (err) return err;
-  } else {
-    // real: "math B"[c,(rest,k)] still has to be transposed to K-major for G1
-    RN_CHECK(cudaMallocAsync((void**)&p->Cb, sizeof(double) * (size_t)n1 * Lc, st));
-    p->Rb = (double*)R;
-    p->own_Rb = false;
+  int err;
+  if (!p->oz1)   // DMMA path: "math B"[c,(rest,k)] transposed to K-major (and realified) per apply
+    RN_CHECK(cudaMallocAsync((void**)&p->Cb, sizeof(double) * es * es * (size_t)n1 * Lc, st));
+  if (!p->oz3) {
+    if (cplx) {
+      RN_CHECK(cudaMallocAsync((void**)&p->Rb, sizeof(double) * 4 * (size_t)Rl * Rf * Rk, st));
+      p->own_Rb = true;
+      if ((err = launch_pack(st, 1, 1, 0, Rl, Rf * Rk, R, (long)Rf * Rk, 1, p->Rb, (long)Rf * Rk * 2))) return err;
+    } else {
+      p->Rb = (double*)R;
+    }
   }
-  if (nsite >= 1)
+  // the last MPO application can emit G3's left-operand digits directly when a row fits in smem
+  const int lastF = nsite == 2 ? w2_F : w1_F;
+  p->fuse_w = p->oz3 && nsite >= 1 && (size_t)lastF * Rk * es * sizeof(double) <= 160 * 1024;
+  if (nsite >= 1 && !(nsite == 1 && p->fuse_w))
     RN_CHECK(cudaMallocAsync((void**)&p->T2, sizeof(double) * es * (size_t)La * p->d1 * p->g1 * w1_F * p->d2 * p->g2 * Rk, st));
-  if (nsite == 2)
+  if (nsite == 2 && !p->fuse_w)
     RN_CHECK(cudaMallocAsync((void**)&p->T3, sizeof(double) * es * (size_t)La * p->d1 * p->g1 * p->d2 * p->g2 * w2_F * Rk, st));
-  {
-    const long rows3 = (long)La * p->d1 * p->g1 * p->d2 * p->g2;
-    const long K3 = (long)Rf * Rk * es;
-    p->oz1 = use_ozaki(path, (double)La * Lb, (double)n1 * es, (double)Lc * es);
-    p->oz3 = use_ozaki(path, (double)rows3, (double)Rl * es, (double)K3);
-    int err;
-    if (p->oz1) {
-      if ((err = oz_alloc(st, p->ozL, La * Lb, Lc * es, g_ozaki_slices))) return err;
-      if ((err = oz_alloc(st, p->ozC, (int)(n1 * es), Lc * es, g_ozaki_slices))) return err;
-      if ((err = launch_ozaki_split(st, p->L, (long)Lc * es, La * Lb, Lc * es, g_ozaki_slices, p->ozL.q, p->ozL.scale))) return err;
-    }
-    if (p->oz3) {
-      if ((err = oz_alloc(st, p->ozT, (int)rows3, (int)K3, g_ozaki_slices))) return err;
-      if ((err = oz_alloc(st, p->ozR, Rl * es, (int)K3, g_ozaki_slices))) return err;
-      if ((err = launch_ozaki_split(st, p->Rb, K3, Rl * es, (int)K3, g_ozaki_slices, p->ozR.q, p->ozR.scale))) return err;
-    }
+  if (p->oz1) {
+    if ((err = oz_alloc(st, p->ozL, La * Lb, Lc * es, g_ozaki_slices))) return err;
+    if ((err = oz_alloc(st, p->ozC, (int)(n1 * es), Lc * es, g_ozaki_slices))) return err;
+    if ((err = launch_ozaki_split(st, p->L, (long)Lc * es, La * Lb, Lc * es, g_ozaki_slices, p->ozL.q, p->ozL.scale))) return err;
+  }
+  if (p->oz3) {
+    if ((err = oz_alloc(st, p->ozT, (int)rows3, (int)K3, g_ozaki_slices))) return err;
+    if ((err = oz_alloc(st, p->ozR, Rl * es, (int)K3, g_ozaki_slices))) return err;
+    if (cplx)
+      err = launch_ozaki_split_bform(st, (const double*)R, K3, Rl, Rf * Rk, g_ozaki_slices, 0, p->ozR.q, p->ozR.scale);
+    else
+      err = launch_ozaki_split(st, (const double*)R, K3, Rl, (int)K3, g_ozaki_slices, p->ozR.q, p->ozR.scale);
+    if (err) return err;
   }
   *out = p;
   return 0;
 }
 
-extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void* out) {
-  cudaStream_t st = (cudaStream_t)stream;
-  const int es = p->es, cplx = p->cplx;
-  const long n1 = p->rest * p->Rk;
-  int err;
-  // "math B"[c, (rest,k)] -> K-major (and realified when complex)
-  err = launch_pack(st, cplx, cplx ? 1 : 0, 0, (int)n1, p->Lc, c_in, 1, n1, p->Cb, (long)p->Lc * es);
-  if (err) return err;
-  // G1: T1[(a,b), (rest,k)]
-  if (p->oz1)
-    err = oz_gemm(st, p->ozL, nullptr, 0, p->ozC, p->Cb, (long)p->Lc * es, p->T1, n1 * es);
-  else
-    err = gemm_dispatch(st, 0, p->La * p->Lb, (int)(n1 * es), p->Lc * es, p->L, (long)p->Lc * es,
-                        p->Cb, (long)p->Lc * es, p->T1, n1 * es);
-  if (err) return err;
-  const double* lastT = p->T1;
-  long rows3 = p->La;           // rows of the G3 left operand
-  p->launches += 2;
-  if (p->nsite >= 1) {
-    WApplyParams w;
+// MPO application number `which` (0: W1 on T1, 1: W2 on T2) as wapply parameters
+static void hop_wparams(const rn_hop_plan* p, int which, WApplyParams& w) {
+  if (which == 0) {
     const long Yin = (long)p->g1 * p->d2 * p->g2 * p->Rk;   // y = (g1, h, g2, k)
     const long Y2 = (long)p->d2 * p->g2 * p->Rk;
     w.in = p->T1; w.out = p->T2;
@@ -227,15 +215,8 @@ extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void
     w.D = p->w1.D; w.F = p->w1.F; w.Y2 = (int)Y2;
     w.osx = (long)p->d1 * p->g1 * p->w1.F * Y2; w.osd = (long)p->g1 * p->w1.F * Y2;
     w.osy1 = (long)p->w1.F * Y2; w.osf = Y2; w.osy2 = 1;
-    w.rowptr = p->w1.rowptr; w.ent_pq = p->w1.pq; w.ent_val = p->w1.val; w.YT = 0; w.order = 0;
-    err = launch_wapply(st, cplx, w);
-    if (err) return err;
-    lastT = p->T2;
-    rows3 = (long)p->La * p->d1 * p->g1;
-    p->launches += 1;
-  }
-  if (p->nsite == 2) {
-    WApplyParams w;
+    w.rowptr = p->w1.rowptr; w.ent_pq = p->w1.pq; w.ent_val = p->w1.val;
+  } else {
     const long Yin = (long)p->g2 * p->Rk;   // y = (g2, k)
     w.in = p->T2; w.out = p->T3;
     w.X = (int)((long)p->La * p->d1 * p->g1); w.P = p->w2.P; w.Q = p->w2.Q; w.Y = (int)Yin;
@@ -243,17 +224,53 @@ extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void
     w.D = p->w2.D; w.F = p->w2.F; w.Y2 = p->Rk;
     w.osx = (long)p->d2 * p->g2 * p->w2.F * p->Rk; w.osd = (long)p->g2 * p->w2.F * p->Rk;
     w.osy1 = (long)p->w2.F * p->Rk; w.osf = p->Rk; w.osy2 = 1;
-    w.rowptr = p->w2.rowptr; w.ent_pq = p->w2.pq; w.ent_val = p->w2.val; w.YT = 0; w.order = 0;
-    err = launch_wapply(st, cplx, w);
+    w.rowptr = p->w2.rowptr; w.ent_pq = p->w2.pq; w.ent_val = p->w2.val;
+  }
+  w.YT = 0; w.order = 0;
+}
+
+extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void* out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int es = p->es, cplx = p->cplx;
+  const long n1 = p->rest * p->Rk;
+  int err;
+  // G1: T1[(a,b), (rest,k)] = L[(a,b),c] . C[c,(rest,k)]; the right operand is the transposed
+  // (and, when complex, realified) view of c_in
+  if (p->oz1) {
+    err = launch_ozaki_split_t(st, cplx, c_in, n1, (int)n1, p->Lc, p->ozC.nslices, p->ozC.q, p->ozC.scale);
     if (err) return err;
-    lastT = p->T3;
-    rows3 = (long)p->La * p->d1 * p->g1 * p->d2 * p->g2;
+    err = oz_gemm(st, p->ozL, nullptr, 0, p->ozC, nullptr, 0, p->T1, n1 * es);
+  } else {
+    err = launch_pack(st, cplx, cplx ? 1 : 0, 0, (int)n1, p->Lc, c_in, 1, n1, p->Cb, (long)p->Lc * es);
+    if (err) return err;
+    err = gemm_dispatch(st, 0, p->La * p->Lb, (int)(n1 * es), p->Lc * es, p->L, (long)p->Lc * es,
+                        p->Cb, (long)p->Lc * es, p->T1, n1 * es);
+  }
+  if (err) return err;
+  const double* lastT = p->T1;
+  long rows3 = p->La;           // rows of the G3 left operand
+  p->launches += 2;
+  bool digits_ready = false;    // ozT already holds the digits of G3's left operand
+  for (int which = 0; which < p->nsite; ++which) {
+    WApplyParams w;
+    hop_wparams(p, which, w);
+    const bool last = which == p->nsite - 1;
+    if (last && p->fuse_w) {
+      err = launch_wapply_split(st, cplx, w, p->ozT.nslices, p->ozT.q, p->ozT.scale);
+      if (err != 0) return err > 1 ? err : (int)cudaErrorInvalidValue;   // fit was checked at creation
+      digits_ready = true;
+    } else {
+      err = launch_wapply(st, cplx, w);
+      if (err) return err;
+    }
+    lastT = (const double*)w.out;
+    rows3 *= (which == 0 ? (long)p->d1 * p->g1 : (long)p->d2 * p->g2);
     p->launches += 1;
   }
   // G3: out[(rows3), l] = T[(rows3), (f,k)] . R[l, (f,k)]
   const long K3 = (long)p->Rf * p->Rk * es;
   if (p->oz3)
-    err = oz_gemm(st, p->ozT, lastT, K3, p->ozR, nullptr, 0, (double*)out, (long)p->Rl * es);
+    err = oz_gemm(st, p->ozT, digits_ready ? nullptr : lastT, K3, p->ozR, nullptr, 0, (double*)out, (long)p->Rl * es);
   else
     err = gemm_dispatch(st, 0, (int)rows3, p->Rl * es, (int)K3, lastT, K3, p->Rb, K3,
                         (double*)out, (long)p->Rl * es);

@@ -29,6 +29,12 @@ int launch_wapply(cudaStream_t st, int cplx, const WApplyParams& p);
 size_t ozaki_split_bytes(int rows, int K, int nslices);
 int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int K, int nslices,
                        signed char* q, double* scale);
+int launch_ozaki_split_bform(cudaStream_t st, const double* X, long ld, int crows, int ccols, int nslices,
+                             int conj_left, signed char* q, double* scale);
+int launch_ozaki_split_t(cudaStream_t st, int cplx, const void* src, long s_col, int rows, int cols,
+                         int nslices, signed char* q, double* scale);
+int launch_wapply_split(cudaStream_t st, int cplx, const WApplyParams& p, int nslices, signed char* q,
+                        double* scale);
 int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp);
 int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, const CUtensorMap* tmA,
                            const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc);

@@ -1,0 +1,350 @@
+// expm(dt * H_eff) v by the Lanczos / Krylov method, with the whole iteration driven from C++ and
+// the convergence test evaluated on the device (reference: renormalizer/lib/krylov/krylov.py:15-84,
+// _expm_krylov and expm_krylov).
+//
+// Per Lanczos step j the stream sees   H_eff apply (hop.cu)  ->  <v_j, w> partials  ->
+//   [alpha_j]  w -= alpha_j v_j + beta_{j-1} v_{j-1}, |w|^2 partials  ->  [beta_j]  v_{j+1} = w / beta_j
+// (the bracketed scalars are reduced redundantly, in a fixed order, by every block of the kernel
+// that needs them, so no separate reduction launch and no host round trip).  At the reference's
+// own check points (every second step from the fifth on) a single-block kernel diagonalises the
+// tridiagonal matrix (implicit QL, EISPACK tql2), forms the coefficients
+//   u (|v| exp(dt w) u_0)  and the candidate result is compared with the previous one on the
+// device (numpy.allclose semantics); the host reads three integers.
+#include "common.cuh"
+#include "rn_b200.h"
+#include "internal.cuh"
+
+#include <math.h>
+
+namespace rn {
+
+constexpr int K_THREADS = 256;
+constexpr int K_MAXM = 64;          // largest Krylov dimension the device eigen-solver handles
+
+// ---- scalar reduced redundantly by every block: sum of nb (re, im) partial pairs, fixed order
+__device__ __forceinline__ double block_reduce_partials(const double* __restrict__ partial, int nb,
+                                                        double* sh) {
+  if (threadIdx.x < 32) {
+    double re = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 32) re += partial[(long)b * 2];
+    re = warp_sum(re);
+    if (threadIdx.x == 0) *sh = re;
+  }
+  __syncthreads();
+  return *sh;
+}
+
+// w -= alpha v_j + beta_prev v_{j-1}, alpha = sum of the <v_j, w> partials (real part);
+// partial_out[b] = this block's share of |w|^2.  Block 0 stores alpha.
+__global__ void __launch_bounds__(K_THREADS)
+lanczos_axpy_kernel(long nd, double* __restrict__ w, const double* __restrict__ vj,
+                    const double* __restrict__ vjm1, const double* __restrict__ partial_in, int nb_in,
+                    const double* __restrict__ beta_prev, double* __restrict__ alpha_out,
+                    double* __restrict__ partial_out) {
+  __shared__ double sh_alpha;
+  __shared__ double scratch[64];
+  const double alpha = block_reduce_partials(partial_in, nb_in, &sh_alpha);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { alpha_out[0] = alpha; alpha_out[1] = 0.0; }
+  const double beta = vjm1 != nullptr ? beta_prev[0] : 0.0;
+  double acc[2] = {0.0, 0.0};
+  const long step = (long)gridDim.x * blockDim.x;
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += step) {
+    double t = w[k] - alpha * vj[k];
+    if (vjm1 != nullptr) t -= beta * vjm1[k];
+    w[k] = t;
+    acc[0] += t * t;
+  }
+  block_sum<2>(acc, scratch);
+  if (threadIdx.x == 0) {
+    partial_out[(long)blockIdx.x * 2 + 0] = acc[0];
+    partial_out[(long)blockIdx.x * 2 + 1] = 0.0;
+  }
+}
+
+// out = x / sqrt(sum of partials); block 0 stores the norm (value, 0).
+__global__ void __launch_bounds__(K_THREADS)
+lanczos_scale_kernel(long nd, const double* __restrict__ x, const double* __restrict__ partial_in,
+                     int nb_in, double* __restrict__ norm_out, double* __restrict__ out) {
+  __shared__ double sh;
+  double s = block_reduce_partials(partial_in, nb_in, &sh);
+  s = sqrt(s > 0.0 ? s : 0.0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { norm_out[0] = s; norm_out[1] = 0.0; }
+  const double inv = 1.0 / s;
+  const long step = (long)gridDim.x * blockDim.x;
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += step) out[k] = x[k] * inv;
+}
+
+// partial[b] = this block's share of <v, x> (complex: conj(v) x), as in vecops.cu
+template <bool CPLX>
+__global__ void __launch_bounds__(K_THREADS)
+dot_partial_kernel(const double* __restrict__ v, const double* __restrict__ x, long n,
+                   double* __restrict__ partial) {
+  __shared__ double scratch[64];
+  double acc[2] = {0.0, 0.0};
+  const long step = (long)gridDim.x * blockDim.x;
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
+    if constexpr (CPLX) {
+      const double2 a = reinterpret_cast<const double2*>(v)[k];
+      const double2 b = reinterpret_cast<const double2*>(x)[k];
+      acc[0] += a.x * b.x + a.y * b.y;
+      acc[1] += a.x * b.y - a.y * b.x;
+    } else {
+      acc[0] += v[k] * x[k];
+    }
+  }
+  block_sum<2>(acc, scratch);
+  if (threadIdx.x == 0) {
+    partial[(long)blockIdx.x * 2 + 0] = acc[0];
+    partial[(long)blockIdx.x * 2 + 1] = acc[1];
+  }
+}
+
+// ---- tridiagonal eigenproblem + expm coefficients, one block ------------------------------------
+// Every thread runs the (cheap, scalar) implicit-QL recurrence of EISPACK's tql2 on private
+// copies of the diagonal / off-diagonal; thread t additionally carries row t of the eigenvector
+// matrix, so the O(m^2) rotations of the accumulation are spread over the threads without any
+// synchronisation.  status[0] = 1 when a beta below eps_break was found (the Krylov space is
+// invariant; the result is final), status[1] = Krylov dimension m used, coef[0..mtry) = complex
+// coefficients (zero beyond m).
+__global__ void __launch_bounds__(K_MAXM)
+krylov_coef_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int mtry,
+                   int nbeta_check, const double* __restrict__ nrm_ptr, double dt_re, double dt_im,
+                   double eps_break, double* __restrict__ coef, int* __restrict__ status) {
+  __shared__ double z0[K_MAXM];
+  const int t = threadIdx.x;
+  int m = mtry, broke = 0;
+  for (int i = 0; i < nbeta_check; ++i) {
+    const double b = beta[2 * i];
+    if (!(b >= eps_break)) { m = i + 1; broke = 1; break; }
+  }
+  double d[K_MAXM], e[K_MAXM], z[K_MAXM];
+  for (int i = 0; i < K_MAXM; ++i) {
+    d[i] = i < m ? alpha[2 * i] : 0.0;
+    e[i] = i < m - 1 ? beta[2 * i] : 0.0;
+    z[i] = i == t ? 1.0 : 0.0;
+  }
+  const double eps = 2.220446049250313e-16;
+  double f = 0.0, tst1 = 0.0;
+  for (int l = 0; l < m; ++l) {
+    tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+    int mm = l;
+    while (mm < m) {
+      if (fabs(e[mm]) <= eps * tst1) break;
+      ++mm;
+    }
+    if (mm >= m) mm = m - 1;
+    if (mm > l) {
+      int iter = 0;
+      do {
+        ++iter;
+        double g = d[l];
+        double p = (d[l + 1] - g) / (2.0 * e[l]);
+        double r = hypot(p, 1.0);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r);
+        d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < m; ++i) d[i] -= h;
+        f += h;
+        p = d[mm];
+        double c = 1.0, c2 = c, c3 = c;
+        const double el1 = e[l + 1];
+        double s = 0.0, s2 = 0.0;
+        for (int i = mm - 1; i >= l; --i) {
+          c3 = c2; c2 = c; s2 = s;
+          g = c * e[i];
+          h = c * p;
+          r = hypot(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          const double zh = z[i + 1];
+          z[i + 1] = s * z[i] + c * zh;
+          z[i] = c * z[i] - s * zh;
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+      } while (fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] += f;
+    e[l] = 0.0;
+  }
+  if (t == 0)
+    for (int k = 0; k < m; ++k) z0[k] = z[k];
+  __syncthreads();
+  const double nrm = nrm_ptr[0];
+  if (t < mtry) {
+    double cr = 0.0, ci = 0.0;
+    if (t < m) {
+      for (int k = 0; k < m; ++k) {
+        const double mag = nrm * exp(dt_re * d[k]) * z0[k] * z[k];
+        double sn, cs;
+        sincos(dt_im * d[k], &sn, &cs);
+        cr += mag * cs;
+        ci += mag * sn;
+      }
+    }
+    coef[2 * t] = cr;
+    coef[2 * t + 1] = ci;
+  }
+  if (t == 0) { status[0] = broke; status[1] = m; }
+}
+
+// out[k] = sum_{i < min(nvec, *nvec_ptr)} coef[i] V_i[k]; coef holds complex pairs (imaginary parts
+// ignored for real vectors).
+template <bool CPLX>
+__global__ void __launch_bounds__(K_THREADS)
+krylov_combine_kernel(long n, int nvec, const int* __restrict__ nvec_ptr, const double* __restrict__ V,
+                      long ld, const double* __restrict__ coef, double* __restrict__ out) {
+  if (nvec_ptr != nullptr) { const int lim = nvec_ptr[0]; if (lim < nvec) nvec = lim; }
+  const long step = (long)gridDim.x * blockDim.x;
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
+    if constexpr (CPLX) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int i = 0; i < nvec; ++i) {
+        const double2 c = reinterpret_cast<const double2*>(coef)[i];
+        const double2 v = reinterpret_cast<const double2*>(V + (long)i * ld)[k];
+        acc.x += c.x * v.x - c.y * v.y;
+        acc.y += c.x * v.y + c.y * v.x;
+      }
+      reinterpret_cast<double2*>(out)[k] = acc;
+    } else {
+      double acc = 0.0;
+      for (int i = 0; i < nvec; ++i) acc += coef[2 * i] * V[(long)i * ld + k];
+      out[k] = acc;
+    }
+  }
+}
+
+static inline int k_nblocks(long n) {
+  long nb = ceil_div(n, (long)K_THREADS * 4);
+  if (nb < 1) nb = 1;
+  if (nb > RN_REDUCE_BLOCKS) nb = RN_REDUCE_BLOCKS;
+  return (int)nb;
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" int rn_allclose(void*, int, long, const double*, const double*, double, double, int*);
+
+extern "C" int rn_krylov_max_dim(void) { return K_MAXM; }
+
+extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n, const void* v_in,
+                              double dt_re, double dt_im, void* out, int* nsteps_out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0 || plan == nullptr) return (int)cudaErrorInvalidValue;
+  const int es = cplx ? 2 : 1;
+  if (!cplx && dt_im != 0.0) return (int)cudaErrorInvalidValue;
+  const long nd = n * es;
+  const int nb = k_nblocks(nd), nbdot = k_nblocks(n);
+  const int nbs = nb * 4 > 1184 ? 1184 : nb * 4;
+  const double eps_break = 100.0 * (double)n * 2.220446049250313e-16;
+
+  // device scratch: one allocation, carved up
+  int cap = 14;                                     // Krylov vectors the stack can hold
+  if ((long)cap > n) cap = (int)n;
+  if (cap < 2) cap = 2;
+  double* V = nullptr;
+  RN_CHECK(cudaMallocAsync((void**)&V, sizeof(double) * (size_t)nd * cap, st));
+  const size_t small_doubles = (size_t)2 * (K_MAXM + 2) * 2 /*alpha,beta*/ + 2 * K_MAXM /*coef*/ +
+                               4 * RN_REDUCE_BLOCKS /*two partial arrays*/ + 2 /*nrm*/ + 8;
+  double* small = nullptr;
+  RN_CHECK(cudaMallocAsync((void**)&small, sizeof(double) * small_doubles + 64, st));
+  double* alpha = small;
+  double* beta = alpha + 2 * (K_MAXM + 2);
+  double* coef = beta + 2 * (K_MAXM + 2);
+  double* pa = coef + 2 * K_MAXM;
+  double* pb = pa + 2 * RN_REDUCE_BLOCKS;
+  double* nrm = pb + 2 * RN_REDUCE_BLOCKS;
+  int* status = reinterpret_cast<int*>(nrm + 2);    // [broke, m, violations]
+  double *w = nullptr, *res[2] = {nullptr, nullptr};
+  RN_CHECK(cudaMallocAsync((void**)&w, sizeof(double) * (size_t)nd * 3, st));
+  res[0] = w + nd; res[1] = w + 2 * nd;
+  static int* h_status = nullptr;                   // pinned landing zone for the three flags
+  if (!h_status) RN_CHECK(cudaMallocHost((void**)&h_status, 64));
+
+  int err = 0, result_buf = -1, nsteps = 0;
+  auto cleanup = [&]() {
+    cudaFreeAsync(V, st); cudaFreeAsync(small, st); cudaFreeAsync(w, st);
+  };
+#define KRY_TRY(x) do { err = (x); if (err) { cleanup(); return err; } } while (0)
+#define KRY_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { cleanup(); return (int)_e; } } while (0)
+
+  // |v| and V_0 = v / |v|
+  if (cplx) { dot_partial_kernel<true><<<nbdot, K_THREADS, 0, st>>>((const double*)v_in, (const double*)v_in, n, pa); rn::g_launches++; }
+  else { dot_partial_kernel<false><<<nbdot, K_THREADS, 0, st>>>((const double*)v_in, (const double*)v_in, n, pa); rn::g_launches++; }
+  { lanczos_scale_kernel<<<nbs, K_THREADS, 0, st>>>(nd, (const double*)v_in, pa, nbdot, nrm, V); rn::g_launches++; }
+  KRY_CUDA(cudaGetLastError());
+
+  auto combine = [&](int mtry, int nbeta_check, double* dst) -> int {
+    { krylov_coef_kernel<<<1, K_MAXM, 0, st>>>(alpha, beta, mtry, nbeta_check, nrm, dt_re, dt_im, eps_break, coef, status); rn::g_launches++; }
+    int nbc = (int)ceil_div(n, K_THREADS);
+    if (nbc > 148 * 8) nbc = 148 * 8;
+    if (cplx) { krylov_combine_kernel<true><<<nbc, K_THREADS, 0, st>>>(n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
+    else { krylov_combine_kernel<false><<<nbc, K_THREADS, 0, st>>>(n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
+    return (int)cudaGetLastError();
+  };
+  auto fetch_status = [&]() -> int {
+    cudaError_t e = cudaMemcpyAsync(h_status, status, 3 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(st);
+  };
+
+  int have_prev = 0, cur = 0;
+  for (long j = 0; j < n; ++j) {
+    if (j + 1 > K_MAXM) { cleanup(); return (int)cudaErrorNotSupported; }   // caller falls back
+    double* vj = V + j * nd;
+    KRY_TRY(rn_hop_apply(plan, st, vj, w));
+    if (cplx) { dot_partial_kernel<true><<<nbdot, K_THREADS, 0, st>>>(vj, w, n, pa); rn::g_launches++; }
+    else { dot_partial_kernel<false><<<nbdot, K_THREADS, 0, st>>>(vj, w, n, pa); rn::g_launches++; }
+    if (j == n - 1) {
+      // the Krylov space is the full space: alpha_j only, then the final projection
+      { lanczos_axpy_kernel<<<1, K_THREADS, 0, st>>>(0, w, vj, nullptr, pa, nbdot, nullptr, alpha + 2 * j, pb); rn::g_launches++; }
+      KRY_TRY(combine((int)j + 1, (int)j, res[cur]));
+      KRY_TRY(fetch_status());
+      result_buf = cur; nsteps = h_status[1];
+      break;
+    }
+    if (j + 2 > cap) {
+      // grow the Krylov stack (the reference grows in blocks of 50, krylov.py:63-68)
+      int ncap = cap * 2;
+      if ((long)ncap > n) ncap = (int)n;
+      double* V2 = nullptr;
+      KRY_CUDA(cudaMallocAsync((void**)&V2, sizeof(double) * (size_t)nd * ncap, st));
+      KRY_CUDA(cudaMemcpyAsync(V2, V, sizeof(double) * (size_t)nd * (j + 1), cudaMemcpyDeviceToDevice, st));
+      cudaFreeAsync(V, st);
+      V = V2; cap = ncap; vj = V + j * nd;
+    }
+    { lanczos_axpy_kernel<<<nb, K_THREADS, 0, st>>>(nd, w, vj, j > 0 ? vj - nd : nullptr, pa, nbdot,
+                                                   j > 0 ? beta + 2 * (j - 1) : nullptr, alpha + 2 * j, pb); rn::g_launches++; }
+    { lanczos_scale_kernel<<<nbs, K_THREADS, 0, st>>>(nd, w, pb, nb, beta + 2 * j, vj + nd); rn::g_launches++; }
+    KRY_CUDA(cudaGetLastError());
+    const bool check = j > 3 && (j % 2 == 0);
+    if (check) {
+      KRY_TRY(combine((int)j + 1, (int)j + 1, res[cur]));
+      if (have_prev) KRY_TRY(rn_allclose(st, cplx, n, res[cur ^ 1], res[cur], 1e-5, 1e-8, status + 2));
+      KRY_TRY(fetch_status());
+      if (h_status[0]) { result_buf = cur; nsteps = h_status[1]; break; }
+      if (have_prev && h_status[2] == 0) { result_buf = cur; nsteps = (int)j + 1; break; }
+      have_prev = 1; cur ^= 1;
+    } else if (j < 4 && n <= 8) {
+      // tiny problems: the reference tests beta_j at every step
+      KRY_TRY(combine((int)j + 1, (int)j + 1, res[cur]));
+      KRY_TRY(fetch_status());
+      if (h_status[0]) { result_buf = cur; nsteps = h_status[1]; break; }
+    }
+  }
+  if (result_buf < 0) { cleanup(); return (int)cudaErrorUnknown; }
+  KRY_CUDA(cudaMemcpyAsync(out, res[result_buf], sizeof(double) * (size_t)nd, cudaMemcpyDeviceToDevice, st));
+  if (nsteps_out) *nsteps_out = nsteps;
+  cleanup();
+#undef KRY_TRY
+#undef KRY_CUDA
+  return 0;
+}

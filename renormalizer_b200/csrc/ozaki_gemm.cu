@@ -25,6 +25,7 @@
 #include "internal.cuh"
 
 #include <cuda.h>
+#include <type_traits>
 
 namespace rn {
 
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const double* __restrict__ sA, const double* __restrict__ sB,
                   double* __restrict__ C, int m, int n, long ldc, int rowsA, int rowsB, int kblocks,
-                  int nslices, int tiles_m, int tiles_n) {
+                  int nslices, int tiles_m, int tiles_n, int ksplit, int kb_per_split,
+                  double* __restrict__ partial, int* __restrict__ counters) {
   extern __shared__ unsigned char oz_smem_raw[];
   const uint32_t raw = smem_u32(oz_smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-B aligned operand ring
@@ -126,7 +128,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // read from HBM about once
   int tm, tn;
   {
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x / ksplit;
     const int per_group = OZ_GROUP_M * tiles_n;
     const int first_m = (tile / per_group) * OZ_GROUP_M;
     const int gsize = (tiles_m - first_m) < OZ_GROUP_M ? (tiles_m - first_m) : OZ_GROUP_M;
@@ -135,6 +137,11 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tn = in_group / gsize;
   }
   const int row0 = tm * OZ_BM, col0 = tn * OZ_BN;
+  // split-K: this CTA contracts K blocks [kb0, kb1) only; the last CTA of a tile to finish sums
+  // the partial tiles in split order (deterministic) and writes C
+  const int split = blockIdx.x % ksplit;
+  const int kb0 = split * kb_per_split;
+  const int kb1 = (kb0 + kb_per_split) < kblocks ? (kb0 + kb_per_split) : kblocks;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
@@ -157,7 +164,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int g = 0; g < nslices; ++g)
         for (int s = 0; s <= g; ++s) {
           const int t = g - s;
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int st = it % OZ_STAGES;
             const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
             mbar_wait(empty_bar + 8 * st, ph ^ 1u);
@@ -180,7 +187,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t d_tmem = tmem_base + acc * OZ_BN;
         uint32_t accumulate = 0;
         for (int s = 0; s <= g; ++s)
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int st = it % OZ_STAGES;
             const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
             mbar_wait(full_bar + 8 * st, ph);
@@ -224,17 +231,59 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
     }
-    const int grow = row0 + r;
-    if (grow < m) {
-      const double sa = sA[grow];
-      double* crow = C + (long)grow * ldc;
-      const int cbase = col0 + half * 64;
+    if (ksplit > 1) {
+      const int tile_id = blockIdx.x / ksplit;
+      double* mine = partial + ((long)tile_id * ksplit + split) * (OZ_BM * OZ_BN) + r * OZ_BN + half * 64;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const int gc = cbase + i;
-        if (gc < n) crow[gc] = sum[i] * sa * sB[gc];
+      for (int i = 0; i < 64; i += 2) *reinterpret_cast<double2*>(mine + i) = make_double2(sum[i], sum[i + 1]);
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ew == 0 && lane == 0) {
+        const int old = atomicAdd(counters + tile_id, 1);
+        const int last = old == ksplit - 1;
+        if (last) counters[tile_id] = 0;          // self-resetting: ready for the next launch
+        *tmem_slot_ptr = (uint32_t)last;          // tmem_base was read by every thread long ago
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool last = *tmem_slot_ptr != 0u;
+      if (last) {
+        __threadfence();
+        const double* p0 = partial + (long)tile_id * ksplit * (OZ_BM * OZ_BN) + r * OZ_BN + half * 64;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) sum[i] = 0.0;
+        for (int sp = 0; sp < ksplit; ++sp) {
+          const double* ps = p0 + (long)sp * (OZ_BM * OZ_BN);
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(ps + i));
+            sum[i] += v.x; sum[i + 1] += v.y;
+          }
+        }
+      }
+      if (!last) goto oz_epilogue_done;
+    }
+    {
+      const int grow = row0 + r;
+      if (grow < m) {
+        const double sa = sA[grow];
+        double* crow = C + (long)grow * ldc;
+        const int cbase = col0 + half * 64;
+        if (cbase + 64 <= n && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const double2 sb = *reinterpret_cast<const double2*>(sB + cbase + i);
+            *reinterpret_cast<double2*>(crow + cbase + i) = make_double2(sum[i] * sa * sb.x, sum[i + 1] * sa * sb.y);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const int gc = cbase + i;
+            if (gc < n) crow[gc] = sum[i] * sa * sB[gc];
+          }
+        }
       }
     }
+  oz_epilogue_done:;
   }
   tc_fence_before();
   __syncthreads();
@@ -245,11 +294,36 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // --------------------------------------------------------------------------------------- split
-// One warp per row: row maximum -> power-of-two scale -> S int8 digits per element.
+// Digit extraction shared by the split kernels: v (already divided by the row scale and
+// multiplied by 64) -> S signed digits, most significant first.  All steps are exact in FP64.
+__device__ __forceinline__ void oz_digits(double rr, int nslices, signed char (&d)[OZ_MAX_SLICES]) {
+#pragma unroll
+  for (int s = 0; s < OZ_MAX_SLICES; ++s) {
+    if (s < nslices) {
+      const double qd = rint(rr);
+      d[s] = (signed char)(int)qd;
+      rr = (rr - qd) * 128.0;
+    }
+  }
+}
+
+__device__ __forceinline__ void oz_scale_of(double mx, double& sc, double& inv64) {
+  int e = 0;
+  if (mx > 0.0) frexp(mx, &e);                      // mx = f * 2^e, f in [0.5, 1)
+  sc = scalbn(1.0, e);
+  inv64 = scalbn(1.0, 6 - e);
+}
+
+// One warp per source row, K contiguous.
+//   FORM 0: real row of K doubles -> one digit row.
+//   FORM 1: complex row of K/2 interleaved elements -> the two rows (2r, 2r+1) of its 2x2 real
+//           representation ("B-form" of pack.cu):  (re, -im | im, re), with conj_left
+//           (re, +im | im, -re).  K counts doubles.
 // q layout: [slice][row][Kp] bytes, Kp a multiple of 16 (zero padded).
+template <int FORM>
 __global__ void __launch_bounds__(256)
 ozaki_split_kernel(const double* __restrict__ X, long ld, int rows, int K, int Kp, int nslices,
-                   signed char* __restrict__ q, double* __restrict__ scale) {
+                   signed char* __restrict__ q, double* __restrict__ scale, int conj_left) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -258,32 +332,195 @@ ozaki_split_kernel(const double* __restrict__ X, long ld, int rows, int K, int K
   for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(x[k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  int e = 0;
-  if (mx > 0.0) frexp(mx, &e);                      // mx = f * 2^e, f in [0.5, 1)
-  const double sc = scalbn(1.0, e);
-  const double inv = scalbn(1.0, -e);
-  if (lane == 0) scale[row] = sc;
-  const long slice_stride = (long)rows * Kp;
-  signed char* qrow = q + (long)row * Kp;
+  double sc, inv64;
+  oz_scale_of(mx, sc, inv64);
+  const int out_rows = FORM == 1 ? 2 * rows : rows;
+  if (lane == 0) {
+    if (FORM == 1) { scale[2 * row] = sc; scale[2 * row + 1] = sc; }
+    else scale[row] = sc;
+  }
+  const long slice_stride = (long)out_rows * Kp;
+  signed char* qrow = q + (long)(FORM == 1 ? 2 * row : row) * Kp;
   for (int k0 = lane * 4; k0 < Kp; k0 += 128) {
-    double rr[4];
+    signed char dg[4][OZ_MAX_SLICES];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) rr[j] = (k0 + j < K) ? x[k0 + j] * inv * 64.0 : 0.0;
-    for (int s = 0; s < nslices; ++s) {
-      char4 out;
-      signed char* o = reinterpret_cast<signed char*>(&out);
+    for (int j = 0; j < 4; ++j) oz_digits((k0 + j < K) ? x[k0 + j] * inv64 : 0.0, nslices, dg[j]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double qd = rint(rr[j]);
-        o[j] = (signed char)(int)qd;
-        rr[j] = (rr[j] - qd) * 128.0;
+    for (int s = 0; s < OZ_MAX_SLICES; ++s) {
+      if (s >= nslices) break;
+      if (FORM == 0) {
+        char4 o = make_char4(dg[0][s], dg[1][s], dg[2][s], dg[3][s]);
+        *reinterpret_cast<char4*>(qrow + s * slice_stride + k0) = o;
+      } else {
+        // (re0, im0, re1, im1) -> row 2r: (re0, -+im0, re1, -+im1); row 2r+1: (im0, +-re0, im1, +-re1)
+        const signed char sg = conj_left ? 1 : -1;
+        char4 o0 = make_char4(dg[0][s], (signed char)(sg * dg[1][s]), dg[2][s], (signed char)(sg * dg[3][s]));
+        char4 o1 = make_char4(dg[1][s], (signed char)(-sg * dg[0][s]), dg[3][s], (signed char)(-sg * dg[2][s]));
+        *reinterpret_cast<char4*>(qrow + s * slice_stride + k0) = o0;
+        *reinterpret_cast<char4*>(qrow + s * slice_stride + Kp + k0) = o1;
       }
-      *reinterpret_cast<char4*>(qrow + s * slice_stride + k0) = out;
+    }
+  }
+}
+
+// Transposing split: logical operand P[r][c] = src[r + c*s_col] (rows contiguous in memory, the
+// contraction index strided) -- the centre tensor C[c,(rest,k)] seen as the K-major right operand
+// of G1.  Fuses pack.cu's transpose / realification with the digit split: coalesced reads along
+// r, digits staged in shared memory, coalesced 64-byte row segments out.
+//   CPLX: out rows (2r, 2r+1) = B-form, K = 2*cols;  real: out row r, K = cols.
+// grid = (ceil(rows/32), CY): every block scans all of c for the row maxima (L2 resident) and
+// emits the digits of its own share of the c range.
+constexpr int OZT_RT = 32;        // source rows per block
+constexpr int OZT_KB = 64;        // digit bytes per out row and chunk
+constexpr int OZT_LD = OZT_KB + 4;
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+ozaki_split_t_kernel(const double* __restrict__ src, long s_col, int rows, int cols, int Kp, int nslices,
+                     signed char* __restrict__ q, double* __restrict__ scale, int chunks_per_block) {
+  constexpr int CT = CPLX ? 32 : 64;             // source columns per chunk
+  constexpr int OR = CPLX ? 2 * OZT_RT : OZT_RT; // out rows per block
+  __shared__ __align__(16) signed char stage[OZ_MAX_SLICES * OR * OZT_LD];
+  __shared__ double smax[8][OZT_RT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * OZT_RT + lane;
+  const bool rok = r < rows;
+  // ---- row maxima over the whole c range
+  double mx = 0.0;
+  if (rok) {
+    for (int c = warp; c < cols; c += 8) {
+      if (CPLX) {
+        const double2 v = reinterpret_cast<const double2*>(src)[(long)c * s_col + r];
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+      } else {
+        mx = fmax(mx, fabs(src[(long)c * s_col + r]));
+      }
+    }
+  }
+  smax[warp][lane] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mx = fmax(mx, smax[w][lane]);
+  double sc, inv64;
+  oz_scale_of(mx, sc, inv64);
+  if (blockIdx.y == 0 && warp == 0 && rok) {
+    if (CPLX) { scale[2 * r] = sc; scale[2 * r + 1] = sc; }
+    else scale[r] = sc;
+  }
+  const int out_rows = CPLX ? 2 * rows : rows;
+  const long slice_stride = (long)out_rows * Kp;
+  const int nchunks = (Kp + OZT_KB - 1) / OZT_KB;
+  const int ch0 = blockIdx.y * chunks_per_block;
+  const int ch1 = (ch0 + chunks_per_block) < nchunks ? (ch0 + chunks_per_block) : nchunks;
+  for (int ch = ch0; ch < ch1; ++ch) {
+    const int c0 = ch * CT;
+    __syncthreads();                              // stage free again
+#pragma unroll
+    for (int i = 0; i < CT / 8; ++i) {
+      const int cl = warp + 8 * i, c = c0 + cl;
+      signed char d0[OZ_MAX_SLICES], d1[OZ_MAX_SLICES];
+      if (CPLX) {
+        double2 v = make_double2(0.0, 0.0);
+        if (rok && c < cols) v = reinterpret_cast<const double2*>(src)[(long)c * s_col + r];
+        oz_digits(v.x * inv64, nslices, d0);
+        oz_digits(v.y * inv64, nslices, d1);
+#pragma unroll
+        for (int s = 0; s < OZ_MAX_SLICES; ++s)
+          if (s < nslices) {
+            signed char* b = stage + (s * OR + 2 * lane) * OZT_LD + 2 * cl;
+            *reinterpret_cast<char2*>(b) = make_char2(d0[s], (signed char)(-d1[s]));
+            *reinterpret_cast<char2*>(b + OZT_LD) = make_char2(d1[s], d0[s]);
+          }
+      } else {
+        double v = 0.0;
+        if (rok && c < cols) v = src[(long)c * s_col + r];
+        oz_digits(v * inv64, nslices, d0);
+#pragma unroll
+        for (int s = 0; s < OZ_MAX_SLICES; ++s)
+          if (s < nslices) stage[(s * OR + lane) * OZT_LD + cl] = d0[s];
+      }
+    }
+    __syncthreads();
+    // ---- write out: (slice, out row) segments of 64 bytes, 16 lanes x char4 each
+    const int kbase = ch * OZT_KB;
+    const int seg_total = nslices * OR;
+    for (int seg = warp * 2 + (lane >> 4); seg < seg_total; seg += 16) {
+      const int s = seg / OR, orow = seg % OR;
+      const int grow = blockIdx.x * OR + orow;
+      const int kk = (lane & 15) * 4;
+      if (grow < out_rows && kbase + kk < Kp) {
+        const char4 v = *reinterpret_cast<const char4*>(stage + (s * OR + orow) * OZT_LD + kk);
+        *reinterpret_cast<char4*>(q + s * slice_stride + (long)grow * Kp + kbase + kk) = v;
+      }
+    }
+  }
+}
+
+// MPO-site application fused with the digit split of its result (the left operand of G3):
+//   row (x, d, y1) of  T[x,d,y1,f,y2] = sum_{p,q} W[p,d,q,f] in[x,p,q,(y1,y2)]   (wapply.cu)
+// is produced in shared memory by one block, which then scales it and writes its digits; the FP64
+// tensor T never touches HBM.  Requires the input's y index to be contiguous.
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+wapply_split_kernel(WApplyParams p, int Kp, int nslices, signed char* __restrict__ q,
+                    double* __restrict__ scale) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  extern __shared__ __align__(16) double ws_row[];
+  __shared__ double red[8];
+  const int Y1 = p.Y / p.Y2;
+  const int row = blockIdx.x;
+  const int y1 = row % Y1, xd = row / Y1;
+  const int d = xd % p.D, x = xd / p.D;
+  const T* in = reinterpret_cast<const T*>(p.in) + (long)x * p.isx + (long)y1 * p.Y2;
+  double mx = 0.0;
+  for (int f = 0; f < p.F; ++f) {
+    const int e0 = p.rowptr[d * p.F + f], e1 = p.rowptr[d * p.F + f + 1];
+    for (int y2 = threadIdx.x; y2 < p.Y2; y2 += 256) {
+      T acc;
+      if constexpr (CPLX) acc = make_double2(0.0, 0.0); else acc = 0.0;
+      for (int e = e0; e < e1; ++e) {
+        const int pq = p.ent_pq[e];
+        const double w = p.ent_val[e];
+        const T v = in[(long)(pq / p.Q) * p.isp + (long)(pq % p.Q) * p.isq + y2];
+        if constexpr (CPLX) { acc.x = fma(w, v.x, acc.x); acc.y = fma(w, v.y, acc.y); }
+        else acc = fma(w, v, acc);
+      }
+      if constexpr (CPLX) {
+        reinterpret_cast<double2*>(ws_row)[f * p.Y2 + y2] = acc;
+        mx = fmax(mx, fmax(fabs(acc.x), fabs(acc.y)));
+      } else {
+        ws_row[f * p.Y2 + y2] = acc;
+        mx = fmax(mx, fabs(acc));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mx = fmax(mx, red[w]);
+  double sc, inv64;
+  oz_scale_of(mx, sc, inv64);
+  if (threadIdx.x == 0) scale[row] = sc;
+  const int K = p.F * p.Y2 * (CPLX ? 2 : 1);
+  const long slice_stride = (long)gridDim.x * Kp;
+  signed char* qrow = q + (long)row * Kp;
+  for (int k0 = threadIdx.x * 4; k0 < Kp; k0 += 1024) {
+    signed char dg[4][OZ_MAX_SLICES];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oz_digits((k0 + j < K) ? ws_row[k0 + j] * inv64 : 0.0, nslices, dg[j]);
+#pragma unroll
+    for (int s = 0; s < OZ_MAX_SLICES; ++s) {
+      if (s >= nslices) break;
+      *reinterpret_cast<char4*>(qrow + s * slice_stride + k0) = make_char4(dg[0][s], dg[1][s], dg[2][s], dg[3][s]);
     }
   }
 }
 
 // -------------------------------------------------------------------------------------- host
+static int g_oz_sms = -1;
+static int g_oz_force_ksplit = 0;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -329,7 +566,62 @@ int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int 
                        signed char* q, double* scale) {
   if (rows <= 0) return 0;
   const int Kp = (K + 15) & ~15;
-  { ozaki_split_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale); rn::g_launches++; }
+  { ozaki_split_kernel<0><<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
+  RN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Complex source rows (crows x ccols interleaved elements, leading dimension ld in DOUBLES) ->
+// digits of the 2*crows x 2*ccols B-form operand.
+int launch_ozaki_split_bform(cudaStream_t st, const double* X, long ld, int crows, int ccols, int nslices,
+                             int conj_left, signed char* q, double* scale) {
+  if (crows <= 0) return 0;
+  const int K = 2 * ccols, Kp = (K + 15) & ~15;
+  { ozaki_split_kernel<1><<<(unsigned)ceil_div(crows, 8), 256, 0, st>>>(X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
+  RN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Transposed view: logical P[r][c] = src[r + c*s_col] (elements), see ozaki_split_t_kernel.
+int launch_ozaki_split_t(cudaStream_t st, int cplx, const void* src, long s_col, int rows, int cols,
+                         int nslices, signed char* q, double* scale) {
+  if (rows <= 0) return 0;
+  const int K = cplx ? 2 * cols : cols, Kp = (K + 15) & ~15;
+  const int nchunks = (Kp + OZT_KB - 1) / OZT_KB;
+  const int bx = (int)ceil_div(rows, OZT_RT);
+  int by = (int)ceil_div(296, bx);
+  if (by > nchunks) by = nchunks;
+  if (by < 1) by = 1;
+  const int cpb = (nchunks + by - 1) / by;
+  by = (nchunks + cpb - 1) / cpb;
+  dim3 grid((unsigned)bx, (unsigned)by);
+  if (cplx) { ozaki_split_t_kernel<true><<<grid, 256, 0, st>>>((const double*)src, s_col, rows, cols, Kp, nslices, q, scale, cpb); rn::g_launches++; }
+  else { ozaki_split_t_kernel<false><<<grid, 256, 0, st>>>((const double*)src, s_col, rows, cols, Kp, nslices, q, scale, cpb); rn::g_launches++; }
+  RN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Fused MPO application + split (see wapply_split_kernel).  Returns 1 when the row does not fit in
+// shared memory or the layout is not supported (caller falls back to wapply + split), 0 on
+// success, a CUDA error otherwise.
+int launch_wapply_split(cudaStream_t st, int cplx, const WApplyParams& p, int nslices, signed char* q,
+                        double* scale) {
+  if (p.isy != 1 || p.Y2 <= 0 || p.Y % p.Y2 != 0) return 1;
+  const int es = cplx ? 2 : 1;
+  const long K = (long)p.F * p.Y2 * es;
+  const size_t smem = (size_t)((K + 3) & ~3L) * sizeof(double);
+  if (smem > 160 * 1024) return 1;
+  const long rows = (long)p.X * p.D * (p.Y / p.Y2);
+  if (rows <= 0) return 0;
+  const int Kp = (int)((K + 15) & ~15L);
+  static size_t max_set[2] = {0, 0};
+  if (smem + 1024 > 48 * 1024 && smem > max_set[cplx]) {
+    if (cplx) RN_CHECK(cudaFuncSetAttribute(wapply_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    else RN_CHECK(cudaFuncSetAttribute(wapply_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    max_set[cplx] = 160 * 1024;
+  }
+  if (cplx) { wapply_split_kernel<true><<<(unsigned)rows, 256, smem, st>>>(p, Kp, nslices, q, scale); rn::g_launches++; }
+  else { wapply_split_kernel<false><<<(unsigned)rows, 256, smem, st>>>(p, Kp, nslices, q, scale); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -346,9 +638,47 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
   const int Kp = (K + 15) & ~15;
   const int kblocks = (Kp + OZ_BK - 1) / OZ_BK;
   const int tiles_m = (int)ceil_div(m, OZ_BM), tiles_n = (int)ceil_div(n, OZ_BN);
-  { ozaki_gemm_kernel<<<(unsigned)(tiles_m * tiles_n), OZ_THREADS, OZ_SMEM, st>>>(
-      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n); rn::g_launches++; }
+  const int tiles = tiles_m * tiles_n;
+  // split-K when the tile count leaves SMs idle: pick the K partition with the smallest modelled
+  // time  waves * (K blocks per CTA * products * 256 clk + fixed CTA cost) + reduction
+  int ksplit = 1, kb_per = kblocks;
+  if (g_oz_sms < 0) {
+    int dev = 0;
+    RN_CHECK(cudaGetDevice(&dev));
+    RN_CHECK(cudaDeviceGetAttribute(&g_oz_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char* e = getenv("RN_OZ_KSPLIT")) g_oz_force_ksplit = atoi(e);
+  }
+  {
+    const double t_kb = 256.0 * (nslices * (nslices + 1) / 2), t_fixed = 9000.0, t_red = 1200.0;
+    double best = 1e300;
+    const int smax = kblocks < 16 ? kblocks : 16;
+    for (int s = 1; s <= smax; ++s) {
+      const int per = (kblocks + s - 1) / s;
+      const int seff = (kblocks + per - 1) / per;
+      if (seff != s) continue;
+      if ((double)tiles * seff * OZ_BM * OZ_BN * 8.0 > 192e6) continue;   // partial tiles stay L2 resident
+      const long waves = ceil_div((long)tiles * seff, g_oz_sms);
+      const double cost = waves * (per * t_kb + t_fixed) + (seff > 1 ? t_red * seff + 2000.0 : 0.0);
+      if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; }
+    }
+    if (g_oz_force_ksplit > 0 && g_oz_force_ksplit <= kblocks) {
+      kb_per = (kblocks + g_oz_force_ksplit - 1) / g_oz_force_ksplit;
+      ksplit = (kblocks + kb_per - 1) / kb_per;
+    }
+  }
+  double* partial = nullptr;
+  int* counters = nullptr;
+  if (ksplit > 1) {
+    const size_t pbytes = (size_t)tiles * ksplit * OZ_BM * OZ_BN * sizeof(double);
+    RN_CHECK(cudaMallocAsync((void**)&partial, pbytes + sizeof(int) * (size_t)tiles, st));
+    counters = reinterpret_cast<int*>(reinterpret_cast<char*>(partial) + pbytes);
+    RN_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)tiles, st));
+  }
+  { ozaki_gemm_kernel<<<(unsigned)(tiles * ksplit), OZ_THREADS, OZ_SMEM, st>>>(
+      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, ksplit, kb_per,
+      partial, counters); rn::g_launches++; }
   RN_LAUNCH_CHECK();
+  if (partial) RN_CHECK(cudaFreeAsync(partial, st));
   return 0;
 }
 

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "rn_b200.h"
 #include "internal.cuh"
+#include "qr_common.cuh"
 
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -20,37 +21,6 @@ namespace rn {
 constexpr int Q_THREADS = 1024;  // passes over a column are L2-latency bound: few rows per thread
 constexpr int QT_THREADS = 256;   // register-heavy T builder
 constexpr int Q_CPB = 4;  // trailing columns per block
-
-template <bool CPLX>
-struct Cx;
-template <>
-struct Cx<false> {
-  using T = double;
-  __device__ static T zero() { return 0.0; }
-  __device__ static T one() { return 1.0; }
-  __device__ static T mul(T a, T b) { return a * b; }
-  __device__ static T cmul(T a, T b) { return a * b; }  // conj(a) * b
-  __device__ static T sub(T a, T b) { return a - b; }
-  __device__ static T conj(T a) { return a; }
-  __device__ static double abs2(T a) { return a * a; }
-  __device__ static double re(T a) { return a; }
-  __device__ static double im(T) { return 0.0; }
-  __device__ static T make(double r, double) { return r; }
-};
-template <>
-struct Cx<true> {
-  using T = double2;
-  __device__ static T zero() { return make_double2(0.0, 0.0); }
-  __device__ static T one() { return make_double2(1.0, 0.0); }
-  __device__ static T mul(T a, T b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-  __device__ static T cmul(T a, T b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
-  __device__ static T sub(T a, T b) { return make_double2(a.x - b.x, a.y - b.y); }
-  __device__ static T conj(T a) { return make_double2(a.x, -a.y); }
-  __device__ static double abs2(T a) { return a.x * a.x + a.y * a.y; }
-  __device__ static double re(T a) { return a.x; }
-  __device__ static double im(T a) { return a.y; }
-  __device__ static T make(double r, double i) { return make_double2(r, i); }
-};
 
 // Reflector of column j (LAPACK zlarfg): H = I - tau v v^H, v[j] = 1, H^H x = beta e_j.
 template <bool CPLX>
@@ -863,6 +833,12 @@ __global__ void extract_r_kernel(const typename Cx<CPLX>::T* __restrict__ At, co
   }
 }
 
+template <bool CPLX>
+int qr_colmajor_panel(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, long ldt,
+                      typename Cx<CPLX>::T* V, typename Cx<CPLX>::T* tau, double* rdiag,
+                      typename Cx<CPLX>::T* Qt);
+
+static int g_qr_panel = -1;      // blocked cluster-panel QR (qr_panel.cu); RN_QR_PANEL=0 disables it
 static int g_qr_warp_formq = 0;
 static int g_qr_use_flow = 1;   // flag-chained elimination (slower on B200 than the grid barrier)
 static int g_qr_coop_blocks[2] = {-1, -1};   // co-resident block budget per dtype, -1 = unknown
@@ -872,6 +848,14 @@ static int qr_colmajor(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, 
                        typename Cx<CPLX>::T* V, typename Cx<CPLX>::T* tau, double* rdiag,
                        typename Cx<CPLX>::T* Qt) {
   const int k = m < n ? m : n;
+  if (g_qr_panel < 0) {
+    const char* e = getenv("RN_QR_PANEL");
+    g_qr_panel = e ? atoi(e) : 1;
+  }
+  if (g_qr_panel) {
+    const int perr = qr_colmajor_panel<CPLX>(st, m, n, At, ldt, V, tau, rdiag, Qt);
+    if (perr != 1) return perr;       // 1 = shape outside the cluster kernel's range: fall through
+  }
   int& budget = g_qr_coop_blocks[CPLX ? 1 : 0];
   if (budget < 0) {
     if (const char* e = getenv("RN_QR_FLOW")) g_qr_use_flow = atoi(e);

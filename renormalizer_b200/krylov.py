@@ -61,6 +61,10 @@ def expm_krylov(Afunc, dt, vstart, block_size=50):
     if np.iscomplex(dt) and not vstart.is_complex():
         vstart = vstart.to(torch.complex128)
     n = vstart.numel()
+    if plan is not None and plan.dtype == vstart.dtype and (vstart.is_complex() or not np.iscomplex(dt)):
+        got = ops.expm_krylov_plan(plan, vstart, dt)
+        if got is not None:
+            return got
     st = _Lanczos(n, vstart.dtype, vstart.device, block_size)
     nrmv = float(torch.linalg.vector_norm(vstart))
     assert nrmv > 0

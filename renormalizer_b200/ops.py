@@ -383,6 +383,24 @@ def lanczos_step(plan, n, V, j, alpha, beta, w, ws):
     LaunchCounter.add(plan.nlaunch + 5)
 
 
+_CUDA_ERROR_NOT_SUPPORTED = 801
+
+
+def expm_krylov_plan(plan, v, dt):
+    """expm(dt * H_eff) v through rn_expm_krylov (whole Lanczos loop in one C call).
+    Returns (result, H_eff applications) or None when the Krylov dimension outgrows the device
+    eigen-solver (the caller then iterates step by step)."""
+    out = torch.empty_like(v)
+    nsteps = ctypes.c_int(0)
+    dt = complex(dt)
+    err = plan.lib.rn_expm_krylov(plan.handle, stream_ptr(), _is_cplx(v), v.numel(), _ptr(v),
+                                  dt.real, dt.imag, _ptr(out), ctypes.byref(nsteps))
+    if err == _CUDA_ERROR_NOT_SUPPORTED:
+        return None
+    check(err, "rn_expm_krylov")
+    return out, nsteps.value
+
+
 def allclose(a, b, rtol=1e-5, atol=1e-8, flag=None):
     """numpy.allclose(a, b) for two device vectors of the same dtype (one D2H int read)."""
     lib = _lib.get()

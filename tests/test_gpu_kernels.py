@@ -287,3 +287,141 @@ def test_hop_tensor_path_matches_fp64_path(cplx):
         got = host(plan.apply(dev(C)))
         plan.close()
         assert relerr(got, ref) < (1e-12 if path == 0 else 1e-11), path
+
+
+@pytest.fixture
+def all_tensor_path():
+    """Route every contraction GEMM, however small, through the tcgen05 split path (exercises the
+    fused split kernels and split-K at ragged sizes)."""
+    from renormalizer_b200 import _lib
+    lib = _lib.get()
+    lib.rn_set_ozaki(7, 0.0)
+    yield
+    lib.rn_set_ozaki(7, 4.0e6)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("Ml,Mr,w,d,g", [(1, 1, 1, 2, 1), (13, 9, 3, 4, 1), (70, 48, 5, 8, 1),
+                                         (33, 21, 3, 3, 2), (130, 100, 4, 3, 1)])
+def test_hop_fused_split_kernels(all_tensor_path, cplx, Ml, Mr, w, d, g):
+    """0-, 1- and 2-site H_eff.C with the transposing split, the MPO-apply+split kernel and the
+    B-form split of R (all on the tcgen05 path), with and without ancilla indices."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(Ml * 5 + Mr + g)
+    dt = torch.complex128 if cplx else torch.float64
+    L = rnd(rng, (Ml + 1, w, Ml), cplx)
+    R = rnd(rng, (Mr + 2, w + 1, Mr), cplx)
+    R0 = rnd(rng, (Mr + 2, w, Mr), cplx)
+    W1 = rng.standard_normal((w, d, d, w + 1)) * (rng.random((w, d, d, w + 1)) < 0.4)
+    W2 = rng.standard_normal((w + 1, d, d, w + 1)) * (rng.random((w + 1, d, d, w + 1)) < 0.4)
+    anc = (g,) if g > 1 else ()
+    cases = [([], R0, (Ml, Mr)), ([W1], R, (Ml, d) + anc + (Mr,)),
+             ([W1, W2], R, (Ml, d) + anc + (d,) + anc + (Mr,))]
+    for cmo, r, shape in cases:
+        C = rnd(rng, shape, cplx)
+        ref = oc.hop_apply(L, r, cmo, C)
+        plan = ops.HopPlan(dev(L), dev(r), [ops.MpoSite(x) for x in cmo], C.shape, dt, path=1)
+        got = host(plan.apply(dev(C)))
+        plan.close()
+        assert relerr(got, ref) < 1e-11, (len(cmo), shape)
+
+
+@pytest.mark.parametrize("m,n,k,ks", [(256, 512, 1536, 12), (768, 512, 512, 4), (130, 70, 1000, 3),
+                                      (128, 128, 4096, 16), (2048, 512, 1536, 2)])
+def test_ozaki_gemm_split_k(m, n, k, ks, monkeypatch):
+    """Split-K partition of the digit GEMMs: deterministic and equal to the unsplit product."""
+    import os
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(m + n + k)
+    a, b = rng.standard_normal((m, k)), rng.standard_normal((n, k))
+    ref = a @ b.T
+    bound = np.abs(a).max(axis=1)[:, None] * np.abs(b).max(axis=1)[None, :] * k
+    c1 = host(ops.ozaki_gemm_tn(dev(a), dev(b), m, n, k, k, k, nslices=7))
+    c2 = host(ops.ozaki_gemm_tn(dev(a), dev(b), m, n, k, k, k, nslices=7))
+    assert np.array_equal(c1, c2)                      # run-to-run reproducible
+    assert (np.abs(c1 - ref) / bound).max() < 4e-14
+
+
+def _herm_env(rng, M, w, cplx):
+    e = rnd(rng, (M, w, M), cplx)
+    return e + e.conj().transpose(2, 1, 0)
+
+
+@pytest.mark.parametrize("cplx_dt", [True, False])
+@pytest.mark.parametrize("Ml,Mr,w,d", [(1, 1, 1, 1), (1, 2, 1, 1), (2, 3, 2, 1), (6, 5, 2, 3), (24, 20, 3, 4)])
+def test_expm_krylov_plan_vs_oracle(cplx_dt, Ml, Mr, w, d):
+    """rn_expm_krylov (C++ Lanczos loop, device-side tridiagonal eigen-solver and convergence
+    test) against the oracle's expm_krylov on the same H_eff: same result, same step count."""
+    from renormalizer_b200 import ops
+    from renormalizer_b200.hop_expr import hop_expr_dtype
+    from renormalizer_b200.krylov import expm_krylov
+    from oracle.krylov import expm_krylov as oracle_expm
+    rng = np.random.default_rng(Ml * 11 + Mr)
+    L, R = _herm_env(rng, Ml, w, True), _herm_env(rng, Mr, w, True)
+    W = rng.standard_normal((w, d, d, w))
+    W = W + W.transpose(0, 2, 1, 3)
+    scale = 1.0 / max(1.0, np.abs(L).max() * np.abs(R).max() * np.abs(W).max() * Ml * Mr * w * d)
+    L = L * scale
+    C = rnd(rng, (Ml, d, Mr), True)
+    dt = -0.3j if cplx_dt else -0.3
+    ref, jref = oracle_expm(lambda y: oc.hop_apply(L, R, [W], y.reshape(C.shape)).ravel(), dt, C.ravel())
+    hop = hop_expr_dtype(dev(L), dev(R), [W], C.shape, torch.complex128)
+    got, j = expm_krylov(hop, dt, dev(C).reshape(-1))
+    hop.close()
+    assert j == jref
+    assert relerr(host(got), ref) < 1e-10
+
+
+def test_expm_krylov_plan_breakdown():
+    """Start vector inside a small invariant subspace: the Lanczos recurrence breaks down and the
+    device-side check must stop at the reference's step."""
+    from renormalizer_b200.hop_expr import hop_expr_dtype
+    from renormalizer_b200.krylov import expm_krylov
+    from oracle.krylov import expm_krylov as oracle_expm
+    M = 12
+    L = np.zeros((M, 1, M), dtype=complex)
+    L[np.arange(M), 0, np.arange(M)] = np.arange(1, M + 1)
+    R = np.ones((1, 1, 1), dtype=complex)
+    C = np.zeros((M, 1), dtype=complex)
+    C[2, 0], C[5, 0], C[7, 0] = 1.0, -2.0, 0.5j
+    ref, jref = oracle_expm(lambda y: oc.hop_apply(L, R, [], y.reshape(C.shape)).ravel(), -0.2j, C.ravel())
+    hop = hop_expr_dtype(dev(L), dev(R), [], C.shape, torch.complex128)
+    got, j = expm_krylov(hop, -0.2j, dev(C).reshape(-1))
+    hop.close()
+    assert j == jref
+    assert relerr(host(got), ref) < 1e-10
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("m,n", [(2048, 256), (256, 2048), (256, 256), (1000, 97), (96, 96), (33, 31)])
+def test_qr_panel_bench_shapes(cplx, m, n):
+    """Blocked cluster-panel Householder QR / LQ at the sweep's bond-matrix shapes: orthonormal
+    factor, reconstruction, triangular factor, and LAPACK's reflector convention (tall case)."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(m + 7 * n)
+    a = rnd(rng, (m, n), cplx)
+    k = min(m, n)
+    q, r = (host(x) for x in ops.qr(dev(a)))
+    assert np.abs(q.conj().T @ q - np.eye(k)).max() < 1e-12
+    assert relerr(q @ r, a) < 1e-12
+    assert np.abs(np.tril(r, -1)).max() == 0
+    if m >= n:
+        qn, rn_ = np.linalg.qr(a)
+        assert relerr(r, rn_) < 1e-10 and relerr(q, qn) < 1e-10
+    l, q2 = (host(x) for x in ops.qr(dev(a), lq=True))
+    assert np.abs(q2 @ q2.conj().T - np.eye(k)).max() < 1e-12
+    assert relerr(l @ q2, a) < 1e-12
+    assert np.abs(np.triu(l, 1)).max() == 0
+
+
+def test_qr_graded_columns():
+    """Columns spanning 14 decades (the conditioning of an evolved TDVP site tensor): Householder
+    QR must stay orthonormal and reconstruct to round-off."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(9)
+    m, n = 700, 150
+    a = rnd(rng, (m, n), True) * np.logspace(0, -14, n)[None, :]
+    a[:, 40] = a[:, 3] * (0.3 - 2j)            # exactly dependent column
+    q, r = (host(x) for x in ops.qr(dev(a)))
+    assert np.abs(q.conj().T @ q - np.eye(n)).max() < 1e-12
+    assert relerr(q @ r, a) < 1e-12
