@@ -305,7 +305,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = _lib.LaunchCounter.total()
+    if args.profiler_range:           # `ncu --profile-from-start off`: capture the timed steps only
+        torch.cuda.cudart().cudaProfilerStart()
     ms = timed(step_device, args.steps)
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = _lib.LaunchCounter.total() - l0
     clocks = sampler.stop() if rank == 0 else None
     sites_total = work["sites_per_step"] * args.steps * world
@@ -456,6 +460,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

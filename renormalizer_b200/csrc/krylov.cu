@@ -117,6 +117,50 @@ krylov_coef_kernel(const double* __restrict__ alpha, const double* __restrict__ 
     const double b = beta[2 * i];
     if (!(b >= eps_break)) { m = i + 1; broke = 1; break; }
   }
+  // Fast path (Krylov dimension <= 32 and |dt| ||T|| <= 16, i.e. every TDVP step in practice):
+  // coef = |v| exp(dt T) e_0 by 2^s Taylor sub-steps of norm <= 1 (20 terms, truncation 1/21!),
+  // one warp, lane i <-> entry i, the tridiagonal product through shuffles.  The eigen-solver below
+  // remains for long spaces / large norms; both evaluate the same vector to round-off.
+  if (m <= 32) {
+    const int lane = t & 31;
+    const bool in = lane < m;
+    const double al = in ? alpha[2 * lane] : 0.0;
+    const double bu = (in && lane < m - 1) ? beta[2 * lane] : 0.0;          // couples lane, lane + 1
+    const double bd = (in && lane > 0) ? beta[2 * (lane - 1)] : 0.0;        // couples lane - 1, lane
+    double rs = fabs(al) + fabs(bu) + fabs(bd);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
+    const double na = hypot(dt_re, dt_im) * rs;
+    int s2 = 0;
+    while (s2 <= 4 && ldexp(1.0, s2) < na) ++s2;
+    if (s2 <= 4) {
+      if (t < 32) {
+        const int nsub = 1 << s2;
+        const double hr = dt_re / nsub, hi = dt_im / nsub;
+        double yr = (lane == 0) ? nrm_ptr[0] : 0.0, yi = 0.0;
+        for (int sub = 0; sub < nsub; ++sub) {
+          double tr = yr, ti = yi;
+          for (int k = 1; k <= 20; ++k) {
+            const double ur = __shfl_up_sync(0xffffffffu, tr, 1), ui = __shfl_up_sync(0xffffffffu, ti, 1);
+            const double dr = __shfl_down_sync(0xffffffffu, tr, 1), di = __shfl_down_sync(0xffffffffu, ti, 1);
+            const double pr = al * tr + bd * ur + bu * dr;       // (T term)_lane; bd = 0 on lane 0, bu = 0 on the last
+            const double pi = al * ti + bd * ui + bu * di;
+            const double ik = 1.0 / k;
+            tr = (hr * pr - hi * pi) * ik;
+            ti = (hr * pi + hi * pr) * ik;
+            yr += tr; yi += ti;
+          }
+        }
+        if (lane < mtry) {
+          coef[2 * lane] = in ? yr : 0.0;
+          coef[2 * lane + 1] = in ? yi : 0.0;
+        }
+        if (lane == 0) { status[0] = broke; status[1] = m; }
+      }
+      for (int i = 32 + t; i < mtry; i += K_MAXM) { coef[2 * i] = 0.0; coef[2 * i + 1] = 0.0; }
+      return;
+    }
+  }
   double d[K_MAXM], e[K_MAXM], z[K_MAXM];
   for (int i = 0; i < K_MAXM; ++i) {
     d[i] = i < m ? alpha[2 * i] : 0.0;

@@ -31,6 +31,7 @@ namespace rn {
 
 constexpr int OZ_BM = 128, OZ_BN = 128, OZ_BK = 128;     // tile: rows, cols, K bytes (= int8 elems)
 constexpr int OZ_STAGES = 5;
+constexpr int OZ_ACC = 4;                                  // TMEM accumulators (128 columns each)
 constexpr int OZ_THREADS = 320;
 constexpr int OZ_TILE_BYTES = OZ_BM * OZ_BK;             // 16 KiB per operand tile
 constexpr int OZ_SMEM = OZ_STAGES * 2 * OZ_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -117,8 +118,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-B aligned operand ring
   const uint32_t bars = tiles + OZ_STAGES * 2 * OZ_TILE_BYTES;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * OZ_STAGES;
-  const uint32_t tfull_bar = bars + 16 * OZ_STAGES, tempty_bar = tfull_bar + 16;
-  const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t tfull_bar = bars + 16 * OZ_STAGES, tempty_bar = tfull_bar + 8 * OZ_ACC;
+  const uint32_t tmem_slot = tempty_bar + 8 * OZ_ACC;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(oz_smem_raw + (tmem_slot - raw));
 
@@ -145,11 +146,11 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
+    for (int a = 0; a < OZ_ACC; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(OZ_ACC * OZ_BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -157,37 +158,45 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Levels are processed in PAIRS (lo, hi = lo + 1) so that operand tiles are shared between digit
+  // products: step s of a pair loads A-slice s and B-slice hi - s and feeds TWO products,
+  //   A_s x B_(hi-s) -> level hi      and      A_(s-1) x B_(hi-s) -> level lo,
+  // the second one re-using the A tile of the previous step.  Per K block that is hi + 1 tile
+  // pairs for 2 hi + 1 products instead of one pair per product: L2 -> shared-memory traffic
+  // (the bound of this kernel) drops from 56 to 32 tiles per K block at 7 digits.
+  // With an odd digit count level 0 runs alone first.
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int g = 0; g < nslices; ++g)
-        for (int s = 0; s <= g; ++s) {
-          const int t = g - s;
-          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+      for (int g = (nslices & 1) ? -1 : 0; g < nslices; g += 2) {
+        const int hi = g + 1;
+        for (int kb = kb0; kb < kb1; ++kb)
+          for (int s = 0; s <= hi; ++s, ++it) {
             const int st = it % OZ_STAGES;
             const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
             mbar_wait(empty_bar + 8 * st, ph ^ 1u);
             mbar_expect_tx(full_bar + 8 * st, 2 * OZ_TILE_BYTES);
             tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES, &tmA, full_bar + 8 * st, kb * OZ_BK, s * rowsA + row0);
             tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES, &tmB, full_bar + 8 * st, kb * OZ_BK,
-                        t * rowsB + col0);
+                        (hi - s) * rowsB + col0);
           }
-        }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       int it = 0;
-      for (int g = 0; g < nslices; ++g) {
-        const int acc = g & 1;
-        const uint32_t use = (uint32_t)(g >> 1);
-        mbar_wait(tempty_bar + 8 * acc, (use & 1u) ^ 1u);
+      for (int g = (nslices & 1) ? -1 : 0; g < nslices; g += 2) {
+        const int lo = g, hi = g + 1;
+        if (lo >= 0) mbar_wait(tempty_bar + 8 * (lo & 3), (((uint32_t)lo >> 2) & 1u) ^ 1u);
+        mbar_wait(tempty_bar + 8 * (hi & 3), (((uint32_t)hi >> 2) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * OZ_BN;
-        uint32_t accumulate = 0;
-        for (int s = 0; s <= g; ++s)
-          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const uint32_t d_lo = tmem_base + (uint32_t)((lo & 3) * OZ_BN), d_hi = tmem_base + (uint32_t)((hi & 3) * OZ_BN);
+        uint32_t acc_lo = 0, acc_hi = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          int prev = -1;
+          for (int s = 0; s <= hi; ++s, ++it) {
             const int st = it % OZ_STAGES;
             const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
             mbar_wait(full_bar + 8 * st, ph);
@@ -196,12 +205,24 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t bdesc = make_smem_desc(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES);
 #pragma unroll
             for (int k4 = 0; k4 < OZ_BK / 32; ++k4) {
-              umma_i8(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, accumulate);
-              accumulate = 1;
+              umma_i8(d_hi, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_hi);
+              acc_hi = 1;
             }
-            umma_commit(empty_bar + 8 * st);       // stage reusable once these MMAs retire
+            if (s >= 1) {
+              const uint64_t pdesc = make_smem_desc(tiles + prev * 2 * OZ_TILE_BYTES);
+#pragma unroll
+              for (int k4 = 0; k4 < OZ_BK / 32; ++k4) {
+                umma_i8(d_lo, pdesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_lo);
+                acc_lo = 1;
+              }
+              umma_commit(empty_bar + 8 * prev);   // previous step's tiles are free once these retire
+            }
+            prev = st;
           }
-        umma_commit(tfull_bar + 8 * acc);          // level g complete in TMEM
+          umma_commit(empty_bar + 8 * prev);
+        }
+        if (lo >= 0) umma_commit(tfull_bar + 8 * (lo & 3));
+        umma_commit(tfull_bar + 8 * (hi & 3));     // levels complete in TMEM
       }
     }
   } else {
@@ -214,8 +235,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 64; ++i) sum[i] = 0.0;
     for (int g = 0; g < nslices; ++g) {
-      const int acc = g & 1;
-      const uint32_t use = (uint32_t)(g >> 1);
+      const int acc = g & 3;
+      const uint32_t use = (uint32_t)(g >> 2);
       mbar_wait(tfull_bar + 8 * acc, use & 1u);
       tc_fence_after();
       const double wg = scalbn(1.0, -12 - 7 * g);
@@ -232,10 +253,13 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
     }
     if (ksplit > 1) {
+      // partial tiles are private to this kernel: stored thread-major so that every store / load
+      // instruction of a warp covers 512 contiguous bytes
       const int tile_id = blockIdx.x / ksplit;
-      double* mine = partial + ((long)tile_id * ksplit + split) * (OZ_BM * OZ_BN) + r * OZ_BN + half * 64;
+      double2* mine = reinterpret_cast<double2*>(partial + ((long)tile_id * ksplit + split) * (OZ_BM * OZ_BN)) +
+                      (half * 32) * OZ_BM + r;
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) *reinterpret_cast<double2*>(mine + i) = make_double2(sum[i], sum[i + 1]);
+      for (int i = 0; i < 32; ++i) mine[i * OZ_BM] = make_double2(sum[2 * i], sum[2 * i + 1]);
       __threadfence();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ew == 0 && lane == 0) {
@@ -248,38 +272,41 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool last = *tmem_slot_ptr != 0u;
       if (last) {
         __threadfence();
-        const double* p0 = partial + (long)tile_id * ksplit * (OZ_BM * OZ_BN) + r * OZ_BN + half * 64;
+        const double2* p0 = reinterpret_cast<const double2*>(partial + (long)tile_id * ksplit * (OZ_BM * OZ_BN)) +
+                            (half * 32) * OZ_BM + r;
 #pragma unroll
         for (int i = 0; i < 64; ++i) sum[i] = 0.0;
         for (int sp = 0; sp < ksplit; ++sp) {
-          const double* ps = p0 + (long)sp * (OZ_BM * OZ_BN);
+          const double2* ps = p0 + (long)sp * (OZ_BM * OZ_BN / 2);
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            const double2 v = __ldcg(reinterpret_cast<const double2*>(ps + i));
-            sum[i] += v.x; sum[i + 1] += v.y;
+          for (int i = 0; i < 32; ++i) {
+            const double2 v = __ldcg(ps + i * OZ_BM);
+            sum[2 * i] += v.x; sum[2 * i + 1] += v.y;
           }
         }
       }
       if (!last) goto oz_epilogue_done;
     }
     {
+      // C tile through shared memory (the operand ring is idle now): thread-per-row results are
+      // transposed so that every global store of a warp writes 256 contiguous bytes of one row
+      double* stage = reinterpret_cast<double*>(oz_smem_raw + (tiles - raw));     // [128 cols][129]
       const int grow = row0 + r;
-      if (grow < m) {
-        const double sa = sA[grow];
-        double* crow = C + (long)grow * ldc;
-        const int cbase = col0 + half * 64;
-        if (cbase + 64 <= n && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+      const double sa = grow < m ? sA[grow] : 0.0;
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
-            const double2 sb = *reinterpret_cast<const double2*>(sB + cbase + i);
-            *reinterpret_cast<double2*>(crow + cbase + i) = make_double2(sum[i] * sa * sb.x, sum[i + 1] * sa * sb.y);
-          }
-        } else {
+      for (int i = 0; i < 64; ++i) stage[(half * 64 + i) * (OZ_BM + 1) + r] = sum[i] * sa;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      double sb[4];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const int gc = cbase + i;
-            if (gc < n) crow[gc] = sum[i] * sa * sB[gc];
-          }
+      for (int j = 0; j < 4; ++j) sb[j] = (col0 + lane + 32 * j < n) ? sB[col0 + lane + 32 * j] : 0.0;
+      for (int rr = ew; rr < OZ_BM; rr += 8) {
+        const int gr = row0 + rr;
+        if (gr >= m) break;
+        double* crow = C + (long)gr * ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = lane + 32 * j;
+          if (col0 + col < n) crow[col] = stage[col * (OZ_BM + 1) + rr] * sb[j];
         }
       }
     }
@@ -289,7 +316,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(OZ_ACC * OZ_BN));
   }
 }
 

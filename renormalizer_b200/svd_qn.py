@@ -24,6 +24,16 @@ def get_qn_mask(qnmat: np.ndarray, qntot):
     return np.all(qnmat == np.array(qntot), axis=-1)
 
 
+def _distinct_qn(lqn):
+    """The reference iterates `set([tuple(t) for t in lqn])` (svd_qn.py:140); a set's layout depends
+    only on the sequence of DISTINCT insertions, so inserting the first occurrences in order gives
+    the same iteration order without a Python loop over every row."""
+    if lqn.shape[0] <= 64:
+        return set([tuple(t) for t in lqn])
+    _, first = np.unique(lqn, axis=0, return_index=True)
+    return set([tuple(t) for t in lqn[np.sort(first)]])
+
+
 def _idx(a, device):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(device)
 
@@ -93,7 +103,7 @@ def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray
 
     u_nz, u_z, v_nz, v_z, s_nz, su_z, sv_z = [], [], [], [], [], [], []
     ql_nz, ql_z, qr_nz, qr_z = [], [], [], []
-    for ql in set([tuple(t) for t in lqn]):
+    for ql in _distinct_qn(lqn):
         qr_ = qntot - ql
         rset = np.where(get_qn_mask(rqn, qr_))[0]
         if len(rset) == 0:
