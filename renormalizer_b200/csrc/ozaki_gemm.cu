@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const double* __restrict__ sA, const double* __restrict__ sB,
                   double* __restrict__ C, int m, int n, long ldc, int rowsA, int rowsB, int kblocks,
-                  int nslices, int tiles_m, int tiles_n, int ksplit, int kb_per_split,
+                  int nslices, int tiles_m, int tiles_n, int n_full, int ksplit_tail, int kb_per_split,
                   double* __restrict__ partial, int* __restrict__ counters) {
   extern __shared__ unsigned char oz_smem_raw[];
   const uint32_t raw = smem_u32(oz_smem_raw);
@@ -127,9 +127,19 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // grouped rasterisation: the ~148 tiles in flight form a block of OZ_GROUP_M row tiles by a
   // dozen column tiles, so that the digit slices they share stay L2 resident and every slice is
   // read from HBM about once
+  // CTAs [0, n_full) own one whole tile each; the remaining tiles (all of them when n_full == 0)
+  // are split along K into ksplit_tail CTAs, so that a ragged last wave finishes in a fraction of
+  // a tile time.  The last CTA of a split tile to finish sums the partial tiles in split order
+  // (deterministic) and writes C.
+  int tile_id, split, ksplit;
+  if ((int)blockIdx.x < n_full) { tile_id = blockIdx.x; split = 0; ksplit = 1; }
+  else {
+    const int t = (int)blockIdx.x - n_full;
+    tile_id = n_full + t / ksplit_tail; split = t % ksplit_tail; ksplit = ksplit_tail;
+  }
   int tm, tn;
   {
-    const int tile = blockIdx.x / ksplit;
+    const int tile = tile_id;
     const int per_group = OZ_GROUP_M * tiles_n;
     const int first_m = (tile / per_group) * OZ_GROUP_M;
     const int gsize = (tiles_m - first_m) < OZ_GROUP_M ? (tiles_m - first_m) : OZ_GROUP_M;
@@ -138,11 +148,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tn = in_group / gsize;
   }
   const int row0 = tm * OZ_BM, col0 = tn * OZ_BN;
-  // split-K: this CTA contracts K blocks [kb0, kb1) only; the last CTA of a tile to finish sums
-  // the partial tiles in split order (deterministic) and writes C
-  const int split = blockIdx.x % ksplit;
-  const int kb0 = split * kb_per_split;
-  const int kb1 = (kb0 + kb_per_split) < kblocks ? (kb0 + kb_per_split) : kblocks;
+  const int kb0 = ksplit > 1 ? split * kb_per_split : 0;
+  const int kb1 = ksplit > 1 ? ((kb0 + kb_per_split) < kblocks ? (kb0 + kb_per_split) : kblocks) : kblocks;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
@@ -255,24 +262,24 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (ksplit > 1) {
       // partial tiles are private to this kernel: stored thread-major so that every store / load
       // instruction of a warp covers 512 contiguous bytes
-      const int tile_id = blockIdx.x / ksplit;
-      double2* mine = reinterpret_cast<double2*>(partial + ((long)tile_id * ksplit + split) * (OZ_BM * OZ_BN)) +
+      const int ptile = tile_id - n_full;        // partial tiles / counters exist for split tiles only
+      double2* mine = reinterpret_cast<double2*>(partial + ((long)ptile * ksplit + split) * (OZ_BM * OZ_BN)) +
                       (half * 32) * OZ_BM + r;
 #pragma unroll
       for (int i = 0; i < 32; ++i) mine[i * OZ_BM] = make_double2(sum[2 * i], sum[2 * i + 1]);
       __threadfence();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ew == 0 && lane == 0) {
-        const int old = atomicAdd(counters + tile_id, 1);
+        const int old = atomicAdd(counters + ptile, 1);
         const int last = old == ksplit - 1;
-        if (last) counters[tile_id] = 0;          // self-resetting: ready for the next launch
+        if (last) counters[ptile] = 0;            // self-resetting: ready for the next launch
         *tmem_slot_ptr = (uint32_t)last;          // tmem_base was read by every thread long ago
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const bool last = *tmem_slot_ptr != 0u;
       if (last) {
         __threadfence();
-        const double2* p0 = reinterpret_cast<const double2*>(partial + (long)tile_id * ksplit * (OZ_BM * OZ_BN)) +
+        const double2* p0 = reinterpret_cast<const double2*>(partial + (long)ptile * ksplit * (OZ_BM * OZ_BN)) +
                             (half * 32) * OZ_BM + r;
 #pragma unroll
         for (int i = 0; i < 64; ++i) sum[i] = 0.0;
@@ -347,18 +354,29 @@ __device__ __forceinline__ void oz_scale_of(double mx, double& sc, double& inv64
 //           representation ("B-form" of pack.cu):  (re, -im | im, re), with conj_left
 //           (re, +im | im, -re).  K counts doubles.
 // q layout: [slice][row][Kp] bytes, Kp a multiple of 16 (zero padded).
-template <int FORM>
+// WPR warps work on one row (1: a warp per row, 8 rows per block; 8: the whole block on one row,
+// for operands with few long rows).
+template <int FORM, int WPR>
 __global__ void __launch_bounds__(256)
 ozaki_split_kernel(const double* __restrict__ X, long ld, int rows, int K, int Kp, int nslices,
                    signed char* __restrict__ q, double* __restrict__ scale, int conj_left) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  __shared__ double smx[8];
+  const int warp = threadIdx.x >> 5;
+  const int lane = WPR == 1 ? (threadIdx.x & 31) : threadIdx.x;       // position inside the row team
+  constexpr int TEAM = 32 * WPR;
+  const int row = WPR == 1 ? blockIdx.x * 8 + warp : blockIdx.x;
   if (row >= rows) return;
   const double* x = X + (long)row * ld;
   double mx = 0.0;
-  for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(x[k]));
+  for (int k = lane; k < K; k += TEAM) mx = fmax(mx, fabs(x[k]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (WPR > 1) {
+    if ((threadIdx.x & 31) == 0) smx[warp] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mx = fmax(mx, smx[w]);
+  }
   double sc, inv64;
   oz_scale_of(mx, sc, inv64);
   const int out_rows = FORM == 1 ? 2 * rows : rows;
@@ -368,7 +386,7 @@ ozaki_split_kernel(const double* __restrict__ X, long ld, int rows, int K, int K
   }
   const long slice_stride = (long)out_rows * Kp;
   signed char* qrow = q + (long)(FORM == 1 ? 2 * row : row) * Kp;
-  for (int k0 = lane * 4; k0 < Kp; k0 += 128) {
+  for (int k0 = lane * 4; k0 < Kp; k0 += 4 * TEAM) {
     signed char dg[4][OZ_MAX_SLICES];
 #pragma unroll
     for (int j = 0; j < 4; ++j) oz_digits((k0 + j < K) ? x[k0 + j] * inv64 : 0.0, nslices, dg[j]);
@@ -593,7 +611,10 @@ int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int 
                        signed char* q, double* scale) {
   if (rows <= 0) return 0;
   const int Kp = (K + 15) & ~15;
-  { ozaki_split_kernel<0><<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
+  if (rows >= 2048 || K < 512)
+    { ozaki_split_kernel<0, 1><<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
+  else
+    { ozaki_split_kernel<0, 8><<<(unsigned)rows, 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -604,7 +625,10 @@ int launch_ozaki_split_bform(cudaStream_t st, const double* X, long ld, int crow
                              int conj_left, signed char* q, double* scale) {
   if (crows <= 0) return 0;
   const int K = 2 * ccols, Kp = (K + 15) & ~15;
-  { ozaki_split_kernel<1><<<(unsigned)ceil_div(crows, 8), 256, 0, st>>>(X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
+  if (crows >= 2048 || K < 512)
+    { ozaki_split_kernel<1, 1><<<(unsigned)ceil_div(crows, 8), 256, 0, st>>>(X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
+  else
+    { ozaki_split_kernel<1, 8><<<(unsigned)crows, 256, 0, st>>>(X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -668,7 +692,7 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
   const int tiles = tiles_m * tiles_n;
   // split-K when the tile count leaves SMs idle: pick the K partition with the smallest modelled
   // time  waves * (K blocks per CTA * products * 256 clk + fixed CTA cost) + reduction
-  int ksplit = 1, kb_per = kblocks;
+  int ksplit = 1, kb_per = kblocks, n_full = 0;
   if (g_oz_sms < 0) {
     int dev = 0;
     RN_CHECK(cudaGetDevice(&dev));
@@ -679,6 +703,7 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
     const double t_kb = 256.0 * (nslices * (nslices + 1) / 2), t_fixed = 9000.0, t_red = 1200.0;
     double best = 1e300;
     const int smax = kblocks < 16 ? kblocks : 16;
+    // (a) every tile split the same way
     for (int s = 1; s <= smax; ++s) {
       const int per = (kblocks + s - 1) / s;
       const int seff = (kblocks + per - 1) / per;
@@ -686,23 +711,38 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
       if ((double)tiles * seff * OZ_BM * OZ_BN * 8.0 > 192e6) continue;   // partial tiles stay L2 resident
       const long waves = ceil_div((long)tiles * seff, g_oz_sms);
       const double cost = waves * (per * t_kb + t_fixed) + (seff > 1 ? t_red * seff + 2000.0 : 0.0);
-      if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; }
+      if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; n_full = 0; }
+    }
+    // (b) whole waves unsplit, the ragged last wave split along K
+    const int tail = tiles % g_oz_sms, full = tiles - tail;
+    if (full > 0 && tail > 0) {
+      const int st_max = g_oz_sms / tail < smax ? g_oz_sms / tail : smax;
+      for (int s = 2; s <= st_max; ++s) {
+        const int per = (kblocks + s - 1) / s;
+        const int seff = (kblocks + per - 1) / per;
+        if (seff != s) continue;
+        const double cost = (full / g_oz_sms) * (kblocks * t_kb + t_fixed) + (per * t_kb + t_fixed) + t_red * seff + 2000.0;
+        if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; n_full = full; }
+      }
     }
     if (g_oz_force_ksplit > 0 && g_oz_force_ksplit <= kblocks) {
       kb_per = (kblocks + g_oz_force_ksplit - 1) / g_oz_force_ksplit;
       ksplit = (kblocks + kb_per - 1) / kb_per;
+      n_full = 0;
     }
   }
+  if (ksplit == 1) n_full = tiles;
+  const int split_tiles = tiles - n_full;
   double* partial = nullptr;
   int* counters = nullptr;
-  if (ksplit > 1) {
-    const size_t pbytes = (size_t)tiles * ksplit * OZ_BM * OZ_BN * sizeof(double);
-    RN_CHECK(cudaMallocAsync((void**)&partial, pbytes + sizeof(int) * (size_t)tiles, st));
+  if (split_tiles > 0) {
+    const size_t pbytes = (size_t)split_tiles * ksplit * OZ_BM * OZ_BN * sizeof(double);
+    RN_CHECK(cudaMallocAsync((void**)&partial, pbytes + sizeof(int) * (size_t)split_tiles, st));
     counters = reinterpret_cast<int*>(reinterpret_cast<char*>(partial) + pbytes);
-    RN_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)tiles, st));
+    RN_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)split_tiles, st));
   }
-  { ozaki_gemm_kernel<<<(unsigned)(tiles * ksplit), OZ_THREADS, OZ_SMEM, st>>>(
-      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, ksplit, kb_per,
+  { ozaki_gemm_kernel<<<(unsigned)(n_full + split_tiles * ksplit), OZ_THREADS, OZ_SMEM, st>>>(
+      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, n_full, ksplit > 1 ? ksplit : 1, kb_per,
       partial, counters); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   if (partial) RN_CHECK(cudaFreeAsync(partial, st));

@@ -476,7 +476,11 @@ class Mps:
         else:
             mps = self.to_complex()
         cdtype = mps.dtype
-        environ = Environ(mps, mpo)
+        # The reference builds both environment chains here and notes that "almost half is not
+        # used" (mps.py:1282-1284): a sweep that starts at the right end only ever reads the L
+        # chain of the initial state (the R environments are rebuilt site by site before they are
+        # read), and vice versa.  Only the chain that is read is constructed.
+        environ = Environ(mps, mpo, "R" if mps.to_right else "L")
         local_steps = []
         n = len(mps)
         for _ in range(2):
