@@ -406,10 +406,19 @@ def gemm_roofline(args, step_fn):
         peak, src = 40.0, "nominal B200 FP64 tensor (DMMA) peak; MEASURED_PEAKS.json has no FP64 figure"
     else:
         peak = peaks.get("bf16_tflops_sustained", 1400.0) * 2 / 28
-        src = "FP64-equivalent: 2 x measured sustained bf16 (int8 rate) / 28 slice products"
+        src = ("FP64-equivalent, of measured: 2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 tensor rate) "
+               "/ 28 digit products; algorithmic work = 2*m*n*k per launch")
+    traffic, traffic_src = None, None
+    if args.path == 1:
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json"))).get(str(args.bond))
+            if t:
+                traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+        except OSError:
+            pass
     return {"bound": "tensor", "kernel": "gemm_tn_f64_kernel" if args.path == 0 else "ozaki_gemm_kernel",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "launches": int(count.value),
+            "traffic": traffic, "traffic_source": traffic_src, "launches": int(count.value),
             "avg_launch_us": ms.value * 1e3 / count.value, "peak_source": src}
 
 

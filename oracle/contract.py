@@ -46,6 +46,30 @@ def hop_apply(ltensor, rtensor, cmo, c):
     return t.transpose(0, 3, 1, 4, 2, 5)                             # a d m g n l
 
 
+def hop_apply_two_layer(ltensor, rtensor, cmo, c):
+    """(H - omega)^2-type H_eff with two MPO layers and 4-index environments.
+
+    Reference: renormalizer/mps/hop_expr.py:24-52
+      1 site : "abcd, befg, cfhi, jgik, aej -> dhk"
+      2 sites: "abcd, befg, cfhi, gjkl, ikmn, olnp, aejo -> dhmp"
+    """
+    if len(cmo) == 1:
+        w = cmo[0]
+        t = np.tensordot(ltensor, c, axes=(0, 0))                    # b c d e j
+        t = np.tensordot(t, w, axes=([0, 3], [0, 1]))                # c d j f g
+        t = np.tensordot(t, w, axes=([0, 3], [0, 1]))                # d j g h i
+        return np.tensordot(t, rtensor, axes=([1, 2, 4], [0, 1, 2])).reshape(
+            ltensor.shape[3], w.shape[2], rtensor.shape[3])          # d h k
+    assert len(cmo) == 2
+    w1, w2 = cmo
+    t = np.tensordot(ltensor, c, axes=(0, 0))                        # b c d e j o
+    t = np.tensordot(t, w1, axes=([0, 3], [0, 1]))                   # c d j o f g
+    t = np.tensordot(t, w1, axes=([0, 4], [0, 1]))                   # d j o g h i
+    t = np.tensordot(t, w2, axes=([3, 1], [0, 1]))                   # d o h i k l
+    t = np.tensordot(t, w2, axes=([3, 4], [0, 1]))                   # d o h l m n
+    return np.tensordot(t, rtensor, axes=([1, 3, 5], [0, 1, 2]))     # d h m p
+
+
 def hop_diag(ltensor, rtensor, cmo):
     """Diagonal of H_eff (Davidson preconditioner).
 

@@ -18,6 +18,33 @@
 
 namespace rn {
 
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// Every kernel of the library is launched with programmaticStreamSerialization and starts with
+// griddepcontrol.wait: the next kernel's CTAs are scheduled (and run their prologue) while the
+// previous grid drains, instead of after the stream's full launch-to-launch gap.  The wait makes
+// all memory of the prerequisite grids visible, so kernel bodies are unchanged.
+// pdl_wait(): let the dependent grid be scheduled as soon as every CTA of this grid is resident
+// (launch_dependents), then block until the prerequisite grids have completed and flushed.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() {
+  pdl_trigger();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define RN_LAUNCH(kernel, grid, block, smem, st, ...) \
+  (void)rn::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, ##__VA_ARGS__)
+
 extern long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
 __host__ __device__ inline long ceil_div(long a, long b) { return (a + b - 1) / b; }

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tn_f64_kernel(const double* __restrict__ A, const double* __restrict__ B,
                    double* __restrict__ C, int m, int n, int K, long lda, long ldb, long ldc,
                    long sA, long sB, long sC, int accumulate) {
+  pdl_wait();
   extern __shared__ __align__(16) double g_smem[];
   double* As = g_smem;
   double* Bs = g_smem + G_STAGES * G_BM * G_BKP;
@@ -144,10 +145,10 @@ int launch_gemm_tn_f64(cudaStream_t st, int m, int n, int k, const double* A, lo
                      (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0);
   dim3 grid((unsigned)ceil_div(n, G_BN), (unsigned)ceil_div(m, G_BM), (unsigned)batch);
   if (vec16)
-    { gemm_tn_f64_kernel<true><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(A, B, C, m, n, k, lda, ldb, ldc,
+    { RN_LAUNCH(gemm_tn_f64_kernel<true>, grid, G_THREADS, G_SMEM_BYTES, st, A, B, C, m, n, k, lda, ldb, ldc,
                                                                     sA, sB, sC, accumulate); rn::g_launches++; }
   else
-    { gemm_tn_f64_kernel<false><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(A, B, C, m, n, k, lda, ldb,
+    { RN_LAUNCH(gemm_tn_f64_kernel<false>, grid, G_THREADS, G_SMEM_BYTES, st, A, B, C, m, n, k, lda, ldb,
                                                                      ldc, sA, sB, sC, accumulate); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;

@@ -41,6 +41,7 @@ lanczos_axpy_kernel(long nd, double* __restrict__ w, const double* __restrict__ 
                     const double* __restrict__ vjm1, const double* __restrict__ partial_in, int nb_in,
                     const double* __restrict__ beta_prev, double* __restrict__ alpha_out,
                     double* __restrict__ partial_out) {
+  pdl_wait();
   __shared__ double sh_alpha;
   __shared__ double scratch[64];
   const double alpha = block_reduce_partials(partial_in, nb_in, &sh_alpha);
@@ -65,6 +66,7 @@ lanczos_axpy_kernel(long nd, double* __restrict__ w, const double* __restrict__ 
 __global__ void __launch_bounds__(K_THREADS)
 lanczos_scale_kernel(long nd, const double* __restrict__ x, const double* __restrict__ partial_in,
                      int nb_in, double* __restrict__ norm_out, double* __restrict__ out) {
+  pdl_wait();
   __shared__ double sh;
   double s = block_reduce_partials(partial_in, nb_in, &sh);
   s = sqrt(s > 0.0 ? s : 0.0);
@@ -79,6 +81,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(K_THREADS)
 dot_partial_kernel(const double* __restrict__ v, const double* __restrict__ x, long n,
                    double* __restrict__ partial) {
+  pdl_wait();
   __shared__ double scratch[64];
   double acc[2] = {0.0, 0.0};
   const long step = (long)gridDim.x * blockDim.x;
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(K_MAXM)
 krylov_coef_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int mtry,
                    int nbeta_check, const double* __restrict__ nrm_ptr, double dt_re, double dt_im,
                    double eps_break, double* __restrict__ coef, int* __restrict__ status) {
+  pdl_wait();
   __shared__ double z0[K_MAXM];
   const int t = threadIdx.x;
   int m = mtry, broke = 0;
@@ -244,6 +248,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(K_THREADS)
 krylov_combine_kernel(long n, int nvec, const int* __restrict__ nvec_ptr, const double* __restrict__ V,
                       long ld, const double* __restrict__ coef, double* __restrict__ out) {
+  pdl_wait();
   if (nvec_ptr != nullptr) { const int lim = nvec_ptr[0]; if (lim < nvec) nvec = lim; }
   const long step = (long)gridDim.x * blockDim.x;
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
@@ -321,17 +326,17 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
 #define KRY_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { cleanup(); return (int)_e; } } while (0)
 
   // |v| and V_0 = v / |v|
-  if (cplx) { dot_partial_kernel<true><<<nbdot, K_THREADS, 0, st>>>((const double*)v_in, (const double*)v_in, n, pa); rn::g_launches++; }
-  else { dot_partial_kernel<false><<<nbdot, K_THREADS, 0, st>>>((const double*)v_in, (const double*)v_in, n, pa); rn::g_launches++; }
-  { lanczos_scale_kernel<<<nbs, K_THREADS, 0, st>>>(nd, (const double*)v_in, pa, nbdot, nrm, V); rn::g_launches++; }
+  if (cplx) { RN_LAUNCH(dot_partial_kernel<true>, nbdot, K_THREADS, 0, st, (const double*)v_in, (const double*)v_in, n, pa); rn::g_launches++; }
+  else { RN_LAUNCH(dot_partial_kernel<false>, nbdot, K_THREADS, 0, st, (const double*)v_in, (const double*)v_in, n, pa); rn::g_launches++; }
+  { RN_LAUNCH(lanczos_scale_kernel, nbs, K_THREADS, 0, st, nd, (const double*)v_in, pa, nbdot, nrm, V); rn::g_launches++; }
   KRY_CUDA(cudaGetLastError());
 
   auto combine = [&](int mtry, int nbeta_check, double* dst) -> int {
-    { krylov_coef_kernel<<<1, K_MAXM, 0, st>>>(alpha, beta, mtry, nbeta_check, nrm, dt_re, dt_im, eps_break, coef, status); rn::g_launches++; }
+    { RN_LAUNCH(krylov_coef_kernel, 1, K_MAXM, 0, st, alpha, beta, mtry, nbeta_check, nrm, dt_re, dt_im, eps_break, coef, status); rn::g_launches++; }
     int nbc = (int)ceil_div(n, K_THREADS);
     if (nbc > 148 * 8) nbc = 148 * 8;
-    if (cplx) { krylov_combine_kernel<true><<<nbc, K_THREADS, 0, st>>>(n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
-    else { krylov_combine_kernel<false><<<nbc, K_THREADS, 0, st>>>(n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
+    if (cplx) { RN_LAUNCH(krylov_combine_kernel<true>, nbc, K_THREADS, 0, st, n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
+    else { RN_LAUNCH(krylov_combine_kernel<false>, nbc, K_THREADS, 0, st, n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
     return (int)cudaGetLastError();
   };
   auto fetch_status = [&]() -> int {
@@ -345,11 +350,11 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
     if (j + 1 > K_MAXM) { cleanup(); return (int)cudaErrorNotSupported; }   // caller falls back
     double* vj = V + j * nd;
     KRY_TRY(rn_hop_apply(plan, st, vj, w));
-    if (cplx) { dot_partial_kernel<true><<<nbdot, K_THREADS, 0, st>>>(vj, w, n, pa); rn::g_launches++; }
-    else { dot_partial_kernel<false><<<nbdot, K_THREADS, 0, st>>>(vj, w, n, pa); rn::g_launches++; }
+    if (cplx) { RN_LAUNCH(dot_partial_kernel<true>, nbdot, K_THREADS, 0, st, vj, w, n, pa); rn::g_launches++; }
+    else { RN_LAUNCH(dot_partial_kernel<false>, nbdot, K_THREADS, 0, st, vj, w, n, pa); rn::g_launches++; }
     if (j == n - 1) {
       // the Krylov space is the full space: alpha_j only, then the final projection
-      { lanczos_axpy_kernel<<<1, K_THREADS, 0, st>>>(0, w, vj, nullptr, pa, nbdot, nullptr, alpha + 2 * j, pb); rn::g_launches++; }
+      { RN_LAUNCH(lanczos_axpy_kernel, 1, K_THREADS, 0, st, 0, w, vj, nullptr, pa, nbdot, nullptr, alpha + 2 * j, pb); rn::g_launches++; }
       KRY_TRY(combine((int)j + 1, (int)j, res[cur]));
       KRY_TRY(fetch_status());
       result_buf = cur; nsteps = h_status[1];
@@ -365,9 +370,9 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
       cudaFreeAsync(V, st);
       V = V2; cap = ncap; vj = V + j * nd;
     }
-    { lanczos_axpy_kernel<<<nb, K_THREADS, 0, st>>>(nd, w, vj, j > 0 ? vj - nd : nullptr, pa, nbdot,
+    { RN_LAUNCH(lanczos_axpy_kernel, nb, K_THREADS, 0, st, nd, w, vj, j > 0 ? vj - nd : nullptr, pa, nbdot,
                                                    j > 0 ? beta + 2 * (j - 1) : nullptr, alpha + 2 * j, pb); rn::g_launches++; }
-    { lanczos_scale_kernel<<<nbs, K_THREADS, 0, st>>>(nd, w, pb, nb, beta + 2 * j, vj + nd); rn::g_launches++; }
+    { RN_LAUNCH(lanczos_scale_kernel, nbs, K_THREADS, 0, st, nd, w, pb, nb, beta + 2 * j, vj + nd); rn::g_launches++; }
     KRY_CUDA(cudaGetLastError());
     const bool check = j > 3 && (j % 2 == 0);
     if (check) {

@@ -113,6 +113,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   double* __restrict__ C, int m, int n, long ldc, int rowsA, int rowsB, int kblocks,
                   int nslices, int tiles_m, int tiles_n, int n_full, int ksplit_tail, int kb_per_split,
                   double* __restrict__ partial, int* __restrict__ counters) {
+  pdl_trigger();
   extern __shared__ unsigned char oz_smem_raw[];
   const uint32_t raw = smem_u32(oz_smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-B aligned operand ring
@@ -164,6 +165,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // barriers and TMEM are set up while the previous kernel drains; its results are needed from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // Levels are processed in PAIRS (lo, hi = lo + 1) so that operand tiles are shared between digit
   // products: step s of a pair loads A-slice s and B-slice hi - s and feeds TWO products,
@@ -360,6 +363,7 @@ template <int FORM, int WPR>
 __global__ void __launch_bounds__(256)
 ozaki_split_kernel(const double* __restrict__ X, long ld, int rows, int K, int Kp, int nslices,
                    signed char* __restrict__ q, double* __restrict__ scale, int conj_left) {
+  pdl_wait();
   __shared__ double smx[8];
   const int warp = threadIdx.x >> 5;
   const int lane = WPR == 1 ? (threadIdx.x & 31) : threadIdx.x;       // position inside the row team
@@ -423,6 +427,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(256)
 ozaki_split_t_kernel(const double* __restrict__ src, long s_col, int rows, int cols, int Kp, int nslices,
                      signed char* __restrict__ q, double* __restrict__ scale, int chunks_per_block) {
+  pdl_wait();
   constexpr int CT = CPLX ? 32 : 64;             // source columns per chunk
   constexpr int OR = CPLX ? 2 * OZT_RT : OZT_RT; // out rows per block
   __shared__ __align__(16) signed char stage[OZ_MAX_SLICES * OR * OZT_LD];
@@ -509,6 +514,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(256)
 wapply_split_kernel(WApplyParams p, int Kp, int nslices, signed char* __restrict__ q,
                     double* __restrict__ scale) {
+  pdl_wait();
   using T = typename std::conditional<CPLX, double2, double>::type;
   extern __shared__ __align__(16) double ws_row[];
   __shared__ double red[8];
@@ -612,9 +618,9 @@ int launch_ozaki_split(cudaStream_t st, const double* X, long ld, int rows, int 
   if (rows <= 0) return 0;
   const int Kp = (K + 15) & ~15;
   if (rows >= 2048 || K < 512)
-    { ozaki_split_kernel<0, 1><<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
+    { RN_LAUNCH((ozaki_split_kernel<0, 1>), (unsigned)ceil_div(rows, 8), 256, 0, st, X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
   else
-    { ozaki_split_kernel<0, 8><<<(unsigned)rows, 256, 0, st>>>(X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
+    { RN_LAUNCH((ozaki_split_kernel<0, 8>), (unsigned)rows, 256, 0, st, X, ld, rows, K, Kp, nslices, q, scale, 0); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -626,9 +632,9 @@ int launch_ozaki_split_bform(cudaStream_t st, const double* X, long ld, int crow
   if (crows <= 0) return 0;
   const int K = 2 * ccols, Kp = (K + 15) & ~15;
   if (crows >= 2048 || K < 512)
-    { ozaki_split_kernel<1, 1><<<(unsigned)ceil_div(crows, 8), 256, 0, st>>>(X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
+    { RN_LAUNCH((ozaki_split_kernel<1, 1>), (unsigned)ceil_div(crows, 8), 256, 0, st, X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
   else
-    { ozaki_split_kernel<1, 8><<<(unsigned)crows, 256, 0, st>>>(X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
+    { RN_LAUNCH((ozaki_split_kernel<1, 8>), (unsigned)crows, 256, 0, st, X, ld, crows, K, Kp, nslices, q, scale, conj_left); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -646,8 +652,8 @@ int launch_ozaki_split_t(cudaStream_t st, int cplx, const void* src, long s_col,
   const int cpb = (nchunks + by - 1) / by;
   by = (nchunks + cpb - 1) / cpb;
   dim3 grid((unsigned)bx, (unsigned)by);
-  if (cplx) { ozaki_split_t_kernel<true><<<grid, 256, 0, st>>>((const double*)src, s_col, rows, cols, Kp, nslices, q, scale, cpb); rn::g_launches++; }
-  else { ozaki_split_t_kernel<false><<<grid, 256, 0, st>>>((const double*)src, s_col, rows, cols, Kp, nslices, q, scale, cpb); rn::g_launches++; }
+  if (cplx) { RN_LAUNCH(ozaki_split_t_kernel<true>, grid, 256, 0, st, (const double*)src, s_col, rows, cols, Kp, nslices, q, scale, cpb); rn::g_launches++; }
+  else { RN_LAUNCH(ozaki_split_t_kernel<false>, grid, 256, 0, st, (const double*)src, s_col, rows, cols, Kp, nslices, q, scale, cpb); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -671,8 +677,8 @@ int launch_wapply_split(cudaStream_t st, int cplx, const WApplyParams& p, int ns
     else RN_CHECK(cudaFuncSetAttribute(wapply_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     max_set[cplx] = 160 * 1024;
   }
-  if (cplx) { wapply_split_kernel<true><<<(unsigned)rows, 256, smem, st>>>(p, Kp, nslices, q, scale); rn::g_launches++; }
-  else { wapply_split_kernel<false><<<(unsigned)rows, 256, smem, st>>>(p, Kp, nslices, q, scale); rn::g_launches++; }
+  if (cplx) { RN_LAUNCH(wapply_split_kernel<true>, (unsigned)rows, 256, smem, st, p, Kp, nslices, q, scale); rn::g_launches++; }
+  else { RN_LAUNCH(wapply_split_kernel<false>, (unsigned)rows, 256, smem, st, p, Kp, nslices, q, scale); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -741,7 +747,7 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
     counters = reinterpret_cast<int*>(reinterpret_cast<char*>(partial) + pbytes);
     RN_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)split_tiles, st));
   }
-  { ozaki_gemm_kernel<<<(unsigned)(n_full + split_tiles * ksplit), OZ_THREADS, OZ_SMEM, st>>>(
+  { RN_LAUNCH(ozaki_gemm_kernel, (unsigned)(n_full + split_tiles * ksplit), OZ_THREADS, OZ_SMEM, st, 
       *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, n_full, ksplit > 1 ? ksplit : 1, kb_per,
       partial, counters); rn::g_launches++; }
   RN_LAUNCH_CHECK();

@@ -27,6 +27,7 @@ template <bool CPLX, int MODE>
 __global__ void __launch_bounds__(256)
 pack_kernel(const typename Elt<CPLX>::T* __restrict__ src, double* __restrict__ dst, int rows,
             int cols, long s_row, long s_col, long dst_ld, int conj_flag, int c_fast) {
+  pdl_wait();
   using T = typename Elt<CPLX>::T;
   __shared__ T tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -69,13 +70,13 @@ int launch_pack(cudaStream_t st, int cplx, int mode, int conj_flag, int rows, in
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
   const int c_fast = s_col <= s_row;
   if (!cplx)
-    { pack_kernel<false, 0><<<grid, block, 0, st>>>((const double*)src, dst, rows, cols, s_row,
+    { RN_LAUNCH((pack_kernel<false, 0>), grid, block, 0, st, (const double*)src, dst, rows, cols, s_row,
                                                    s_col, dst_ld, 0, c_fast); rn::g_launches++; }
   else if (mode == 0)
-    { pack_kernel<true, 0><<<grid, block, 0, st>>>((const double2*)src, dst, rows, cols, s_row,
+    { RN_LAUNCH((pack_kernel<true, 0>), grid, block, 0, st, (const double2*)src, dst, rows, cols, s_row,
                                                   s_col, dst_ld, conj_flag, c_fast); rn::g_launches++; }
   else
-    { pack_kernel<true, 1><<<grid, block, 0, st>>>((const double2*)src, dst, rows, cols, s_row,
+    { RN_LAUNCH((pack_kernel<true, 1>), grid, block, 0, st, (const double2*)src, dst, rows, cols, s_row,
                                                   s_col, dst_ld, conj_flag, c_fast); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;

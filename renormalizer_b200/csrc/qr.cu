@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 house_step_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, long ldt, int j,
                   typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
                   double* __restrict__ rdiag) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   __shared__ double scratch[2 * Q_CPB * 32];
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 house_applyq_kernel(typename Cx<CPLX>::T* __restrict__ Qt, int m, int k, long ldt, int j,
                     const typename Cx<CPLX>::T* __restrict__ V,
                     const typename Cx<CPLX>::T* __restrict__ tau_in) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   __shared__ double scratch[2 * Q_CPB * 32];
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 house_factor_coop_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, int k, long ldt,
                          typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
                          double* __restrict__ rdiag) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   __shared__ double scratch[2 * Q_CPB * 32];
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 house_formq_kernel(typename Cx<CPLX>::T* __restrict__ Qt, int m, int k, long ldt,
                    const typename Cx<CPLX>::T* __restrict__ V,
                    const typename Cx<CPLX>::T* __restrict__ tau_in) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   __shared__ double scratch[2 * Q_CPB * 32];
@@ -321,6 +325,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 house_factor_flow_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, int k, long ldt,
                          typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
                          double* __restrict__ rdiag, double* __restrict__ colinfo, int* __restrict__ ready) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   __shared__ double scratch[2 * Q_CPB * 32];
@@ -415,6 +420,7 @@ house_factor_flow_smem_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int 
                               typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
                               double* __restrict__ rdiag, double* __restrict__ colinfo,
                               int* __restrict__ ready, int cpb) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   extern __shared__ __align__(16) unsigned char qr_smem_raw[];
@@ -502,6 +508,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 house_factor_panel_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, int n, int k, long ldt,
                           typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
                           double* __restrict__ rdiag, int* __restrict__ ready) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   extern __shared__ __align__(16) unsigned char qr_smem_raw[];
@@ -639,6 +646,7 @@ __global__ void __launch_bounds__(256)
 house_formq_warp_kernel(typename Cx<CPLX>::T* __restrict__ Qt, int m, int k, long ldt,
                         const typename Cx<CPLX>::T* __restrict__ V,
                         const typename Cx<CPLX>::T* __restrict__ tau_in) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   const int lane = threadIdx.x & 31;
@@ -675,6 +683,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(QT_THREADS)
 house_build_t_kernel(const typename Cx<CPLX>::T* __restrict__ V, const typename Cx<CPLX>::T* __restrict__ tau_in,
                      int m, int k, long ldt, typename Cx<CPLX>::T* __restrict__ Tall) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   __shared__ double scratch[2 * Q_GB * Q_GB * 32 / 2];   // 28 pairs * 2 <= 64 values
@@ -731,6 +740,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 house_formq_blocked_kernel(typename Cx<CPLX>::T* __restrict__ Qt, int m, int k, long ldt,
                            const typename Cx<CPLX>::T* __restrict__ V,
                            const typename Cx<CPLX>::T* __restrict__ Tall) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   __shared__ double scratch[2 * Q_GB * Q_QCOLS * 32];
@@ -809,6 +819,7 @@ house_formq_blocked_kernel(typename Cx<CPLX>::T* __restrict__ Qt, int m, int k, 
 
 template <bool CPLX>
 __global__ void set_identity_rows_kernel(typename Cx<CPLX>::T* Qt, int m, int k, long ldt) {
+  pdl_wait();
   using C = Cx<CPLX>;
   const long total = (long)k * m;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -823,6 +834,7 @@ template <bool CPLX>
 __global__ void extract_r_kernel(const typename Cx<CPLX>::T* __restrict__ At, const double* __restrict__ rdiag,
                                  int n, int k, long ldt, typename Cx<CPLX>::T* __restrict__ Rout,
                                  long ldr, int lq) {
+  pdl_wait();
   using C = Cx<CPLX>;
   const long total = (long)k * n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -912,15 +924,15 @@ static int qr_colmajor(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, 
       { RN_CHECK(cudaLaunchCooperativeKernel((void*)house_factor_coop_kernel<CPLX>, dim3(nb), dim3(Q_THREADS),
                                            args, 0, st)); rn::g_launches++; }
     if (g_qr_warp_formq == 1)
-      { house_formq_warp_kernel<CPLX><<<(unsigned)ceil_div(k, 8), 256, 0, st>>>(Qt, m, k, ldt, V, tau); rn::g_launches++; }
+      { RN_LAUNCH(house_formq_warp_kernel<CPLX>, (unsigned)ceil_div(k, 8), 256, 0, st, Qt, m, k, ldt, V, tau); rn::g_launches++; }
     else if (g_qr_warp_formq == 2)
-      { house_formq_kernel<CPLX><<<(unsigned)ceil_div(k, Q_CPB), Q_THREADS, 0, st>>>(Qt, m, k, ldt, V, tau); rn::g_launches++; }
+      { RN_LAUNCH(house_formq_kernel<CPLX>, (unsigned)ceil_div(k, Q_CPB), Q_THREADS, 0, st, Qt, m, k, ldt, V, tau); rn::g_launches++; }
     else {
       typename Cx<CPLX>::T* Tall = nullptr;
       const int ngroups = (int)ceil_div(k, Q_GB);
       RN_CHECK(cudaMallocAsync((void**)&Tall, sizeof(typename Cx<CPLX>::T) * (size_t)ngroups * Q_GB * Q_GB, st));
-      { house_build_t_kernel<CPLX><<<ngroups, QT_THREADS, 0, st>>>(V, tau, m, k, ldt, Tall); rn::g_launches++; }
-      { house_formq_blocked_kernel<CPLX><<<(unsigned)ceil_div(k, Q_QCOLS), Q_THREADS, 0, st>>>(Qt, m, k, ldt, V, Tall); rn::g_launches++; }
+      { RN_LAUNCH(house_build_t_kernel<CPLX>, ngroups, QT_THREADS, 0, st, V, tau, m, k, ldt, Tall); rn::g_launches++; }
+      { RN_LAUNCH(house_formq_blocked_kernel<CPLX>, (unsigned)ceil_div(k, Q_QCOLS), Q_THREADS, 0, st, Qt, m, k, ldt, V, Tall); rn::g_launches++; }
       RN_CHECK(cudaFreeAsync(Tall, st));
     }
     RN_LAUNCH_CHECK();
@@ -931,15 +943,15 @@ static int qr_colmajor(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, 
   for (int j = 0; j < k; ++j) {
     int nb = (int)ceil_div(n - j - 1, Q_CPB);
     if (nb < 1) nb = 1;
-    { house_step_kernel<CPLX><<<nb, Q_THREADS, 0, st>>>(At, m, n, ldt, j, V, tau, rdiag); rn::g_launches++; }
+    { RN_LAUNCH(house_step_kernel<CPLX>, nb, Q_THREADS, 0, st, At, m, n, ldt, j, V, tau, rdiag); rn::g_launches++; }
   }
   RN_LAUNCH_CHECK();
   int nbi = (int)ceil_div((long)k * m, 256);
   if (nbi > 1184) nbi = 1184;
-  { set_identity_rows_kernel<CPLX><<<nbi, 256, 0, st>>>(Qt, m, k, ldt); rn::g_launches++; }
+  { RN_LAUNCH(set_identity_rows_kernel<CPLX>, nbi, 256, 0, st, Qt, m, k, ldt); rn::g_launches++; }
   for (int j = k - 1; j >= 0; --j) {
     const int nb = (int)ceil_div(k - j, Q_CPB);
-    { house_applyq_kernel<CPLX><<<nb, Q_THREADS, 0, st>>>(Qt, m, k, ldt, j, V, tau); rn::g_launches++; }
+    { RN_LAUNCH(house_applyq_kernel<CPLX>, nb, Q_THREADS, 0, st, Qt, m, k, ldt, j, V, tau); rn::g_launches++; }
   }
   RN_LAUNCH_CHECK();
   return 0;
@@ -976,7 +988,7 @@ static int qr_driver(cudaStream_t st, int lq, int m, int n, const void* A, long 
   if (err) return err;
   int nbr = (int)ceil_div((long)k * nt, 256);
   if (nbr > 1184) nbr = 1184;
-  { extract_r_kernel<CPLX><<<nbr, 256, 0, st>>>(At, rdiag, nt, k, ldt, (T*)R, ldr, lq); rn::g_launches++; }
+  { RN_LAUNCH(extract_r_kernel<CPLX>, nbr, 256, 0, st, At, rdiag, nt, k, ldt, (T*)R, ldr, lq); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   if (!lq) {
     // Q[r][c] = Qt[c][r]

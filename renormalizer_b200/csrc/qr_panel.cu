@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(QP_THREADS, 1)
 house_panel_cluster_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, long ldt, int j0, int bw, int rloc,
                            typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
                            double* __restrict__ rdiag, typename Cx<CPLX>::T* __restrict__ Tout) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   cg::cluster_group cluster = cg::this_cluster();
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(512, 1)
 house_panel_reg_kernel(typename Cx<CPLX>::T* __restrict__ At, int m, long ldt, int j0, int bw, int rloc,
                        typename Cx<CPLX>::T* __restrict__ V, typename Cx<CPLX>::T* __restrict__ tau_out,
                        double* __restrict__ rdiag, typename Cx<CPLX>::T* __restrict__ Tout) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   constexpr int BW = 16 * NCOL;
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(256)
 wy_dots_kernel(const typename Cx<CPLX>::T* __restrict__ X, long ldx, int c_begin, int c_end, int m, int j0,
                int bw, const typename Cx<CPLX>::T* __restrict__ V, long ldv,
                typename Cx<CPLX>::T* __restrict__ Ypart, int ncols_pad) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   extern __shared__ __align__(16) unsigned char wy_smem_raw[];
@@ -524,6 +527,7 @@ wy_update_kernel(typename Cx<CPLX>::T* __restrict__ X, long ldx, int c_begin, in
                  const typename Cx<CPLX>::T* __restrict__ V, long ldv,
                  const typename Cx<CPLX>::T* __restrict__ Tmat, int trans,
                  const typename Cx<CPLX>::T* __restrict__ Ypart, int nchunks, int ncols_pad) {
+  pdl_wait();
   using C = Cx<CPLX>;
   using T = typename C::T;
   extern __shared__ __align__(16) unsigned char wy_smem_raw[];
@@ -610,6 +614,7 @@ wy_update_kernel(typename Cx<CPLX>::T* __restrict__ X, long ldx, int c_begin, in
 
 template <bool CPLX>
 __global__ void qp_identity_rows_kernel(typename Cx<CPLX>::T* Qt, int m, int k, long ldt) {
+  pdl_wait();
   using C = Cx<CPLX>;
   const long total = (long)k * m;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -638,8 +643,8 @@ static int wy_apply(cudaStream_t st, typename Cx<CPLX>::T* X, long ldx, int c_be
     RN_CHECK(cudaFuncSetAttribute(wy_update_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     attr_done[CPLX ? 1 : 0] = true;
   }
-  { wy_dots_kernel<CPLX><<<grid, 256, smem_a, st>>>(X, ldx, c_begin, c_end, m, j0, bw, V, ldv, Ypart, ncols_pad); rn::g_launches++; }
-  { wy_update_kernel<CPLX><<<grid, 256, smem_b, st>>>(X, ldx, c_begin, c_end, m, j0, bw, V, ldv, Tmat, trans, Ypart,
+  { RN_LAUNCH(wy_dots_kernel<CPLX>, grid, 256, smem_a, st, X, ldx, c_begin, c_end, m, j0, bw, V, ldv, Ypart, ncols_pad); rn::g_launches++; }
+  { RN_LAUNCH(wy_update_kernel<CPLX>, grid, 256, smem_b, st, X, ldx, c_begin, c_end, m, j0, bw, V, ldv, Tmat, trans, Ypart,
                                                       nchunks, ncols_pad); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
@@ -742,7 +747,7 @@ int qr_colmajor_panel(cudaStream_t st, int m, int n, typename Cx<CPLX>::T* At, l
   // Q = H_0 ... H_{k-1} I, panels applied last to first; panel p only touches columns >= j0
   int nbi = (int)ceil_div((long)k * m, 256);
   if (nbi > 1184) nbi = 1184;
-  { qp_identity_rows_kernel<CPLX><<<nbi, 256, 0, st>>>(Qt, m, k, ldt); rn::g_launches++; }
+  { RN_LAUNCH(qp_identity_rows_kernel<CPLX>, nbi, 256, 0, st, Qt, m, k, ldt); rn::g_launches++; }
   for (int p = npanels - 1; p >= 0; --p) {
     const int j0 = p * bw_max;
     const int bw = (k - j0) < bw_max ? (k - j0) : bw_max;

@@ -19,6 +19,7 @@ jacobi_round_kernel(typename std::conditional<CPLX, double2, double>::type* __re
                     typename std::conditional<CPLX, double2, double>::type* __restrict__ Vw,
                     int m, int n, int nv, long ldt, long ldv, int round, int N, double tol,
                     int* __restrict__ rotated) {
+  pdl_wait();
   using T = typename std::conditional<CPLX, double2, double>::type;
   __shared__ double scratch[4 * 32];
   int p, q;
@@ -78,6 +79,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(J_THREADS)
 jacobi_finalize_kernel(typename std::conditional<CPLX, double2, double>::type* __restrict__ At,
                        int m, long ldt, double* __restrict__ S) {
+  pdl_wait();
   using T = typename std::conditional<CPLX, double2, double>::type;
   __shared__ double scratch[32];
   T* x = At + (long)blockIdx.x * ldt;
@@ -98,6 +100,7 @@ jacobi_finalize_kernel(typename std::conditional<CPLX, double2, double>::type* _
 
 template <bool CPLX>
 __global__ void jacobi_eye_kernel(typename std::conditional<CPLX, double2, double>::type* Vw, int n, long ldv) {
+  pdl_wait();
   const long total = (long)n * n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i / n), r = (int)(i % n);
@@ -128,7 +131,7 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
   if (err) return err;
   int nbe = (int)ceil_div((long)nt * nt, 256);
   if (nbe > 1184) nbe = 1184;
-  { jacobi_eye_kernel<CPLX><<<nbe, 256, 0, st>>>(Vw, nt, ldv); rn::g_launches++; }
+  { RN_LAUNCH(jacobi_eye_kernel<CPLX>, nbe, 256, 0, st, Vw, nt, ldv); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   const int N = (nt + 1) & ~1;  // even number of players
   const double tol = sqrt((double)mt) * 2.220446049250313e-16;
@@ -137,7 +140,7 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
     for (; sweeps < max_sweeps; ++sweeps) {
       RN_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
       for (int round = 0; round < N - 1; ++round)
-        { jacobi_round_kernel<CPLX><<<N / 2, J_THREADS, 0, st>>>(At, Vw, mt, nt, nt, ldt, ldv, round, N, tol, flag); rn::g_launches++; }
+        { RN_LAUNCH(jacobi_round_kernel<CPLX>, N / 2, J_THREADS, 0, st, At, Vw, mt, nt, nt, ldt, ldv, round, N, tol, flag); rn::g_launches++; }
       RN_LAUNCH_CHECK();
       int h = 0;
       RN_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -146,7 +149,7 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
     }
   }
   if (sweeps_out) *sweeps_out = sweeps;
-  { jacobi_finalize_kernel<CPLX><<<nt, J_THREADS, 0, st>>>(At, mt, ldt, S); rn::g_launches++; }
+  { RN_LAUNCH(jacobi_finalize_kernel<CPLX>, nt, J_THREADS, 0, st, At, mt, ldt, S); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   if (!wide) {
     // U[r][c] = At[c][r];  Vh[c][j] = conj(V[j][c]) = conj(Vw[c][j])

@@ -13,6 +13,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(V_THREADS)
 multi_dot_partial_kernel(const double* __restrict__ V, long ld, const double* __restrict__ x,
                          long n, double* __restrict__ partial) {
+  pdl_wait();
   __shared__ double scratch[64];
   const double* v = V + (long)blockIdx.y * ld;
   double acc[2] = {0.0, 0.0};
@@ -37,6 +38,7 @@ multi_dot_partial_kernel(const double* __restrict__ V, long ld, const double* __
 // out[2i + {0,1}] = sum_b partial[i][b]; post == 1: out[2i] = sqrt(re), out[2i+1] = 0
 __global__ void __launch_bounds__(32)
 reduce_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out, int post) {
+  pdl_wait();
   double re = 0.0, im = 0.0;
   for (int b = threadIdx.x; b < nb; b += 32) {
     re += partial[((long)blockIdx.x * nb + b) * 2 + 0];
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(V_THREADS)
 lanczos_update_kernel(long nd, double* __restrict__ w, const double* __restrict__ vj,
                       const double* __restrict__ vjm1, const double* __restrict__ alpha_ptr,
                       const double* __restrict__ beta_ptr, double* __restrict__ partial) {
+  pdl_wait();
   __shared__ double scratch[64];
   const double alpha = alpha_ptr[0];
   const double beta = (beta_ptr != nullptr && vjm1 != nullptr) ? beta_ptr[0] : 0.0;
@@ -78,6 +81,7 @@ lanczos_update_kernel(long nd, double* __restrict__ w, const double* __restrict_
 __global__ void __launch_bounds__(V_THREADS)
 scale_inv_kernel(long nd, const double* __restrict__ x, const double* __restrict__ s,
                  double* __restrict__ out) {
+  pdl_wait();
   const double inv = 1.0 / s[0];
   const long step = (long)gridDim.x * blockDim.x;
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += step) out[k] = x[k] * inv;
@@ -88,6 +92,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(V_THREADS)
 lincomb_kernel(long n, int nvec, const double* __restrict__ V, long ld,
                const double* __restrict__ coef, double* __restrict__ out) {
+  pdl_wait();
   const long step = (long)gridDim.x * blockDim.x;
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
     if constexpr (CPLX) {
@@ -112,6 +117,7 @@ template <bool CPLX>
 __global__ void __launch_bounds__(V_THREADS)
 allclose_kernel(long n, const double* __restrict__ a, const double* __restrict__ b, double rtol,
                 double atol, int* __restrict__ violations) {
+  pdl_wait();
   int bad = 0;
   const long step = (long)gridDim.x * blockDim.x;
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
@@ -148,10 +154,10 @@ extern "C" int rn_multi_dot(void* stream, int cplx, long n, int nvec, const doub
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = nblocks_for(n);
   dim3 grid(nb, nvec);
-  if (cplx) { multi_dot_partial_kernel<true><<<grid, V_THREADS, 0, st>>>(V, ld, x, n, ws); rn::g_launches++; }
-  else { multi_dot_partial_kernel<false><<<grid, V_THREADS, 0, st>>>(V, ld, x, n, ws); rn::g_launches++; }
+  if (cplx) { RN_LAUNCH(multi_dot_partial_kernel<true>, grid, V_THREADS, 0, st, V, ld, x, n, ws); rn::g_launches++; }
+  else { RN_LAUNCH(multi_dot_partial_kernel<false>, grid, V_THREADS, 0, st, V, ld, x, n, ws); rn::g_launches++; }
   RN_LAUNCH_CHECK();
-  { reduce_final_kernel<<<nvec, 32, 0, st>>>(ws, nb, out, 0); rn::g_launches++; }
+  { RN_LAUNCH(reduce_final_kernel, nvec, 32, 0, st, ws, nb, out, 0); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -161,9 +167,9 @@ extern "C" int rn_lanczos_update(void* stream, long nd, double* w, const double*
                                  double* ws, double* beta_out) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = nblocks_for(nd);
-  { lanczos_update_kernel<<<nb, V_THREADS, 0, st>>>(nd, w, vj, vjm1, alpha, beta_prev, ws); rn::g_launches++; }
+  { RN_LAUNCH(lanczos_update_kernel, nb, V_THREADS, 0, st, nd, w, vj, vjm1, alpha, beta_prev, ws); rn::g_launches++; }
   RN_LAUNCH_CHECK();
-  { reduce_final_kernel<<<1, 32, 0, st>>>(ws, nb, beta_out, 1); rn::g_launches++; }
+  { RN_LAUNCH(reduce_final_kernel, 1, 32, 0, st, ws, nb, beta_out, 1); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -171,7 +177,7 @@ extern "C" int rn_lanczos_update(void* stream, long nd, double* w, const double*
 extern "C" int rn_scale_inv(void* stream, long nd, const double* x, const double* s, double* out) {
   cudaStream_t st = (cudaStream_t)stream;
   int nb = nblocks_for(nd) * 4;
-  { scale_inv_kernel<<<nb, V_THREADS, 0, st>>>(nd, x, s, out); rn::g_launches++; }
+  { RN_LAUNCH(scale_inv_kernel, nb, V_THREADS, 0, st, nd, x, s, out); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -182,8 +188,8 @@ extern "C" int rn_lincomb(void* stream, int cplx, long n, int nvec, const double
   int nb = (int)ceil_div(n, V_THREADS);
   if (nb > 148 * 8) nb = 148 * 8;
   if (nb < 1) nb = 1;
-  if (cplx) { lincomb_kernel<true><<<nb, V_THREADS, 0, st>>>(n, nvec, V, ld, coef, out); rn::g_launches++; }
-  else { lincomb_kernel<false><<<nb, V_THREADS, 0, st>>>(n, nvec, V, ld, coef, out); rn::g_launches++; }
+  if (cplx) { RN_LAUNCH(lincomb_kernel<true>, nb, V_THREADS, 0, st, n, nvec, V, ld, coef, out); rn::g_launches++; }
+  else { RN_LAUNCH(lincomb_kernel<false>, nb, V_THREADS, 0, st, n, nvec, V, ld, coef, out); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -194,8 +200,8 @@ extern "C" int rn_allclose(void* stream, int cplx, long n, const double* a, cons
   RN_CHECK(cudaMemsetAsync(violations, 0, sizeof(int), st));
   if (n <= 0) return 0;
   int nb = nblocks_for(n) * 2;
-  if (cplx) { allclose_kernel<true><<<nb, V_THREADS, 0, st>>>(n, a, b, rtol, atol, violations); rn::g_launches++; }
-  else { allclose_kernel<false><<<nb, V_THREADS, 0, st>>>(n, a, b, rtol, atol, violations); rn::g_launches++; }
+  if (cplx) { RN_LAUNCH(allclose_kernel<true>, nb, V_THREADS, 0, st, n, a, b, rtol, atol, violations); rn::g_launches++; }
+  else { RN_LAUNCH(allclose_kernel<false>, nb, V_THREADS, 0, st, n, a, b, rtol, atol, violations); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }

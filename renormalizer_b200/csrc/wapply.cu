@@ -17,6 +17,7 @@ namespace rn {
 
 template <bool CPLX>
 __global__ void __launch_bounds__(256) wapply_kernel(WApplyParams p) {
+  pdl_wait();
   using T = typename std::conditional<CPLX, double2, double>::type;
   extern __shared__ __align__(16) unsigned char w_smem_raw[];
   T* s_in = reinterpret_cast<T*>(w_smem_raw);
@@ -82,8 +83,8 @@ int launch_wapply(cudaStream_t st, int cplx, const WApplyParams& in_p) {
     max_set[cplx] = 200 * 1024;
   }
   dim3 grid((unsigned)p.X, (unsigned)ceil_div(p.Y, yt));
-  if (cplx) { wapply_kernel<true><<<grid, 256, smem, st>>>(p); rn::g_launches++; }
-  else { wapply_kernel<false><<<grid, 256, smem, st>>>(p); rn::g_launches++; }
+  if (cplx) { RN_LAUNCH(wapply_kernel<true>, grid, 256, smem, st, p); rn::g_launches++; }
+  else { RN_LAUNCH(wapply_kernel<false>, grid, 256, smem, st, p); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   return 0;
 }

@@ -21,7 +21,12 @@ def optimize_mps(mps, mpo, omega: float = None):
     """DMRG ground state algorithm (gs.py:54-171).  `mps` is overwritten during the optimisation;
     returns (energies of each macro sweep, optimised mps)."""
     if omega is not None:
-        raise NotImplementedError("omega targeting ((H-omega)^2) is outside the accelerated path")
+        # gs.py:106-111: the variational function (H - omega)^2.  The reference keeps two MPO layers
+        # in 4-index environments; here the same operator is ONE MPO whose bonds are the merged
+        # pairs (mpo.squared), so environments, H_eff and the sweep run on the one-layer kernels.
+        from .mpo import Mpo
+        shifted = mpo.add(Mpo.identity_like(mpo).scale(-omega))
+        mpo = shifted.squared()
     if mps.optimize_config.nroots != 1:
         raise NotImplementedError("state-averaged DMRG (nroots > 1) is outside the accelerated path")
     assert mps.optimize_config.method in ["2site", "1site"]
@@ -44,7 +49,7 @@ def optimize_mps(mps, mpo, omega: float = None):
                                                  max_bonddim=int(compress_config))
         else:
             assert False
-        micro_iteration_result, res_mps, mpo = single_sweep(mps, mpo, environ, omega, percent, opt_e_idx)
+        micro_iteration_result, res_mps, mpo = single_sweep(mps, mpo, environ, None, percent, opt_e_idx)
         opt_e = min(micro_iteration_result)
         macro_iteration_result.append(opt_e[0])
         opt_e_idx = opt_e[1]

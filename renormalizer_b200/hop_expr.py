@@ -21,12 +21,36 @@ def hop_expr(ltensor, rtensor, cmo, cshape, twolayer: bool = False):
     """Return `expr` with expr(cstruct) = H_eff . cstruct for the centre tensor of shape cshape.
 
     Same arguments as the reference (hop_expr.py:7): ltensor (a,b,c), rtensor (l,f,k), cmo a list
-    of 0, 1 or 2 MPO site tensors, cshape with or without ancilla indices.  The two-layer
-    (H - omega)^2 expressions (hop_expr.py:24-52) are outside the accelerated path.
+    of 0, 1 or 2 MPO site tensors, cshape with or without ancilla indices.
+
+    twolayer=True (hop_expr.py:24-52, the (H - omega)^2 expressions): ltensor (a,b,c,d) and
+    rtensor (j,g,i,k) carry two MPO bonds and the result is
+        out[d,h,k]   = L[a,b,c,d] W[b,e,f,g] W[c,f,h,i] R[j,g,i,k] C[a,e,j]        (one site)
+        out[d,h,m,p] = L W1 W1 W2 W2 R C                                         (two sites).
+    It runs on the same kernels as the one-layer case: the pair of MPO bonds is merged into one
+    index, the MPO site becomes the product site of `mpo.two_layer_site` and the environments
+    are read with their outer bonds exchanged (input on the a side, output on the d side).
     """
-    if twolayer:
-        raise NotImplementedError("two-layer (omega-targeting) H_eff is outside the accelerated path")
     ltensor, rtensor = asxp(ltensor), asxp(rtensor)
+    if twolayer:
+        import numpy as np
+        from .mpo import two_layer_site
+        nsite = len(cmo)
+        if nsite not in (1, 2) or len(cshape) != nsite + 2:
+            raise AssertionError("two-layer expressions exist for 1 or 2 sites without ancilla")
+        a, b, c, d = ltensor.shape
+        j, g, i, k = rtensor.shape
+        lt = ltensor.permute(3, 1, 2, 0).reshape(d, b * c, a).contiguous()
+        rt = rtensor.permute(3, 1, 2, 0).reshape(k, g * i, j).contiguous()
+        sites = []
+        for m in cmo:
+            w = np.asarray(ops.as_mpo_site(m).array)
+            # out index h is the DOWN index of the lower layer, the contracted e the UP index of
+            # the upper layer: as a one-layer site W'[(b,c), h, e, (g,i)]
+            sites.append(ops.MpoSite(np.ascontiguousarray(two_layer_site(w, w).transpose(0, 2, 1, 3))))
+        cplx = lt.is_complex() or rt.is_complex()
+        dtype = torch.complex128 if cplx else torch.float64
+        return _HopCallable(ops.HopPlan(lt, rt, sites, cshape, dtype))
     sites = [ops.as_mpo_site(m) for m in cmo]
     cplx = ltensor.is_complex() or rtensor.is_complex()
     dtype = torch.complex128 if cplx else torch.float64

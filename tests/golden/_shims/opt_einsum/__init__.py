@@ -14,6 +14,9 @@ def contract(*args, **kwargs):
     opt = kwargs.pop("optimize", "optimal")
     if opt not in ("optimal", "greedy", True, False):
         opt = "optimal"
+    nops = sum(1 for a in args if not isinstance(a, str))
+    if nops > 5 and opt == "optimal":
+        opt = "greedy"
     return np.einsum(*args, optimize=opt)
 
 
@@ -23,6 +26,8 @@ def contract_expression(subscripts, *operands, constants=None, optimize="optimal
     const_ops = {i: operands[i] for i in constants}
     var_pos = [i for i in range(n) if i not in const_ops]
 
+    cache = {}
+
     def expr(*arrays, backend=None, **kw):
         assert len(arrays) == len(var_pos)
         ops = [None] * n
@@ -30,6 +35,10 @@ def contract_expression(subscripts, *operands, constants=None, optimize="optimal
             ops[i] = a
         for i, a in zip(var_pos, arrays):
             ops[i] = a
-        return np.einsum(subscripts, *ops, optimize="optimal")
+        # the contraction path is searched once per expression (the two-layer expressions have
+        # up to seven operands: an "optimal" search on every call would dominate the run time)
+        if "path" not in cache:
+            cache["path"] = np.einsum_path(subscripts, *ops, optimize="optimal" if n <= 5 else "greedy")[0]
+        return np.einsum(subscripts, *ops, optimize=cache["path"])
 
     return expr

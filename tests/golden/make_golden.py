@@ -72,6 +72,13 @@ def gen_kernels():
         out[f"{tag}_hop2"] = hop_expr(L, R, [W1.copy(), W2.copy()], C2.shape)(C2)
         out[f"{tag}_hop1a"] = hop_expr(L, R1, [W1.copy()], C1a.shape)(C1a)
         out[f"{tag}_hop2a"] = hop_expr(L, R, [W1.copy(), W2.copy()], C2a.shape)(C2a)
+        # two-layer (H - omega)^2 expressions (hop_expr.py:24-52): 4-index environments
+        L4 = crand(rng, (Ml, w0, w0, Ml), cplx)
+        R41 = crand(rng, (Mr, w1, w1, Mr), cplx)
+        R42 = crand(rng, (Mr, w2, w2, Mr), cplx)
+        out.update({f"{tag}_L4": L4, f"{tag}_R41": R41, f"{tag}_R42": R42})
+        out[f"{tag}_hop1_2l"] = hop_expr(L4, R41, [W1.copy()], C1.shape, twolayer=True)(C1)
+        out[f"{tag}_hop2_2l"] = hop_expr(L4, R42, [W1.copy(), W2.copy()], C2.shape, twolayer=True)(C2)
         # environment updates: MPS site (ndim 3) and MPDM site (ndim 4)
         A3 = crand(rng, (Ml, d1, Mr), cplx)
         A4 = crand(rng, (Ml, d1, anc, Mr), cplx)
@@ -220,6 +227,17 @@ def gen_holstein():
         out[f"{method}_nsweeps"] = np.array(len(micro))
         out[f"{method}_expectation"] = np.array(opt.expectation(mpo))
         dump_mp(f"{method}_opt", opt, out)
+    # omega targeting: (H - omega)^2 with two-layer environments (gs.py:106-111, test_gs.py:66-86)
+    m = mps.copy()
+    m.optimize_config.procedure = procedure
+    m.optimize_config.method = "2site"
+    m.optimize_config.e_atol = 1e-6
+    m.optimize_config.e_rtol = 1e-6
+    np.random.seed(99)
+    energies, opt = optimize_mps(m, mpo, omega=0.084)
+    out["omega"] = np.array(0.084)
+    out["omega_energies"] = np.array(energies)
+    out["omega_expectation"] = np.array(opt.expectation(mpo))
     np.savez_compressed(os.path.join(HERE, "holstein.npz"), **out)
 
 

@@ -425,3 +425,17 @@ def test_qr_graded_columns():
     q, r = (host(x) for x in ops.qr(dev(a)))
     assert np.abs(q.conj().T @ q - np.eye(n)).max() < 1e-12
     assert relerr(q @ r, a) < 1e-12
+
+
+@pytest.mark.parametrize("t", ["r", "c"])
+def test_hop_two_layer_golden(golden, t):
+    """The (H - omega)^2 expressions of hop_expr.py:24-52 (4-index environments, two MPO layers)
+    against vectors produced by the reference's hop_expr(twolayer=True)."""
+    from renormalizer_b200.hop_expr import hop_expr
+    g = golden("kernels")
+    L4, R41, R42, W1, W2 = (g[f"{t}_{k}"] for k in ("L4", "R41", "R42", "W1", "W2"))
+    for name, r, cmo, ck in [("hop1_2l", R41, [W1], "C1"), ("hop2_2l", R42, [W1, W2], "C2")]:
+        c = g[f"{t}_{ck}"]
+        got = host(hop_expr(dev(L4), dev(r), list(cmo), c.shape, twolayer=True)(dev(c)))
+        assert got.shape == g[f"{t}_{name}"].shape
+        assert relerr(got, g[f"{t}_{name}"]) < TOL, name

@@ -304,3 +304,24 @@ def test_dmrg_holstein_golden_tensor_path(golden, tensor_path):
     ref = g["2site_energies"]
     assert abs(energies[-1] - ref[-1]) < 1e-9
     assert abs(opt.expectation(mpo) - float(g["2site_expectation"])) < 1e-9
+
+
+def test_dmrg_omega_targeting_golden(golden):
+    """optimize_mps(..., omega) -- the (H - omega)^2 variational function of gs.py:106-111 -- against
+    the reference run of the same start state and the reference's own acceptance value
+    (mps/tests/test_gs.py:66-86: 0.08401412 + zero point energy)."""
+    from renormalizer_b200.gs import optimize_mps
+    from renormalizer_b200.mpo import Mpo
+    g = golden("holstein")
+    mpo = Mpo(load_mpo(g))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    mps.optimize_config.procedure = [[int(a), float(b)] for a, b in g["procedure"]]
+    mps.optimize_config.method = "2site"
+    mps.optimize_config.e_atol = 1e-6
+    mps.optimize_config.e_rtol = 1e-6
+    np.random.seed(99)
+    energies, opt = optimize_mps(mps, mpo, omega=float(g["omega"]))
+    e = opt.expectation(mpo)
+    assert np.allclose(e, 0.08401412 + float(g["gs_zpe"]))          # the reference's own test
+    assert abs(e - float(g["omega_expectation"])) < 1e-7
+    assert abs(energies[-1] - g["omega_energies"][-1]) < 1e-9

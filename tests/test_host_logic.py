@@ -133,3 +133,36 @@ def test_compute_without_gpu_fails_loudly():
     from renormalizer_b200 import _lib
     with pytest.raises(_lib.RnError):
         _lib.get()
+
+
+def _dense_from_mpo(sites):
+    """Contract MPO site tensors W[b, up, down, f] into the dense operator (rows = up indices)."""
+    cur = sites[0][0]                                   # (up, down, f)
+    cur = cur.transpose(2, 0, 1)[None]                  # dummy: (1, f, up, down)
+    op = sites[0][0].transpose(2, 0, 1)                 # (f, U, D)
+    for w in sites[1:]:
+        op = np.einsum("fUD,fudg->gUuDd", op, w)
+        g, U, u, D, d = op.shape
+        op = op.reshape(g, U * u, D * d)
+    return op[0]
+
+
+def test_mpo_algebra_for_omega_targeting():
+    """Mpo.add / scale / identity_like / squared (gs.py:106-111 needs (H - omega)^2 as an MPO):
+    checked against dense operator algebra."""
+    from renormalizer_b200.mpo import Mpo
+    rng = np.random.default_rng(5)
+    pd = [2, 3, 2, 2]
+    bonds = [1, 3, 4, 2, 1]
+    sites = [rng.standard_normal((bonds[i], pd[i], pd[i], bonds[i + 1])) for i in range(4)]
+    mpo = Mpo(sites)
+    H = _dense_from_mpo(mpo.to_numpy())
+    n = H.shape[0]
+    ident = Mpo.identity_like(mpo)
+    assert np.allclose(_dense_from_mpo(ident.to_numpy()), np.eye(n))
+    shifted = mpo.add(ident.scale(-0.37))
+    Hs = _dense_from_mpo(shifted.to_numpy())
+    assert np.allclose(Hs, H - 0.37 * np.eye(n), atol=1e-13)
+    sq = shifted.squared()
+    assert sq.bond_dims == [b * b for b in shifted.bond_dims]
+    assert np.allclose(_dense_from_mpo(sq.to_numpy()), Hs @ Hs, atol=1e-11)

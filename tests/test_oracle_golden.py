@@ -27,6 +27,17 @@ def test_hop_and_env(golden, t):
     assert relerr(contract.env_update(R1, g[f"{t}_A4"], W1, "R"), g[f"{t}_envR4"]) < TOL
 
 
+@pytest.mark.parametrize("t", ["r", "c"])
+def test_hop_two_layer(golden, t):
+    """Oracle restatement of the two-layer expressions pinned to the reference's own output."""
+    g = golden("kernels")
+    L4, R41, R42, W1, W2 = (g[f"{t}_{k}"] for k in ("L4", "R41", "R42", "W1", "W2"))
+    got = contract.hop_apply_two_layer(L4, R41, [W1], g[f"{t}_C1"])
+    assert relerr(got, g[f"{t}_hop1_2l"]) < 1e-13
+    got = contract.hop_apply_two_layer(L4, R42, [W1, W2], g[f"{t}_C2"])
+    assert relerr(got, g[f"{t}_hop2_2l"]) < 1e-13
+
+
 def test_hop_diag_matches_dense_diagonal(golden):
     g = golden("kernels")
     L, R1, R, W1, W2 = g["r_L"], g["r_R1"], g["r_R"], g["r_W1"], g["r_W2"]
