@@ -301,6 +301,11 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_device()
+    # keep the interpreter's cyclic garbage collector out of the timed region (a collection in the
+    # middle of a half sweep shows up as a multi-millisecond host stall)
+    import gc
+    gc.collect()
+    gc.disable()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -454,7 +459,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sbm_tdvp", choices=["sbm_tdvp", "holstein_dmrg"])

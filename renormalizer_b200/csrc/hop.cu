@@ -92,7 +92,8 @@ static bool use_ozaki(int path, double m, double n, double k) {
 
 // GEMM with pre-split operands (either may be split on the fly from X when `fresh` is given)
 static int oz_gemm(cudaStream_t st, OzOperand& a, const double* a_fresh, long lda, OzOperand& b,
-                   const double* b_fresh, long ldb, double* C, long ldc) {
+                   const double* b_fresh, long ldb, double* C, long ldc, const double* dotv = nullptr,
+                   double* dot_partial = nullptr) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int err;
   if (a_fresh) { err = launch_ozaki_split(st, a_fresh, lda, a.rows, a.K, a.nslices, a.q, a.scale); if (err) return err; }
@@ -102,7 +103,8 @@ static int oz_gemm(cudaStream_t st, OzOperand& a, const double* a_fresh, long ld
     RN_CHECK(cudaEventCreate(&e1));
     RN_CHECK(cudaEventRecord(e0, st));
   }
-  err = launch_ozaki_gemm_maps(st, a.rows, b.rows, a.K, a.nslices, &a.map, a.scale, &b.map, b.scale, C, ldc);
+  err = launch_ozaki_gemm_maps(st, a.rows, b.rows, a.K, a.nslices, &a.map, a.scale, &b.map, b.scale, C, ldc,
+                               dotv, dot_partial);
   if (g_prof.on) {
     RN_CHECK(cudaEventRecord(e1, st));
     g_prof.ev.push_back(e0);
@@ -229,8 +231,21 @@ static void hop_wparams(const rn_hop_plan* p, int which, WApplyParams& w) {
   w.YT = 0; w.order = 0;
 }
 
+// Number of partial sums hop_apply_dot produces (0: the plan's last GEMM is not on the tensor path
+// and the caller has to form the inner product itself).
+int rn::hop_dot_tiles(const rn_hop_plan* p) {
+  if (!p->oz3) return 0;
+  const long rows3 = (long)p->La * p->d1 * p->g1 * p->d2 * p->g2;
+  return ozaki_gemm_tiles((int)rows3, p->Rl * p->es);
+}
+
 extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void* out) {
-  cudaStream_t st = (cudaStream_t)stream;
+  return rn::hop_apply_dot(p, (cudaStream_t)stream, c_in, out, nullptr);
+}
+
+// H_eff . c_in, optionally with the partial sums of Re <c_in, H_eff c_in> (one pair per output tile
+// of the last GEMM) written to dot_partial: the Lanczos alpha without a separate pass.
+int rn::hop_apply_dot(rn_hop_plan* p, cudaStream_t st, const void* c_in, void* out, double* dot_partial) {
   const int es = p->es, cplx = p->cplx;
   const long n1 = p->rest * p->Rk;
   int err;
@@ -270,7 +285,8 @@ extern "C" int rn_hop_apply(rn_hop_plan* p, void* stream, const void* c_in, void
   // G3: out[(rows3), l] = T[(rows3), (f,k)] . R[l, (f,k)]
   const long K3 = (long)p->Rf * p->Rk * es;
   if (p->oz3)
-    err = oz_gemm(st, p->ozT, digits_ready ? nullptr : lastT, K3, p->ozR, nullptr, 0, (double*)out, (long)p->Rl * es);
+    err = oz_gemm(st, p->ozT, digits_ready ? nullptr : lastT, K3, p->ozR, nullptr, 0, (double*)out, (long)p->Rl * es,
+                  dot_partial ? (const double*)c_in : nullptr, dot_partial);
   else
     err = gemm_dispatch(st, 0, (int)rows3, p->Rl * es, (int)K3, lastT, K3, p->Rb, K3,
                         (double*)out, (long)p->Rl * es);

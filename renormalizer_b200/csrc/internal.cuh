@@ -37,8 +37,16 @@ int launch_wapply_split(cudaStream_t st, int cplx, const WApplyParams& p, int ns
                         double* scale);
 int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp);
 int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, const CUtensorMap* tmA,
-                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc);
+                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc,
+                           const double* dotv = nullptr, double* dot_partial = nullptr);
+int ozaki_gemm_tiles(int m, int n);
 int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
                       const double* sA, const signed char* qB, const double* sB, double* C, long ldc);
 
+}  // namespace rn
+
+struct rn_hop_plan;
+namespace rn {
+int hop_dot_tiles(const rn_hop_plan* p);
+int hop_apply_dot(rn_hop_plan* p, cudaStream_t st, const void* c_in, void* out, double* dot_partial);
 }  // namespace rn

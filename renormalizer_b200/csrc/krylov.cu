@@ -49,11 +49,29 @@ lanczos_axpy_kernel(long nd, double* __restrict__ w, const double* __restrict__ 
   const double beta = vjm1 != nullptr ? beta_prev[0] : 0.0;
   double acc[2] = {0.0, 0.0};
   const long step = (long)gridDim.x * blockDim.x;
-  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += step) {
-    double t = w[k] - alpha * vj[k];
-    if (vjm1 != nullptr) t -= beta * vjm1[k];
-    w[k] = t;
-    acc[0] += t * t;
+  const bool vec2 = (nd & 1) == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(vj) |
+                                       reinterpret_cast<uintptr_t>(vjm1)) & 15) == 0;
+  if (vec2) {
+    // 16-byte accesses; the two lanes of a pair are accumulated separately (fixed order)
+    double2* w2 = reinterpret_cast<double2*>(w);
+    const double2* a2 = reinterpret_cast<const double2*>(vj);
+    const double2* b2 = reinterpret_cast<const double2*>(vjm1);
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd / 2; k += step) {
+      double2 t = w2[k];
+      const double2 a = a2[k];
+      t.x -= alpha * a.x; t.y -= alpha * a.y;
+      if (vjm1 != nullptr) { const double2 b = b2[k]; t.x -= beta * b.x; t.y -= beta * b.y; }
+      w2[k] = t;
+      acc[0] += t.x * t.x; acc[1] += t.y * t.y;
+    }
+    acc[0] += acc[1]; acc[1] = 0.0;
+  } else {
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += step) {
+      double t = w[k] - alpha * vj[k];
+      if (vjm1 != nullptr) t -= beta * vjm1[k];
+      w[k] = t;
+      acc[0] += t * t;
+    }
   }
   block_sum<2>(acc, scratch);
   if (threadIdx.x == 0) {
@@ -73,7 +91,16 @@ lanczos_scale_kernel(long nd, const double* __restrict__ x, const double* __rest
   if (blockIdx.x == 0 && threadIdx.x == 0) { norm_out[0] = s; norm_out[1] = 0.0; }
   const double inv = 1.0 / s;
   const long step = (long)gridDim.x * blockDim.x;
-  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += step) out[k] = x[k] * inv;
+  if ((nd & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    double2* o2 = reinterpret_cast<double2*>(out);
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd / 2; k += step) {
+      const double2 v = x2[k];
+      o2[k] = make_double2(v.x * inv, v.y * inv);
+    }
+  } else {
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += step) out[k] = x[k] * inv;
+  }
 }
 
 // partial[b] = this block's share of <v, x> (complex: conj(v) x), as in vecops.cu
@@ -301,15 +328,19 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
   if (cap < 2) cap = 2;
   double* V = nullptr;
   RN_CHECK(cudaMallocAsync((void**)&V, sizeof(double) * (size_t)nd * cap, st));
+  // alpha = Re <v_j, H v_j> comes out of the last GEMM's epilogue (one partial per output tile) when
+  // that GEMM runs on the tensor path; otherwise a separate dot kernel forms it
+  const int dot_tiles = hop_dot_tiles(plan);
+  const size_t pa_doubles = 2 * (size_t)(dot_tiles > RN_REDUCE_BLOCKS ? dot_tiles : RN_REDUCE_BLOCKS);
   const size_t small_doubles = (size_t)2 * (K_MAXM + 2) * 2 /*alpha,beta*/ + 2 * K_MAXM /*coef*/ +
-                               4 * RN_REDUCE_BLOCKS /*two partial arrays*/ + 2 /*nrm*/ + 8;
+                               pa_doubles + 2 * RN_REDUCE_BLOCKS /*two partial arrays*/ + 2 /*nrm*/ + 8;
   double* small = nullptr;
   RN_CHECK(cudaMallocAsync((void**)&small, sizeof(double) * small_doubles + 64, st));
   double* alpha = small;
   double* beta = alpha + 2 * (K_MAXM + 2);
   double* coef = beta + 2 * (K_MAXM + 2);
   double* pa = coef + 2 * K_MAXM;
-  double* pb = pa + 2 * RN_REDUCE_BLOCKS;
+  double* pb = pa + pa_doubles;
   double* nrm = pb + 2 * RN_REDUCE_BLOCKS;
   int* status = reinterpret_cast<int*>(nrm + 2);    // [broke, m, violations]
   double *w = nullptr, *res[2] = {nullptr, nullptr};
@@ -349,12 +380,18 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
   for (long j = 0; j < n; ++j) {
     if (j + 1 > K_MAXM) { cleanup(); return (int)cudaErrorNotSupported; }   // caller falls back
     double* vj = V + j * nd;
-    KRY_TRY(rn_hop_apply(plan, st, vj, w));
-    if (cplx) { RN_LAUNCH(dot_partial_kernel<true>, nbdot, K_THREADS, 0, st, vj, w, n, pa); rn::g_launches++; }
-    else { RN_LAUNCH(dot_partial_kernel<false>, nbdot, K_THREADS, 0, st, vj, w, n, pa); rn::g_launches++; }
+    int nb_alpha = nbdot;
+    if (dot_tiles > 0) {
+      KRY_TRY(hop_apply_dot(plan, st, vj, w, pa));
+      nb_alpha = dot_tiles;
+    } else {
+      KRY_TRY(rn_hop_apply(plan, st, vj, w));
+      if (cplx) { RN_LAUNCH(dot_partial_kernel<true>, nbdot, K_THREADS, 0, st, vj, w, n, pa); rn::g_launches++; }
+      else { RN_LAUNCH(dot_partial_kernel<false>, nbdot, K_THREADS, 0, st, vj, w, n, pa); rn::g_launches++; }
+    }
     if (j == n - 1) {
       // the Krylov space is the full space: alpha_j only, then the final projection
-      { RN_LAUNCH(lanczos_axpy_kernel, 1, K_THREADS, 0, st, 0, w, vj, nullptr, pa, nbdot, nullptr, alpha + 2 * j, pb); rn::g_launches++; }
+      { RN_LAUNCH(lanczos_axpy_kernel, 1, K_THREADS, 0, st, 0, w, vj, nullptr, pa, nb_alpha, nullptr, alpha + 2 * j, pb); rn::g_launches++; }
       KRY_TRY(combine((int)j + 1, (int)j, res[cur]));
       KRY_TRY(fetch_status());
       result_buf = cur; nsteps = h_status[1];
@@ -370,7 +407,7 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
       cudaFreeAsync(V, st);
       V = V2; cap = ncap; vj = V + j * nd;
     }
-    { RN_LAUNCH(lanczos_axpy_kernel, nb, K_THREADS, 0, st, nd, w, vj, j > 0 ? vj - nd : nullptr, pa, nbdot,
+    { RN_LAUNCH(lanczos_axpy_kernel, nb, K_THREADS, 0, st, nd, w, vj, j > 0 ? vj - nd : nullptr, pa, nb_alpha,
                                                    j > 0 ? beta + 2 * (j - 1) : nullptr, alpha + 2 * j, pb); rn::g_launches++; }
     { RN_LAUNCH(lanczos_scale_kernel, nbs, K_THREADS, 0, st, nd, w, pb, nb, beta + 2 * j, vj + nd); rn::g_launches++; }
     KRY_CUDA(cudaGetLastError());

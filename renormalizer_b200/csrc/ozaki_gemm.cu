@@ -25,6 +25,8 @@
 #include "internal.cuh"
 
 #include <cuda.h>
+#include <map>
+#include <mutex>
 #include <type_traits>
 
 namespace rn {
@@ -112,7 +114,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const double* __restrict__ sA, const double* __restrict__ sB,
                   double* __restrict__ C, int m, int n, long ldc, int rowsA, int rowsB, int kblocks,
                   int nslices, int tiles_m, int tiles_n, int n_full, int ksplit_tail, int kb_per_split,
-                  double* __restrict__ partial, int* __restrict__ counters) {
+                  double* __restrict__ partial, int* __restrict__ counters,
+                  const double* __restrict__ dotv, double* __restrict__ dot_partial) {
   pdl_trigger();
   extern __shared__ unsigned char oz_smem_raw[];
   const uint32_t raw = smem_u32(oz_smem_raw);
@@ -309,14 +312,35 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       double sb[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) sb[j] = (col0 + lane + 32 * j < n) ? sB[col0 + lane + 32 * j] : 0.0;
+      // optional fused inner product with a vector laid out like C (the Lanczos alpha = <v_j, H v_j>):
+      // one partial per tile, summed in a fixed order -> deterministic
+      double dacc = 0.0;
       for (int rr = ew; rr < OZ_BM; rr += 8) {
         const int gr = row0 + rr;
         if (gr >= m) break;
         double* crow = C + (long)gr * ldc + col0;
+        const double* vrow = dotv ? dotv + (long)gr * ldc + col0 : nullptr;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int col = lane + 32 * j;
-          if (col0 + col < n) crow[col] = stage[col * (OZ_BM + 1) + rr] * sb[j];
+          if (col0 + col < n) {
+            const double val = stage[col * (OZ_BM + 1) + rr] * sb[j];
+            crow[col] = val;
+            if (vrow) dacc = fma(val, vrow[col], dacc);
+          }
+        }
+      }
+      if (dotv) {
+        dacc = warp_sum(dacc);
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone is done reading the stage
+        if (lane == 0) stage[ew] = dacc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ew == 0 && lane == 0) {
+          double t = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) t += stage[w8];
+          dot_partial[2 * tile_id] = t;
+          dot_partial[2 * tile_id + 1] = 0.0;
         }
       }
     }
@@ -571,6 +595,21 @@ wapply_split_kernel(WApplyParams p, int Kp, int nslices, signed char* __restrict
 
 // -------------------------------------------------------------------------------------- host
 static int g_oz_sms = -1;
+
+// Split-K scratch (partial tiles + self-resetting tile counters), one per stream: launches on one
+// stream are ordered, so consecutive GEMMs can share it.
+struct OzScratch {
+  double* partial = nullptr;
+  size_t partial_bytes = 0;
+  int* counters = nullptr;
+  int ncounters = 0;
+};
+static std::mutex g_oz_scratch_mu;
+static std::map<cudaStream_t, OzScratch> g_oz_scratch;
+static OzScratch& oz_scratch(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_oz_scratch_mu);
+  return g_oz_scratch[st];
+}
 static int g_oz_force_ksplit = 0;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -683,8 +722,11 @@ int launch_wapply_split(cudaStream_t st, int cplx, const WApplyParams& p, int ns
   return 0;
 }
 
+int ozaki_gemm_tiles(int m, int n) { return (int)(ceil_div(m, OZ_BM) * ceil_div(n, OZ_BN)); }
+
 int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, const CUtensorMap* tmA,
-                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc) {
+                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc,
+                           const double* dotv, double* dot_partial) {
   if (m <= 0 || n <= 0) return 0;
   if (nslices < 1 || nslices > OZ_MAX_SLICES) return (int)cudaErrorInvalidValue;
   static bool attr_set = false;
@@ -742,16 +784,30 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
   double* partial = nullptr;
   int* counters = nullptr;
   if (split_tiles > 0) {
+    // per-stream scratch that outlives the launch: the tile counters reset themselves (last CTA),
+    // so they are zeroed once, and no allocation / memset node sits between the kernels of a chain
+    OzScratch& sc = oz_scratch(st);
     const size_t pbytes = (size_t)split_tiles * ksplit * OZ_BM * OZ_BN * sizeof(double);
-    RN_CHECK(cudaMallocAsync((void**)&partial, pbytes + sizeof(int) * (size_t)split_tiles, st));
-    counters = reinterpret_cast<int*>(reinterpret_cast<char*>(partial) + pbytes);
-    RN_CHECK(cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)split_tiles, st));
+    if (pbytes > sc.partial_bytes) {
+      if (sc.partial) RN_CHECK(cudaFreeAsync(sc.partial, st));
+      const size_t want = pbytes < (32u << 20) ? (32u << 20) : pbytes;
+      RN_CHECK(cudaMallocAsync((void**)&sc.partial, want, st));
+      sc.partial_bytes = want;
+    }
+    if (split_tiles > sc.ncounters) {
+      if (sc.counters) RN_CHECK(cudaFreeAsync(sc.counters, st));
+      const int want = split_tiles < 4096 ? 4096 : split_tiles;
+      RN_CHECK(cudaMallocAsync((void**)&sc.counters, sizeof(int) * (size_t)want, st));
+      RN_CHECK(cudaMemsetAsync(sc.counters, 0, sizeof(int) * (size_t)want, st));
+      sc.ncounters = want;
+    }
+    partial = sc.partial;
+    counters = sc.counters;
   }
-  { RN_LAUNCH(ozaki_gemm_kernel, (unsigned)(n_full + split_tiles * ksplit), OZ_THREADS, OZ_SMEM, st, 
+  { RN_LAUNCH(ozaki_gemm_kernel, (unsigned)(n_full + split_tiles * ksplit), OZ_THREADS, OZ_SMEM, st,
       *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, n_full, ksplit > 1 ? ksplit : 1, kb_per,
-      partial, counters); rn::g_launches++; }
+      partial, counters, dotv, dot_partial); rn::g_launches++; }
   RN_LAUNCH_CHECK();
-  if (partial) RN_CHECK(cudaFreeAsync(partial, st));
   return 0;
 }
 
@@ -764,7 +820,7 @@ int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const s
   if (err) return err;
   err = ozaki_make_map(&tmB, qB, (long)nslices * n, Kp);
   if (err) return err;
-  return launch_ozaki_gemm_maps(st, m, n, K, nslices, &tmA, sA, &tmB, sB, C, ldc);
+  return launch_ozaki_gemm_maps(st, m, n, K, nslices, &tmA, sA, &tmB, sB, C, ldc, nullptr, nullptr);
 }
 
 }  // namespace rn

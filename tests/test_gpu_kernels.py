@@ -439,3 +439,26 @@ def test_hop_two_layer_golden(golden, t):
         got = host(hop_expr(dev(L4), dev(r), list(cmo), c.shape, twolayer=True)(dev(c)))
         assert got.shape == g[f"{t}_{name}"].shape
         assert relerr(got, g[f"{t}_{name}"]) < TOL, name
+
+
+def test_qr_fallback_path_subprocess():
+    """The launch-per-reflector fallback (used when a panel does not fit on chip) still factors
+    correctly; it is selected with RN_QR_PANEL=0, read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, '.')\n"
+        "from renormalizer_b200 import ops\n"
+        "from renormalizer_b200.backend import asxp\n"
+        "rng = np.random.default_rng(1)\n"
+        "a = rng.standard_normal((300, 70)) + 1j * rng.standard_normal((300, 70))\n"
+        "q, r = (x.cpu().numpy() for x in ops.qr(asxp(a)))\n"
+        "assert np.abs(q.conj().T @ q - np.eye(70)).max() < 1e-12\n"
+        "assert np.abs(q @ r - a).max() < 1e-11\n"
+        "print('fallback ok')\n")
+    env = dict(os.environ, RN_QR_PANEL="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]
