@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #define RN_CHECK(expr)                                                                       \
   do {                                                                                       \
@@ -39,7 +40,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  static int pdl_on = -1;                 // RN_PDL=0 launches without the attribute (diagnostics)
+  if (pdl_on < 0) { const char* e = getenv("RN_PDL"); pdl_on = (e && e[0] == '0') ? 0 : 1; }
+  cfg.attrs = attr; cfg.numAttrs = pdl_on ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #define RN_LAUNCH(kernel, grid, block, smem, st, ...) \

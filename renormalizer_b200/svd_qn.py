@@ -46,9 +46,29 @@ def _complete(q, extra):
         return q
     a = torch.from_numpy(np.random.rand(m, extra)).to(q.device).to(q.dtype)
     for _ in range(2):
-        a = a - ops.matmul(q, ops.matmul(q.conj().transpose(0, 1).contiguous(), a))
+        if n > 0:
+            a = a - ops.matmul(q, ops.matmul(q.conj().transpose(0, 1).contiguous(), a))
     qa, _ = ops.qr(a)
     return torch.cat([q, qa], dim=1)
+
+
+def _orthonormal_null_vectors(u, s, vh):
+    """One-sided Jacobi delivers the left vectors as (A V)_j / sigma_j: for a (numerically) zero
+    singular value that column is zero or normalised round-off, not a unit vector orthogonal to the
+    others as LAPACK's would be.  The sweeps do keep such vectors (bond dimension larger than the
+    rank), so they are replaced by an orthonormal completion of the well-defined ones, exactly the
+    construction the reference uses for its own null-space columns (svd_qn.py:52-66)."""
+    k = s.numel()
+    if k == 0:
+        return u, vh
+    sh = s.cpu().numpy()
+    tol = sh.max() * max(u.shape[0], vh.shape[1]) * np.finfo(float).eps
+    ngood = int(np.count_nonzero(sh > tol))          # s is sorted: the null vectors come last
+    if ngood == k:
+        return u, vh
+    u = _complete(u[:, :ngood].contiguous(), k - ngood)
+    vh = _complete(vh[:ngood].conj().transpose(0, 1).contiguous(), k - ngood).conj().transpose(0, 1).contiguous()
+    return u, vh
 
 
 def _block_svd(block, full_matrices, opt_full_matrices):
@@ -60,6 +80,7 @@ def _block_svd(block, full_matrices, opt_full_matrices):
         opt_full_matrices = False
     opt = opt_full_matrices and not (1 / 3 < m / n < 3)
     u, s, vh = ops.svd(block)
+    u, vh = _orthonormal_null_vectors(u, s, vh)
     if full_matrices:
         k = min(m, n)
         if opt:

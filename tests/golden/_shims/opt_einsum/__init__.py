@@ -9,14 +9,24 @@ import numpy as np
 from . import parser  # noqa: F401
 
 
+_PATHS = {}
+
+
+def _path(subscripts, ops):
+    """Optimal pairwise contraction order, searched once per (expression, shapes)."""
+    key = (subscripts, tuple(np.shape(o) for o in ops))
+    if key not in _PATHS:
+        _PATHS[key] = np.einsum_path(subscripts, *ops, optimize=("optimal" if len(ops) <= 7 else "greedy", 2 ** 40))[0]
+    return _PATHS[key]
+
+
 def contract(*args, **kwargs):
     kwargs.pop("backend", None)
     opt = kwargs.pop("optimize", "optimal")
     if opt not in ("optimal", "greedy", True, False):
         opt = "optimal"
-    nops = sum(1 for a in args if not isinstance(a, str))
-    if nops > 5 and opt == "optimal":
-        opt = "greedy"
+    if isinstance(args[0], str) and opt == "optimal":
+        return np.einsum(*args, optimize=_path(args[0], args[1:]))
     return np.einsum(*args, optimize=opt)
 
 
@@ -38,7 +48,7 @@ def contract_expression(subscripts, *operands, constants=None, optimize="optimal
         # the contraction path is searched once per expression (the two-layer expressions have
         # up to seven operands: an "optimal" search on every call would dominate the run time)
         if "path" not in cache:
-            cache["path"] = np.einsum_path(subscripts, *ops, optimize="optimal" if n <= 5 else "greedy")[0]
+            cache["path"] = _path(subscripts, ops)
         return np.einsum(subscripts, *ops, optimize=cache["path"])
 
     return expr

@@ -325,3 +325,27 @@ def test_dmrg_omega_targeting_golden(golden):
     assert np.allclose(e, 0.08401412 + float(g["gs_zpe"]))          # the reference's own test
     assert abs(e - float(g["omega_expectation"])) < 1e-7
     assert abs(energies[-1] - g["omega_energies"][-1]) < 1e-9
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_svd_qn_rank_deficient_block_keeps_orthonormal_vectors(cplx):
+    """A bond whose dimension exceeds the rank: the vectors with zero singular value that the sweep
+    keeps must still be orthonormal (LAPACK returns them so; plain one-sided Jacobi returns zeros)."""
+    from renormalizer_b200.svd_qn import svd_qn, add_outer
+    rng = np.random.default_rng(12)
+    def rnd(shape):
+        a = rng.standard_normal(shape)
+        return a + 1j * rng.standard_normal(shape) if cplx else a
+    l, d, r, rank = 12, 4, 20, 5
+    a = (rnd((l * d, rank)) @ rnd((rank, r))).reshape(l, d, r)
+    qnl = np.zeros((l, 1), dtype=int)
+    qnr = np.zeros((r, 1), dtype=int)
+    sq = np.zeros((d, 1), dtype=int)
+    u, su, _, v, sv, _ = svd_qn(dev(a), add_outer(qnl, sq), qnr, np.array([0]), system="L", full_matrices=False)
+    u, v = host(u), host(v)
+    k = min(l * d, r)
+    assert u.shape == (l * d, k) and v.shape == (r, k)
+    assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-11
+    assert np.abs(v.conj().T @ v - np.eye(k)).max() < 1e-11
+    assert np.abs((u * su) @ v.T - a.reshape(l * d, r)).max() < 1e-12 * np.abs(a).max() * 100
+    assert np.all(su[rank:] < 1e-12 * su[0])
