@@ -423,3 +423,54 @@ def evolve_tdvp_ps(mps_in, mpo, dt, normalize=True, stats=None):
     if normalize:
         mps.normalize_mps_only()
     return mps
+
+
+def evolve_tdvp_ps2(mps_in, mpo, dt, m_max, normalize=True, stats=None):
+    """One time step of two-site projector-splitting TDVP with a fixed maximal bond dimension.
+
+    Reference: renormalizer/mps/mps.py:1407-1517 (_evolve_tdvp_ps2, ivp_solver == "krylov"),
+    mp.py:651-888 (_update_mps) and mp.py:890-908 (_push_cano).
+    """
+    mps = mps_in.to_complex() if not np.iscomplex(dt) else mps_in.copy()
+    n = len(mps)
+    environ = Environ(mps, mpo)
+    for _ in range(2):
+        for imps in mps.iter_idx_list(full=False):
+            if mps.to_right:
+                lidx, cidx0, cidx1, ridx = range(imps - 1, imps + 3)
+                cidx2, last_idx = cidx1, n - 2
+            else:
+                lidx, cidx0, cidx1, ridx = range(imps - 2, imps + 2)
+                cidx2, last_idx = cidx0, 1
+            l_array = environ.read("L", lidx)
+            r_array = environ.read("R", ridx)
+            ms2 = np.tensordot(mps.sites[cidx0], mps.sites[cidx1], axes=1)
+            shape2 = ms2.shape
+            w0, w1 = mpo[cidx0], mpo[cidx1]
+            mps_t, j = expm_krylov(
+                lambda y: hop_apply(l_array, r_array, [w0, w1], y.reshape(shape2)).ravel(),
+                -1j * dt / 2, ms2.ravel())
+            if stats is not None:
+                stats.append(j)
+            qnbigl, qnbigr, _ = mps.big_qn([cidx0, cidx1])
+            update_mps(mps, mps_t.reshape(shape2), [cidx0, cidx1], qnbigl, qnbigr, m_max)
+            if imps == last_idx:
+                continue
+            if mps.to_right:
+                l_array = environ.get_lr("L", lidx + 1, mps, mpo, "System")
+            else:
+                r_array = environ.get_lr("R", ridx - 1, mps, mpo, "System")
+            ms1 = mps.sites[cidx2]
+            shape1 = ms1.shape
+            w2 = mpo[cidx2]
+            back, j = expm_krylov(
+                lambda y: hop_apply(l_array, r_array, [w2], y.reshape(shape1)).ravel(),
+                1j * dt / 2, ms1.ravel())
+            if stats is not None:
+                stats.append(j)
+            mps.sites[cidx2] = back.reshape(shape1)
+            mps.push_cano(cidx2)
+        mps.switch_direction()
+    if normalize:
+        mps.normalize_mps_only()
+    return mps

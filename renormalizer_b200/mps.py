@@ -424,13 +424,18 @@ class Mps:
     # ------------------------------------------------------------------ time evolution
     def evolve(self, mpo, evolve_dt, normalize=True):
         """mps.py:644-662.  Only the projector-splitting integrator is accelerated."""
-        if self.evolve_config.method is not EvolveMethod.tdvp_ps:
+        method = self.evolve_config.method
+        if method not in (EvolveMethod.tdvp_ps, EvolveMethod.tdvp_ps2):
             raise NotImplementedError(
-                f"evolve method {self.evolve_config.method} is outside the accelerated path "
-                "(TDVP-PS, mps.py:1268, is)")
+                f"evolve method {method} is outside the accelerated path "
+                "(the projector-splitting integrators TDVP-PS / TDVP-PS2, mps.py:1268,1407, are)")
         if self.evolve_config.ivp_solver != "krylov":
             raise NotImplementedError("only the Krylov local solver is accelerated")
-        if self.evolve_config.adaptive:
+        if method is EvolveMethod.tdvp_ps2:
+            if self.evolve_config.adaptive:
+                raise NotImplementedError("adaptive step control wraps the one-site integrator only (mps.py:46)")
+            new_mps = self._evolve_tdvp_ps2(mpo, evolve_dt)
+        elif self.evolve_config.adaptive:
             new_mps = self._evolve_adaptive(mpo, evolve_dt)
         else:
             new_mps = self._evolve_tdvp_ps(mpo, evolve_dt)
@@ -523,6 +528,56 @@ class Mps:
                     mps[imps + 1] = ops.tensordot1(back.reshape(shape_svt), mps[imps + 1])
                 else:
                     mps[imps] = mps_t
+            mps._switch_direction()
+        mps.evolve_config.stat = local_steps
+        return mps
+
+    def _evolve_tdvp_ps2(self, mpo, evolve_dt):
+        """Two-site projector-splitting TDVP step (mps.py:1407-1517, Krylov local solver): every
+        pair of neighbouring sites is evolved forward by dt/2 with the two-site H_eff and split by
+        the truncating SVD of `_update_mps`; the site that moves on with the sweep is evolved
+        backwards with the one-site H_eff and re-canonicalised."""
+        if np.iscomplex(evolve_dt):
+            mps = self.copy()
+        else:
+            mps = self.to_complex()
+        cdtype = mps.dtype
+        # mps.py:1422-1424 builds both environment chains; only the one this sweep reads is needed
+        environ = Environ(mps, mpo, "R" if mps.to_right else "L")
+        local_steps = []
+        n = len(mps)
+        for _ in range(2):
+            for imps in mps.iter_idx_list(full=False):
+                if mps.to_right:
+                    lidx, cidx0, cidx1, ridx = range(imps - 1, imps + 3)
+                    cidx2, last_idx = cidx1, n - 2
+                else:
+                    lidx, cidx0, cidx1, ridx = range(imps - 2, imps + 2)
+                    cidx2, last_idx = cidx0, 1
+                l_array = environ.read("L", lidx)
+                r_array = environ.read("R", ridx)
+                ms2 = ops.tensordot1(mps[cidx0], mps[cidx1])
+                shape2 = list(ms2.shape)
+                hop = hop_expr_dtype(l_array, r_array, [mpo[cidx0], mpo[cidx1]], shape2, cdtype)
+                mps_t, j = expm_krylov(hop, -1j * evolve_dt / 2, ms2.reshape(-1))
+                hop.close()
+                local_steps.append(j)
+                qnbigl, qnbigr, _ = mps._get_big_qn([cidx0, cidx1])
+                mps._update_mps(mps_t.reshape(shape2), [cidx0, cidx1], qnbigl, qnbigr)
+                if imps == last_idx:
+                    continue
+                if mps.to_right:
+                    l_array = environ.GetLR("L", lidx + 1, mps, mpo, itensor=l_array, method="System")
+                else:
+                    r_array = environ.GetLR("R", ridx - 1, mps, mpo, itensor=r_array, method="System")
+                ms1 = mps[cidx2]
+                shape1 = list(ms1.shape)
+                hop1 = hop_expr_dtype(l_array, r_array, [mpo[cidx2]], shape1, cdtype)
+                back, j = expm_krylov(hop1, 1j * evolve_dt / 2, ms1.reshape(-1))
+                hop1.close()
+                local_steps.append(j)
+                mps[cidx2] = back.reshape(shape1)
+                mps._push_cano(cidx2)
             mps._switch_direction()
         mps.evolve_config.stat = local_steps
         return mps

@@ -14,7 +14,7 @@ Every array below is produced by reference code paths:
   davidson.npz  davidson (lib/davidson/davidson.py:73)
   holstein.npz  Mpo(holstein_model), Mps.random, optimize_mps (mps/gs.py:54), 1site + 2site
   sbm.npz       SpinBosonModel MPO, expand_bond_dimension'd MPS, Mps.evolve with tdvp_ps
-                (mps/mps.py:1268), sigma_z trajectory and final MPS
+                (mps/mps.py:1268) and tdvp_ps2 (mps/mps.py:1407), sigma_z trajectory and final MPS
 """
 import os
 import sys
@@ -284,6 +284,23 @@ def gen_sbm():
     out["mpsT_coeff"] = np.array(mps.coeff)
     out["mpsT_qnidx"] = np.array(mps.qnidx)
     out["mpsT_to_right"] = np.array(bool(mps.to_right))
+    # two-site projector splitting (mps.py:1407) from the same start state
+    np.random.seed(4242)
+    mps2 = Mps.ground_state(model, False)
+    mps2.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=12)
+    mps2.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps2, adaptive=False)
+    mps2 = mps2.expand_bond_dimension(mpo, coef=1e-6, include_ex=False)
+    sz2 = [mps2.expectation(sigma_z)]
+    en2 = [mps2.expectation(mpo)]
+    for i in range(4):
+        mps2 = mps2.evolve(mpo, dt)
+        sz2.append(mps2.expectation(sigma_z))
+        en2.append(mps2.expectation(mpo))
+    out["ps2_nsteps"] = np.array(4)
+    out["ps2_sigma_z_t"] = np.array(sz2)
+    out["ps2_energy_t"] = np.array(en2)
+    out["ps2_bond_dims"] = np.array(mps2.bond_dims)
+    dump_mp("ps2_mpsT", mps2, out)
     np.savez_compressed(os.path.join(HERE, "sbm.npz"), **out)
 
 

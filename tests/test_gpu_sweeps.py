@@ -349,3 +349,27 @@ def test_svd_qn_rank_deficient_block_keeps_orthonormal_vectors(cplx):
     assert np.abs(v.conj().T @ v - np.eye(k)).max() < 1e-11
     assert np.abs((u * su) @ v.T - a.reshape(l * d, r)).max() < 1e-12 * np.abs(a).max() * 100
     assert np.all(su[rank:] < 1e-12 * su[0])
+
+
+def test_tdvp_ps2_golden(golden):
+    """Mps.evolve with the two-site projector-splitting integrator (mps.py:1407-1517) on the
+    reference's spin-boson run: observables, energy conservation, bond dimensions, final state."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig, EvolveMethod
+    from renormalizer_b200.mpo import Mpo
+    g = golden("sbm")
+    mpo = Mpo(load_mpo(g))
+    sz = Mpo(load_mpo(g, "sigma_z"))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=12)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps2, adaptive=False)
+    dt = float(g["dt"])
+    szs, es = [mps.expectation(sz)], [mps.expectation(mpo)]
+    for i in range(int(g["ps2_nsteps"])):
+        mps = mps.evolve(mpo, dt)
+        szs.append(mps.expectation(sz))
+        es.append(mps.expectation(mpo))
+    assert np.abs(np.array(szs) - g["ps2_sigma_z_t"]).max() < E_TOL
+    assert np.abs(np.array(es) - g["ps2_energy_t"]).max() < E_TOL
+    assert mps.bond_dims == list(g["ps2_bond_dims"])
+    refT = to_device_mps(load_oracle_mps(g, "ps2_mpsT"))
+    assert abs(abs(refT.conj().dot(mps)) - 1) < T_TOL

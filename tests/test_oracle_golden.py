@@ -144,3 +144,25 @@ def test_tdvp_ps_spin_boson(golden):
     assert np.abs(np.array(es) - g["energy_t"]).max() < 1e-12
     refT = load_oracle_mps(g, "mpsT")
     assert abs(abs(refT.dot_conj(mps)) - 1) < 1e-11
+
+
+def test_tdvp_ps2_spin_boson(golden):
+    """Two-site projector splitting (mps.py:1407-1517) pinned to the reference's trajectory."""
+    from oracle.sweep import evolve_tdvp_ps2
+    g = golden("sbm")
+    mpo = load_mpo(g)
+    sz = load_mpo(g, "sigma_z")
+    mps = load_oracle_mps(g, "mps0")
+    dt = float(g["dt"])
+    szs, es = [mps.expectation(sz)], [mps.expectation(mpo)]
+    for i in range(int(g["ps2_nsteps"])):
+        mps = evolve_tdvp_ps2(mps, mpo, dt, 12)
+        szs.append(mps.expectation(sz))
+        es.append(mps.expectation(mpo))
+    assert np.abs(np.array(szs) - g["ps2_sigma_z_t"]).max() < 1e-10
+    assert np.abs(np.array(es) - g["ps2_energy_t"]).max() < 1e-10
+    assert [s.shape[0] for s in mps.sites] + [1] == list(g["ps2_bond_dims"])
+    ref = load_oracle_mps(g, "ps2_mpsT")
+    ov = mps.conj().dot(ref) if hasattr(mps, "conj") else None
+    if ov is not None:
+        assert abs(abs(ov) - 1) < 1e-8
