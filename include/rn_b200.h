@@ -33,6 +33,12 @@ int rn_dgemm_tn(void* stream, int m, int n, int k, const double* A, long lda, co
                 long ldb, double* C, long ldc, int accumulate, int batch, long strideA,
                 long strideB, long strideC);
 
+/* out (M x N) = a (M x K) . b (K x N), all row-major, float64 or complex128: xp.tensordot with one
+ * contracted axis / xp.dot (renormalizer/mps/matrix.py:210) as ONE call.  path as for rn_hop_plan:
+ * 0 = FP64 DMMA, 1 = tcgen05 int8 split GEMM for products large enough to fill tiles. */
+int rn_matmul(void* stream, int cplx, int M, int K, int N, const void* a, const void* b, void* out,
+              int path);
+
 /* Same contraction with FP64 accuracy on the tcgen05 tensor cores: both operands are split into
  * `nslices` (1..8) signed 8-bit digits per element (Ozaki scheme), the digit products run as
  * int8 tcgen05.mma with int32 TMEM accumulators and are recombined in FP64.  nslices = 7 bounds

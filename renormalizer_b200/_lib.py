@@ -20,6 +20,7 @@ SIGNATURES = {
     "rn_init": (_i, [_i, POINTER(_i), POINTER(_i)]),
     "rn_version": (c_char_p, []),
     "rn_dgemm_tn": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _l, _i, _i, _l, _l, _l]),
+    "rn_matmul": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     "rn_ozaki_gemm_tn": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _l, _i]),
     "rn_set_ozaki": (_i, [_i, c_double]),
     "rn_pack": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _l, _l, _vp, _l]),

@@ -404,6 +404,37 @@ extern "C" int rn_env_update(void* stream, int cplx, int domain, const void* env
   return 0;
 }
 
+// ---- plain matrix product ------------------------------------------------------------------------
+// out (M x N) = a (M x K) . b (K x N), row-major, real or complex: xp.tensordot / xp.dot of the sweep
+// (absorbing a bond matrix into the next site, overlaps, norms).  Large products run on the
+// tcgen05 split path: the left operand is split row-wise through its real view, the right one by
+// the transposing split (which also realifies it), so no packed FP64 copy is made.
+extern "C" int rn_matmul(void* stream, int cplx, int M, int K, int N, const void* a, const void* b,
+                         void* out, int path) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M <= 0 || N <= 0) return 0;
+  const int es = cplx ? 2 : 1;
+  if (K <= 0) { RN_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * es * (size_t)M * N, st)); return 0; }
+  int err;
+  if (use_ozaki(path, (double)M, (double)N * es, (double)K * es)) {
+    OzOperand oa, ob;
+    if ((err = oz_alloc(st, oa, M, K * es, g_ozaki_slices))) return err;
+    if ((err = oz_alloc(st, ob, N * es, K * es, g_ozaki_slices))) return err;
+    if ((err = launch_ozaki_split(st, (const double*)a, (long)K * es, M, K * es, oa.nslices, oa.q, oa.scale))) return err;
+    if ((err = launch_ozaki_split_t(st, cplx, b, N, N, K, ob.nslices, ob.q, ob.scale))) return err;
+    err = oz_gemm(st, oa, nullptr, 0, ob, nullptr, 0, (double*)out, (long)N * es);
+    oz_free(st, oa); oz_free(st, ob);
+    return err;
+  }
+  double* bp = nullptr;
+  RN_CHECK(cudaMallocAsync((void**)&bp, sizeof(double) * es * es * (size_t)N * K, st));
+  err = launch_pack(st, cplx, cplx ? 1 : 0, 0, N, K, b, 1, N, bp, (long)K * es);
+  if (!err) err = gemm_dispatch(st, 0, M, N * es, K * es, (const double*)a, (long)K * es, bp, (long)K * es,
+                                (double*)out, (long)N * es);
+  cudaFreeAsync(bp, st);
+  return err;
+}
+
 // ---- GEMM launch profiling (used by bench.py only) ---------------------------------------------
 extern "C" int rn_profile_begin(void) {
   g_prof.on = true;

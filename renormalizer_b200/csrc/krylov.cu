@@ -7,8 +7,8 @@
 // (the bracketed scalars are reduced redundantly, in a fixed order, by every block of the kernel
 // that needs them, so no separate reduction launch and no host round trip).  At the reference's
 // own check points (every second step from the fifth on) a single-block kernel diagonalises the
-// tridiagonal matrix (implicit QL, EISPACK tql2), forms the coefficients
-//   u (|v| exp(dt w) u_0)  and the candidate result is compared with the previous one on the
+// tridiagonal matrix (Chebyshev expansion of exp(dt T) e_0 in one warp, or implicit QL / EISPACK tql2
+// for general complex dt), forms the coefficients  u (|v| exp(dt w) u_0)  and the candidate result is compared with the previous one on the
 // device (numpy.allclose semantics); the host reads three integers.
 #include "common.cuh"
 #include "rn_b200.h"
@@ -20,6 +20,7 @@ namespace rn {
 
 constexpr int K_THREADS = 256;
 constexpr int K_MAXM = 64;          // largest Krylov dimension the device eigen-solver handles
+constexpr int K_CHEB_MAX = 600;     // most Chebyshev terms of the fast coefficient path (|dt| h up to ~450)
 
 // ---- scalar reduced redundantly by every block: sum of nb (re, im) partial pairs, fixed order
 __device__ __forceinline__ double block_reduce_partials(const double* __restrict__ partial, int nb,
@@ -148,43 +149,94 @@ krylov_coef_kernel(const double* __restrict__ alpha, const double* __restrict__ 
     const double b = beta[2 * i];
     if (!(b >= eps_break)) { m = i + 1; broke = 1; break; }
   }
-  // Fast path (Krylov dimension <= 32 and |dt| ||T|| <= 16, i.e. every TDVP step in practice):
-  // coef = |v| exp(dt T) e_0 by 2^s Taylor sub-steps of norm <= 1 (20 terms, truncation 1/21!),
-  // one warp, lane i <-> entry i, the tridiagonal product through shuffles.  The eigen-solver below
-  // remains for long spaces / large norms; both evaluate the same vector to round-off.
-  if (m <= 32) {
+  // Fast path (Krylov dimension <= 32 and dt purely real or purely imaginary, i.e. every TDVP /
+  // imaginary-time step): coef = |v| exp(dt T) e_0 by the Chebyshev expansion of the exponential on
+  // the Gershgorin interval [c - h, c + h] of T,
+  //   exp(i y x) = sum_k (2 - d_k0) i^k J_k(y) T_k(x),   exp(y x) = sum_k (2 - d_k0) I_k(y) T_k(x),
+  // with x = (T - c) / h.  One warp: lane i <-> entry i, the tridiagonal product through shuffles,
+  // the Bessel coefficients by Miller's backward recurrence (lane 0).  About |dt| h + 30 terms,
+  // truncation below 1e-17.  The eigen-solver below remains for general complex dt, long spaces and
+  // very large |dt| h; both evaluate the same vector to round-off.
+  if (m <= 32 && (dt_re == 0.0 || dt_im == 0.0)) {
+    __shared__ double bes[K_CHEB_MAX + 2];
     const int lane = t & 31;
     const bool in = lane < m;
     const double al = in ? alpha[2 * lane] : 0.0;
     const double bu = (in && lane < m - 1) ? beta[2 * lane] : 0.0;          // couples lane, lane + 1
     const double bd = (in && lane > 0) ? beta[2 * (lane - 1)] : 0.0;        // couples lane - 1, lane
-    double rs = fabs(al) + fabs(bu) + fabs(bd);
+    double lo = in ? al - fabs(bu) - fabs(bd) : 1e300, hi = in ? al + fabs(bu) + fabs(bd) : -1e300;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
-    const double na = hypot(dt_re, dt_im) * rs;
-    int s2 = 0;
-    while (s2 <= 4 && ldexp(1.0, s2) < na) ++s2;
-    if (s2 <= 4) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    const double c = 0.5 * (lo + hi);
+    double h = 0.5 * (hi - lo);
+    if (!(h > 0.0)) h = 1.0;                       // T = c I: x = 0, only the k = 0 term survives
+    const bool imag = dt_re == 0.0;
+    const double y = (imag ? dt_im : dt_re) * h;   // signed argument
+    const double z = fabs(y);
+    const int K = (int)(z + 12.0 * cbrt(z)) + 24;
+    // real dt: the series is summed against the factor e^z, so a loose Gershgorin interval costs
+    // digits (cancellation ~ e^(2z) eps); only small arguments take the fast path there
+    if (K <= K_CHEB_MAX && (imag || z <= 4.0)) {
       if (t < 32) {
-        const int nsub = 1 << s2;
-        const double hr = dt_re / nsub, hi = dt_im / nsub;
-        double yr = (lane == 0) ? nrm_ptr[0] : 0.0, yi = 0.0;
-        for (int sub = 0; sub < nsub; ++sub) {
-          double tr = yr, ti = yi;
-          for (int k = 1; k <= 20; ++k) {
-            const double ur = __shfl_up_sync(0xffffffffu, tr, 1), ui = __shfl_up_sync(0xffffffffu, ti, 1);
-            const double dr = __shfl_down_sync(0xffffffffu, tr, 1), di = __shfl_down_sync(0xffffffffu, ti, 1);
-            const double pr = al * tr + bd * ur + bu * dr;       // (T term)_lane; bd = 0 on lane 0, bu = 0 on the last
-            const double pi = al * ti + bd * ui + bu * di;
-            const double ik = 1.0 / k;
-            tr = (hr * pr - hi * pi) * ik;
-            ti = (hr * pi + hi * pr) * ik;
-            yr += tr; yi += ti;
+        // Bessel J_k(z) (imaginary dt) or exp(-z) I_k(z) (real dt), k = 0..K
+        if (lane == 0) {
+          if (z < 1e-300) {
+            bes[0] = 1.0;
+            for (int k = 1; k <= K; ++k) bes[k] = 0.0;
+          } else {
+            const int N = 2 * ((K + 40 + (int)sqrt(200.0 * (K + 1))) / 2);
+            const double tz = 2.0 / z;
+            double bjp = 0.0, bj = 1e-250, sum = 0.0;
+            for (int j = N; j >= 1; --j) {
+              const double bjm = imag ? j * tz * bj - bjp : j * tz * bj + bjp;
+              bjp = bj; bj = bjm;                                   // bj = B_{j-1}
+              if (fabs(bj) > 1e200) {
+                bj *= 1e-200; bjp *= 1e-200; sum *= 1e-200;
+                for (int k = j; k <= K; ++k) bes[k] *= 1e-200;
+              }
+              if (j - 1 <= K) bes[j - 1] = bj;
+              if (imag) { if (((j - 1) & 1) == 0) sum += (j - 1 == 0 ? 1.0 : 2.0) * bj; }
+              else sum += (j - 1 == 0 ? 1.0 : 2.0) * bj;
+            }
+            const double inv = 1.0 / sum;        // J: J_0 + 2 sum J_2k = 1;  I: I_0 + 2 sum I_k = e^z
+            for (int k = 0; k <= K; ++k) bes[k] *= inv;
           }
         }
+        __syncwarp();
+        const double ih = 1.0 / h;
+        const double sgn = y < 0.0 ? -1.0 : 1.0;
+        double tp = (lane == 0) ? nrm_ptr[0] : 0.0;                 // T_0(x) e_0 |v|
+        double ur = __shfl_up_sync(0xffffffffu, tp, 1), dr = __shfl_down_sync(0xffffffffu, tp, 1);
+        double tc = ((al - c) * tp + bd * ur + bu * dr) * ih;       // T_1(x) e_0 |v|
+        if (!in) tc = 0.0;
+        // phase^k: imaginary dt -> (i sgn)^k, real dt -> sgn^k
+        double accr = bes[0] * tp, acci = 0.0;
+        if (imag) acci = 2.0 * bes[1] * sgn * tc; else accr += 2.0 * bes[1] * sgn * tc;
+        for (int k = 2; k <= K; ++k) {
+          ur = __shfl_up_sync(0xffffffffu, tc, 1);
+          dr = __shfl_down_sync(0xffffffffu, tc, 1);
+          double tn = 2.0 * ((al - c) * tc + bd * ur + bu * dr) * ih - tp;
+          if (!in) tn = 0.0;
+          tp = tc; tc = tn;
+          const double ck = 2.0 * bes[k] * tn;
+          if (imag) {
+            const int q = k & 3;                                    // (i sgn)^k
+            if (q == 0) accr += ck; else if (q == 2) accr -= ck;
+            else if (q == 1) acci += sgn * ck; else acci -= sgn * ck;
+          } else {
+            accr += ((k & 1) && sgn < 0.0) ? -ck : ck;
+          }
+        }
+        // overall factor exp(dt c) (and e^z for the scaled modified Bessel functions)
+        double fr, fi;
+        if (imag) { sincos(dt_im * c, &fi, &fr); }
+        else { fr = exp(dt_re * c + z); fi = 0.0; }
         if (lane < mtry) {
-          coef[2 * lane] = in ? yr : 0.0;
-          coef[2 * lane + 1] = in ? yi : 0.0;
+          coef[2 * lane] = in ? accr * fr - acci * fi : 0.0;
+          coef[2 * lane + 1] = in ? accr * fi + acci * fr : 0.0;
         }
         if (lane == 0) { status[0] = broke; status[1] = m; }
       }

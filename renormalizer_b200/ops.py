@@ -93,10 +93,8 @@ def matmul(a, b):
         return out
     if K == 0:
         return out.zero_()
-    # right operand "math B"[k, j] = b[k*N + j] -> K-major rows j
-    bp = pack(b, N, K, 1, N, mode=1 if cplx else 0)
-    gemm_tn(torch.view_as_real(a) if cplx else a, bp, M, N * es, K * es, K * es, K * es,
-            out=torch.view_as_real(out) if cplx else out, ldc=N * es)
+    check(_lib.get().rn_matmul(stream_ptr(), cplx, M, K, N, _ptr(a), _ptr(b), _ptr(out), backend.gemm_path),
+          "rn_matmul")
     return out
 
 
