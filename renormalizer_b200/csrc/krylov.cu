@@ -15,6 +15,8 @@
 #include "internal.cuh"
 
 #include <math.h>
+#include <map>
+#include <mutex>
 
 namespace rn {
 
@@ -322,13 +324,20 @@ krylov_coef_kernel(const double* __restrict__ alpha, const double* __restrict__ 
 }
 
 // out[k] = sum_{i < min(nvec, *nvec_ptr)} coef[i] V_i[k]; coef holds complex pairs (imaginary parts
-// ignored for real vectors).
+// ignored for real vectors).  Fused with the convergence test of krylov.py:79: when `prev` is given,
+// blocks count elements with !(|prev - out| <= atol + rtol |out|) (numpy.allclose(prev, out)).  The
+// last block to finish publishes [broke, m, violations] and then the epoch number to `host_flags`
+// (pinned, mapped host memory), so the host learns the outcome without a copy node or a stream
+// synchronisation; `sync` = {violation count, block ticket} lives in device memory and is left zeroed.
 template <bool CPLX>
 __global__ void __launch_bounds__(K_THREADS)
-krylov_combine_kernel(long n, int nvec, const int* __restrict__ nvec_ptr, const double* __restrict__ V,
-                      long ld, const double* __restrict__ coef, double* __restrict__ out) {
+krylov_combine_kernel(long n, int nvec, const int* __restrict__ status, const double* __restrict__ V,
+                      long ld, const double* __restrict__ coef, double* __restrict__ out,
+                      const double* __restrict__ prev, double rtol, double atol, int* __restrict__ sync,
+                      volatile int* __restrict__ host_flags, int epoch) {
   pdl_wait();
-  if (nvec_ptr != nullptr) { const int lim = nvec_ptr[0]; if (lim < nvec) nvec = lim; }
+  { const int lim = status[1]; if (lim < nvec) nvec = lim; }
+  int bad = 0;
   const long step = (long)gridDim.x * blockDim.x;
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
     if constexpr (CPLX) {
@@ -340,10 +349,30 @@ krylov_combine_kernel(long n, int nvec, const int* __restrict__ nvec_ptr, const 
         acc.y += c.x * v.y + c.y * v.x;
       }
       reinterpret_cast<double2*>(out)[k] = acc;
+      if (prev != nullptr) {
+        const double2 p = reinterpret_cast<const double2*>(prev)[k];
+        if (!(hypot(p.x - acc.x, p.y - acc.y) <= atol + rtol * hypot(acc.x, acc.y))) bad = 1;
+      }
     } else {
       double acc = 0.0;
       for (int i = 0; i < nvec; ++i) acc += coef[2 * i] * V[(long)i * ld + k];
       out[k] = acc;
+      if (prev != nullptr && !(fabs(prev[k] - acc) <= atol + rtol * fabs(acc))) bad = 1;
+    }
+  }
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    if (bad) atomicAdd(sync, 1);
+    __threadfence();
+    const int ticket = atomicAdd(sync + 1, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      __threadfence();
+      host_flags[0] = status[0];
+      host_flags[1] = status[1];
+      host_flags[2] = *reinterpret_cast<volatile int*>(sync);
+      sync[0] = 0; sync[1] = 0;
+      __threadfence_system();
+      host_flags[3] = epoch;
     }
   }
 }
@@ -359,7 +388,20 @@ static inline int k_nblocks(long n) {
 
 using namespace rn;
 
-extern "C" int rn_allclose(void*, int, long, const double*, const double*, double, double, int*);
+namespace {
+struct KrylovFlags {
+  volatile int* host = nullptr;
+  int* dev = nullptr;
+  int epoch = 0;
+};
+std::mutex g_kf_mu;
+std::map<cudaStream_t, KrylovFlags> g_kf;
+KrylovFlags& krylov_flags(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_kf_mu);
+  return g_kf[st];
+}
+}  // namespace
+
 
 extern "C" int rn_krylov_max_dim(void) { return K_MAXM; }
 
@@ -398,8 +440,21 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
   double *w = nullptr, *res[2] = {nullptr, nullptr};
   RN_CHECK(cudaMallocAsync((void**)&w, sizeof(double) * (size_t)nd * 3, st));
   res[0] = w + nd; res[1] = w + 2 * nd;
-  static int* h_status = nullptr;                   // pinned landing zone for the three flags
-  if (!h_status) RN_CHECK(cudaMallocHost((void**)&h_status, 64));
+  // pinned, device-mapped landing zone per stream: [broke, m, violations, epoch]; the last block of
+  // the combine kernel writes it, the host polls the epoch word
+  KrylovFlags& kf = krylov_flags(st);
+  if (!kf.host) {
+    int* hp = nullptr;
+    RN_CHECK(cudaHostAlloc((void**)&hp, 64, cudaHostAllocMapped));
+    for (int i = 0; i < 16; ++i) hp[i] = 0;
+    RN_CHECK(cudaHostGetDevicePointer((void**)&kf.dev, hp, 0));
+    kf.host = hp;
+  }
+  volatile int* h_status = kf.host;
+  int* d_status_map = kf.dev;
+  int& epoch = kf.epoch;
+  int* gsync = reinterpret_cast<int*>(nrm + 4);     // {violations, block ticket} of the combine kernel
+  RN_CHECK(cudaMemsetAsync(gsync, 0, 2 * sizeof(int), st));
 
   int err = 0, result_buf = -1, nsteps = 0;
   auto cleanup = [&]() {
@@ -414,18 +469,28 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
   { RN_LAUNCH(lanczos_scale_kernel, nbs, K_THREADS, 0, st, nd, (const double*)v_in, pa, nbdot, nrm, V); rn::g_launches++; }
   KRY_CUDA(cudaGetLastError());
 
-  auto combine = [&](int mtry, int nbeta_check, double* dst) -> int {
+  // coefficient vector + candidate result (+ numpy.allclose against `prev`); returns after launching
+  auto combine = [&](int mtry, int nbeta_check, double* dst, const double* prev) -> int {
     { RN_LAUNCH(krylov_coef_kernel, 1, K_MAXM, 0, st, alpha, beta, mtry, nbeta_check, nrm, dt_re, dt_im, eps_break, coef, status); rn::g_launches++; }
     int nbc = (int)ceil_div(n, K_THREADS);
     if (nbc > 148 * 8) nbc = 148 * 8;
-    if (cplx) { RN_LAUNCH(krylov_combine_kernel<true>, nbc, K_THREADS, 0, st, n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
-    else { RN_LAUNCH(krylov_combine_kernel<false>, nbc, K_THREADS, 0, st, n, mtry, status + 1, V, nd, coef, dst); rn::g_launches++; }
+    ++epoch;
+    if (cplx) { RN_LAUNCH(krylov_combine_kernel<true>, nbc, K_THREADS, 0, st, n, mtry, status, V, nd, coef, dst, prev, 1e-5, 1e-8, gsync, d_status_map, epoch); rn::g_launches++; }
+    else { RN_LAUNCH(krylov_combine_kernel<false>, nbc, K_THREADS, 0, st, n, mtry, status, V, nd, coef, dst, prev, 1e-5, 1e-8, gsync, d_status_map, epoch); rn::g_launches++; }
     return (int)cudaGetLastError();
   };
+  // wait for the combine kernel's completion word (spin on mapped host memory; the stream is polled
+  // now and then so that a launch failure cannot hang the host)
   auto fetch_status = [&]() -> int {
-    cudaError_t e = cudaMemcpyAsync(h_status, status, 3 * sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return (int)e;
-    return (int)cudaStreamSynchronize(st);
+    long spins = 0;
+    while (h_status[3] != epoch) {
+      if ((++spins & 0xfffff) == 0) {
+        cudaError_t q = cudaStreamQuery(st);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
+        if (q == cudaSuccess && h_status[3] != epoch) return (int)cudaErrorUnknown;
+      }
+    }
+    return 0;
   };
 
   int have_prev = 0, cur = 0;
@@ -444,7 +509,7 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
     if (j == n - 1) {
       // the Krylov space is the full space: alpha_j only, then the final projection
       { RN_LAUNCH(lanczos_axpy_kernel, 1, K_THREADS, 0, st, 0, w, vj, nullptr, pa, nb_alpha, nullptr, alpha + 2 * j, pb); rn::g_launches++; }
-      KRY_TRY(combine((int)j + 1, (int)j, res[cur]));
+      KRY_TRY(combine((int)j + 1, (int)j, res[cur], nullptr));
       KRY_TRY(fetch_status());
       result_buf = cur; nsteps = h_status[1];
       break;
@@ -465,15 +530,14 @@ extern "C" int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n,
     KRY_CUDA(cudaGetLastError());
     const bool check = j > 3 && (j % 2 == 0);
     if (check) {
-      KRY_TRY(combine((int)j + 1, (int)j + 1, res[cur]));
-      if (have_prev) KRY_TRY(rn_allclose(st, cplx, n, res[cur ^ 1], res[cur], 1e-5, 1e-8, status + 2));
+      KRY_TRY(combine((int)j + 1, (int)j + 1, res[cur], have_prev ? res[cur ^ 1] : nullptr));
       KRY_TRY(fetch_status());
       if (h_status[0]) { result_buf = cur; nsteps = h_status[1]; break; }
       if (have_prev && h_status[2] == 0) { result_buf = cur; nsteps = (int)j + 1; break; }
       have_prev = 1; cur ^= 1;
     } else if (j < 4 && n <= 8) {
       // tiny problems: the reference tests beta_j at every step
-      KRY_TRY(combine((int)j + 1, (int)j + 1, res[cur]));
+      KRY_TRY(combine((int)j + 1, (int)j + 1, res[cur], nullptr));
       KRY_TRY(fetch_status());
       if (h_status[0]) { result_buf = cur; nsteps = h_status[1]; break; }
     }

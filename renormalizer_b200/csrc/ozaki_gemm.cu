@@ -259,7 +259,12 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sum[c * 32 + i] = fma((double)(int)v[i], wg, sum[c * 32 + i]);
+        for (int i = 0; i < 32; ++i) {
+          // int32 -> double without the (quarter-rate) I2F: 2^52 + 2^31 + v is exact in the
+          // mantissa of a double whose high word is 0x43300000; one subtraction recovers v
+          const double x = __hiloint2double(0x43300000, (int)(v[i] ^ 0x80000000u)) - 4503601774854144.0;
+          sum[c * 32 + i] = fma(x, wg, sum[c * 32 + i]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -547,18 +552,42 @@ wapply_split_kernel(WApplyParams p, int Kp, int nslices, signed char* __restrict
   const int y1 = row % Y1, xd = row / Y1;
   const int d = xd % p.D, x = xd / p.D;
   const T* in = reinterpret_cast<const T*>(p.in) + (long)x * p.isx + (long)y1 * p.Y2;
+  // CSR entries of this d (all f): element offsets and values staged once per block, so the inner
+  // loop has no integer division and no dependent index loads
+  constexpr int WS_MAXE = 256;
+  __shared__ int s_off[WS_MAXE];
+  __shared__ double s_val[WS_MAXE];
+  const int ebase = p.rowptr[d * p.F], eend = p.rowptr[(d + 1) * p.F];
+  const bool staged = (eend - ebase) <= WS_MAXE && (long)p.P * p.isp + (long)p.Q * p.isq < 2147483647L;
+  if (staged) {
+    for (int e = ebase + threadIdx.x; e < eend; e += 256) {
+      const int pq = p.ent_pq[e];
+      s_off[e - ebase] = (int)((long)(pq / p.Q) * p.isp + (long)(pq % p.Q) * p.isq);
+      s_val[e - ebase] = p.ent_val[e];
+    }
+    __syncthreads();
+  }
   double mx = 0.0;
   for (int f = 0; f < p.F; ++f) {
     const int e0 = p.rowptr[d * p.F + f], e1 = p.rowptr[d * p.F + f + 1];
     for (int y2 = threadIdx.x; y2 < p.Y2; y2 += 256) {
       T acc;
       if constexpr (CPLX) acc = make_double2(0.0, 0.0); else acc = 0.0;
-      for (int e = e0; e < e1; ++e) {
-        const int pq = p.ent_pq[e];
-        const double w = p.ent_val[e];
-        const T v = in[(long)(pq / p.Q) * p.isp + (long)(pq % p.Q) * p.isq + y2];
-        if constexpr (CPLX) { acc.x = fma(w, v.x, acc.x); acc.y = fma(w, v.y, acc.y); }
-        else acc = fma(w, v, acc);
+      if (staged) {
+        for (int e = e0 - ebase; e < e1 - ebase; ++e) {
+          const double w = s_val[e];
+          const T v = in[s_off[e] + y2];
+          if constexpr (CPLX) { acc.x = fma(w, v.x, acc.x); acc.y = fma(w, v.y, acc.y); }
+          else acc = fma(w, v, acc);
+        }
+      } else {
+        for (int e = e0; e < e1; ++e) {
+          const int pq = p.ent_pq[e];
+          const double w = p.ent_val[e];
+          const T v = in[(long)(pq / p.Q) * p.isp + (long)(pq % p.Q) * p.isq + y2];
+          if constexpr (CPLX) { acc.x = fma(w, v.x, acc.x); acc.y = fma(w, v.y, acc.y); }
+          else acc = fma(w, v, acc);
+        }
       }
       if constexpr (CPLX) {
         reinterpret_cast<double2*>(ws_row)[f * p.Y2 + y2] = acc;
