@@ -69,7 +69,8 @@ static int gemm_dispatch(cudaStream_t st, int path, int m, int n, int k, const d
 struct OzOperand {
   signed char* q = nullptr;
   double* scale = nullptr;
-  CUtensorMap map;
+  CUtensorMap map;      // 128-row boxes
+  CUtensorMap map64;    // 64-row boxes: the B operand of the CTA-pair kernel
   int rows = 0, K = 0, nslices = 0;
 };
 
@@ -77,7 +78,9 @@ static int oz_alloc(cudaStream_t st, OzOperand& o, int rows, int K, int nslices)
   o.rows = rows; o.K = K; o.nslices = nslices;
   RN_CHECK(cudaMallocAsync((void**)&o.q, ozaki_split_bytes(rows, K, nslices) + 16, st));
   RN_CHECK(cudaMallocAsync((void**)&o.scale, sizeof(double) * (size_t)rows, st));
-  return ozaki_make_map(&o.map, o.q, (long)nslices * rows, (K + 15) & ~15);
+  int err = ozaki_make_map(&o.map, o.q, (long)nslices * rows, (K + 15) & ~15, 128);
+  if (err) return err;
+  return ozaki_make_map(&o.map64, o.q, (long)nslices * rows, (K + 15) & ~15, 64);
 }
 
 static void oz_free(cudaStream_t st, OzOperand& o) {
@@ -103,7 +106,7 @@ static int oz_gemm(cudaStream_t st, OzOperand& a, const double* a_fresh, long ld
     RN_CHECK(cudaEventCreate(&e1));
     RN_CHECK(cudaEventRecord(e0, st));
   }
-  err = launch_ozaki_gemm_maps(st, a.rows, b.rows, a.K, a.nslices, &a.map, a.scale, &b.map, b.scale, C, ldc,
+  err = launch_ozaki_gemm_maps(st, a.rows, b.rows, a.K, a.nslices, &a.map, a.scale, &b.map, &b.map64, b.scale, C, ldc,
                                dotv, dot_partial);
   if (g_prof.on) {
     RN_CHECK(cudaEventRecord(e1, st));

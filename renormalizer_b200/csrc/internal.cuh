@@ -35,10 +35,10 @@ int launch_ozaki_split_t(cudaStream_t st, int cplx, const void* src, long s_col,
                          int nslices, signed char* q, double* scale);
 int launch_wapply_split(cudaStream_t st, int cplx, const WApplyParams& p, int nslices, signed char* q,
                         double* scale);
-int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp);
+int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp, int box_rows = 128);
 int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, const CUtensorMap* tmA,
-                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc,
-                           const double* dotv = nullptr, double* dot_partial = nullptr);
+                           const double* sA, const CUtensorMap* tmB, const CUtensorMap* tmB64, const double* sB,
+                           double* C, long ldc, const double* dotv = nullptr, double* dot_partial = nullptr);
 int ozaki_gemm_tiles(int m, int n);
 int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
                       const double* sA, const signed char* qB, const double* sB, double* C, long ldc);

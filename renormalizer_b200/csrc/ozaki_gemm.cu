@@ -77,6 +77,34 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: operands of one 256 x 128 tile live in the shared memory of
+// two CTAs of a cluster, the leader issues the MMAs, barriers of the leader are addressed from the
+// peer by clearing the peer bit of the shared-memory address.
+constexpr uint32_t OZ_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar & OZ_PEER_MASK), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` of BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {    // arrive on the leader CTA's barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & OZ_PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -94,6 +122,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // s8 x s8 -> s32, M = 128, N = 128, both operands K-major
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
                               ((uint32_t)(OZ_BM >> 4) << 24);
+// the same with M = 256 across a CTA pair
+constexpr uint32_t OZ_IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
+                               ((uint32_t)((2 * OZ_BM) >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -109,6 +140,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------ the GEMM
+// CTA2 = false: one CTA per 128 x 128 tile.  CTA2 = true: a cluster of two CTAs per 256 x 128 tile
+// (tcgen05 cta_group::2): each CTA stages its own 128 rows of A and HALF of the B tile (tmB then has
+// 64-row boxes) and keeps its 128 x 128 accumulators in its own TMEM; the leader CTA issues the
+// MMAs for both.  Per MMA a CTA then reads 6 KB instead of 8 KB from shared memory and TMA writes
+// 24 KB instead of 32 KB per step -- shared-memory bandwidth is what bounds this kernel.
+// "Unit" below = what one scheduling slot computes: a tile (CTA2 = false) or a tile pair.
+template <bool CTA2>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const double* __restrict__ sA, const double* __restrict__ sB,
@@ -135,37 +173,51 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // are split along K into ksplit_tail CTAs, so that a ragged last wave finishes in a fraction of
   // a tile time.  The last CTA of a split tile to finish sums the partial tiles in split order
   // (deterministic) and writes C.
-  int tile_id, split, ksplit;
-  if ((int)blockIdx.x < n_full) { tile_id = blockIdx.x; split = 0; ksplit = 1; }
+  uint32_t rank = 0;                               // CTA rank in the pair
+  if constexpr (CTA2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int unit_idx = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  int unit, split, ksplit;
+  if (unit_idx < n_full) { unit = unit_idx; split = 0; ksplit = 1; }
   else {
-    const int t = (int)blockIdx.x - n_full;
-    tile_id = n_full + t / ksplit_tail; split = t % ksplit_tail; ksplit = ksplit_tail;
+    const int t = unit_idx - n_full;
+    unit = n_full + t / ksplit_tail; split = t % ksplit_tail; ksplit = ksplit_tail;
   }
+  // per-CTA 128 x 128 tile ids (partial tiles, counters, dot partials)
+  const int tile_id = CTA2 ? 2 * unit + (int)rank : unit;
+  const int ptile = CTA2 ? 2 * (unit - n_full) + (int)rank : unit - n_full;
   int tm, tn;
   {
-    const int tile = tile_id;
-    const int per_group = OZ_GROUP_M * tiles_n;
-    const int first_m = (tile / per_group) * OZ_GROUP_M;
-    const int gsize = (tiles_m - first_m) < OZ_GROUP_M ? (tiles_m - first_m) : OZ_GROUP_M;
+    const int tile = unit;
+    constexpr int GM = CTA2 ? OZ_GROUP_M / 2 : OZ_GROUP_M;   // tiles_m counts units (256 rows when CTA2)
+    const int per_group = GM * tiles_n;
+    const int first_m = (tile / per_group) * GM;
+    const int gsize = (tiles_m - first_m) < GM ? (tiles_m - first_m) : GM;
     const int in_group = tile % per_group;
     tm = first_m + in_group % gsize;
     tn = in_group / gsize;
   }
-  const int row0 = tm * OZ_BM, col0 = tn * OZ_BN;
+  const int row0 = CTA2 ? tm * 2 * OZ_BM + (int)rank * OZ_BM : tm * OZ_BM, col0 = tn * OZ_BN;
+  const int bcol0 = CTA2 ? col0 + (int)rank * (OZ_BN / 2) : col0;       // first B row this CTA stages
   const int kb0 = ksplit > 1 ? split * kb_per_split : 0;
   const int kb1 = ksplit > 1 ? ((kb0 + kb_per_split) < kblocks ? (kb0 + kb_per_split) : kblocks) : kblocks;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int a = 0; a < OZ_ACC; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
+    for (int a = 0; a < OZ_ACC; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, CTA2 ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(OZ_ACC * OZ_BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(OZ_ACC * OZ_BN));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(OZ_ACC * OZ_BN));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();          // both CTAs' barriers exist before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // barriers and TMEM are set up while the previous kernel drains; its results are needed from here on
@@ -189,16 +241,24 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int st = it % OZ_STAGES;
             const uint32_t ph = (uint32_t)(it / OZ_STAGES) & 1u;
             mbar_wait(empty_bar + 8 * st, ph ^ 1u);
-            mbar_expect_tx(full_bar + 8 * st, 2 * OZ_TILE_BYTES);
-            tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES, &tmA, full_bar + 8 * st, kb * OZ_BK, s * rowsA + row0);
-            tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES, &tmB, full_bar + 8 * st, kb * OZ_BK,
-                        (hi - s) * rowsB + col0);
+            if constexpr (CTA2) {
+              // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+              if (rank == 0) mbar_expect_tx(full_bar + 8 * st, 2 * (OZ_TILE_BYTES + OZ_TILE_BYTES / 2));
+              tma_load_2d_pair(tiles + st * 2 * OZ_TILE_BYTES, &tmA, full_bar + 8 * st, kb * OZ_BK, s * rowsA + row0);
+              tma_load_2d_pair(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES, &tmB, full_bar + 8 * st, kb * OZ_BK,
+                               (hi - s) * rowsB + bcol0);
+            } else {
+              mbar_expect_tx(full_bar + 8 * st, 2 * OZ_TILE_BYTES);
+              tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES, &tmA, full_bar + 8 * st, kb * OZ_BK, s * rowsA + row0);
+              tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES, &tmB, full_bar + 8 * st, kb * OZ_BK,
+                          (hi - s) * rowsB + col0);
+            }
           }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (the leader CTA only when paired) =====
+    if (lane == 0 && (!CTA2 || rank == 0)) {
       int it = 0;
       for (int g = (nslices & 1) ? -1 : 0; g < nslices; g += 2) {
         const int lo = g, hi = g + 1;
@@ -218,24 +278,33 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t bdesc = make_smem_desc(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES);
 #pragma unroll
             for (int k4 = 0; k4 < OZ_BK / 32; ++k4) {
-              umma_i8(d_hi, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_hi);
+              if constexpr (CTA2) umma_i8_pair(d_hi, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC2, acc_hi);
+              else umma_i8(d_hi, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_hi);
               acc_hi = 1;
             }
             if (s >= 1) {
               const uint64_t pdesc = make_smem_desc(tiles + prev * 2 * OZ_TILE_BYTES);
 #pragma unroll
               for (int k4 = 0; k4 < OZ_BK / 32; ++k4) {
-                umma_i8(d_lo, pdesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_lo);
+                if constexpr (CTA2) umma_i8_pair(d_lo, pdesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC2, acc_lo);
+                else umma_i8(d_lo, pdesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_lo);
                 acc_lo = 1;
               }
-              umma_commit(empty_bar + 8 * prev);   // previous step's tiles are free once these retire
+              // previous step's tiles are free (in both CTAs) once these retire
+              if constexpr (CTA2) umma_commit_pair(empty_bar + 8 * prev); else umma_commit(empty_bar + 8 * prev);
             }
             prev = st;
           }
-          umma_commit(empty_bar + 8 * prev);
+          if constexpr (CTA2) umma_commit_pair(empty_bar + 8 * prev); else umma_commit(empty_bar + 8 * prev);
         }
-        if (lo >= 0) umma_commit(tfull_bar + 8 * (lo & 3));
-        umma_commit(tfull_bar + 8 * (hi & 3));     // levels complete in TMEM
+        // levels complete in TMEM (of both CTAs)
+        if constexpr (CTA2) {
+          if (lo >= 0) umma_commit_pair(tfull_bar + 8 * (lo & 3));
+          umma_commit_pair(tfull_bar + 8 * (hi & 3));
+        } else {
+          if (lo >= 0) umma_commit(tfull_bar + 8 * (lo & 3));
+          umma_commit(tfull_bar + 8 * (hi & 3));
+        }
       }
     }
   } else {
@@ -268,12 +337,12 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(tempty_bar + 8 * acc); else mbar_arrive(tempty_bar + 8 * acc); }
     }
     if (ksplit > 1) {
       // partial tiles are private to this kernel: stored thread-major so that every store / load
       // instruction of a warp covers 512 contiguous bytes
-      const int ptile = tile_id - n_full;        // partial tiles / counters exist for split tiles only
+      // partial tiles / counters exist for split units only (ptile)
       double2* mine = reinterpret_cast<double2*>(partial + ((long)ptile * ksplit + split) * (OZ_BM * OZ_BN)) +
                       (half * 32) * OZ_BM + r;
 #pragma unroll
@@ -353,9 +422,13 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();          // the peer may still be arriving on / reading from this CTA
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(OZ_ACC * OZ_BN));
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(OZ_ACC * OZ_BN));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(OZ_ACC * OZ_BN));
   }
 }
 
@@ -645,8 +718,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp);
-
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -659,12 +730,12 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp) {
+int ozaki_make_map(CUtensorMap* map, const signed char* q, long total_rows, int Kp, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)total_rows};
   cuuint64_t strides[1] = {(cuuint64_t)Kp};
-  cuuint32_t box[2] = {(cuuint32_t)OZ_BK, (cuuint32_t)OZ_BM};
+  cuuint32_t box[2] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)q, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -751,23 +822,40 @@ int launch_wapply_split(cudaStream_t st, int cplx, const WApplyParams& p, int ns
   return 0;
 }
 
-int ozaki_gemm_tiles(int m, int n) { return (int)(ceil_div(m, OZ_BM) * ceil_div(n, OZ_BN)); }
+// CTA-pair (cta_group::2) kernel for m > 128: validated, but measured no faster than one CTA per
+// tile on B200 (M=1024: 90.6 vs 95.6 TFLOP/s FP64-equivalent, the digit GEMMs already sit at the
+// sustained int8 rate under the power cap; M=256: 52 vs 55) -- opt-in with RN_OZ_CTA2=1.
+static int g_oz_cta2 = -1;
+static bool oz_use_pair(int m) {
+  if (g_oz_cta2 < 0) { const char* e = getenv("RN_OZ_CTA2"); g_oz_cta2 = (e && e[0] == '1') ? 1 : 0; }
+  return g_oz_cta2 && m > OZ_BM;
+}
+
+// Number of 128 x 128 CTA tiles (= inner-product partials of the fused dot) of an m x n product.
+int ozaki_gemm_tiles(int m, int n) {
+  const long tn = ceil_div(n, OZ_BN);
+  return (int)(oz_use_pair(m) ? 2 * ceil_div(m, 2 * OZ_BM) * tn : ceil_div(m, OZ_BM) * tn);
+}
 
 int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, const CUtensorMap* tmA,
-                           const double* sA, const CUtensorMap* tmB, const double* sB, double* C, long ldc,
-                           const double* dotv, double* dot_partial) {
+                           const double* sA, const CUtensorMap* tmB, const CUtensorMap* tmB64, const double* sB,
+                           double* C, long ldc, const double* dotv, double* dot_partial) {
   if (m <= 0 || n <= 0) return 0;
   if (nslices < 1 || nslices > OZ_MAX_SLICES) return (int)cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    RN_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    RN_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    RN_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
     attr_set = true;
   }
+  const bool pair = tmB64 != nullptr && oz_use_pair(m);
   const int Kp = (K + 15) & ~15;
   const int kblocks = (Kp + OZ_BK - 1) / OZ_BK;
-  const int tiles_m = (int)ceil_div(m, OZ_BM), tiles_n = (int)ceil_div(n, OZ_BN);
+  // scheduling units: tiles, or 256 x 128 tile pairs run by two CTAs on neighbouring SMs
+  const int tiles_m = (int)ceil_div(m, pair ? 2 * OZ_BM : OZ_BM), tiles_n = (int)ceil_div(n, OZ_BN);
   const int tiles = tiles_m * tiles_n;
-  // split-K when the tile count leaves SMs idle: pick the K partition with the smallest modelled
+  const int per_unit = pair ? 2 : 1;
+  // split-K when the unit count leaves SMs idle: pick the K partition with the smallest modelled
   // time  waves * (K blocks per CTA * products * 256 clk + fixed CTA cost) + reduction
   int ksplit = 1, kb_per = kblocks, n_full = 0;
   if (g_oz_sms < 0) {
@@ -776,29 +864,30 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
     RN_CHECK(cudaDeviceGetAttribute(&g_oz_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("RN_OZ_KSPLIT")) g_oz_force_ksplit = atoi(e);
   }
+  const int slots = g_oz_sms / per_unit;
   {
     const double t_kb = 256.0 * (nslices * (nslices + 1) / 2), t_fixed = 9000.0, t_red = 1200.0;
     double best = 1e300;
     const int smax = kblocks < 16 ? kblocks : 16;
-    // (a) every tile split the same way
+    // (a) every unit split the same way
     for (int s = 1; s <= smax; ++s) {
       const int per = (kblocks + s - 1) / s;
       const int seff = (kblocks + per - 1) / per;
       if (seff != s) continue;
-      if ((double)tiles * seff * OZ_BM * OZ_BN * 8.0 > 192e6) continue;   // partial tiles stay L2 resident
-      const long waves = ceil_div((long)tiles * seff, g_oz_sms);
+      if ((double)tiles * per_unit * seff * OZ_BM * OZ_BN * 8.0 > 192e6) continue;   // partial tiles stay L2 resident
+      const long waves = ceil_div((long)tiles * seff, slots);
       const double cost = waves * (per * t_kb + t_fixed) + (seff > 1 ? t_red * seff + 2000.0 : 0.0);
       if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; n_full = 0; }
     }
     // (b) whole waves unsplit, the ragged last wave split along K
-    const int tail = tiles % g_oz_sms, full = tiles - tail;
+    const int tail = tiles % slots, full = tiles - tail;
     if (full > 0 && tail > 0) {
-      const int st_max = g_oz_sms / tail < smax ? g_oz_sms / tail : smax;
+      const int st_max = slots / tail < smax ? slots / tail : smax;
       for (int s = 2; s <= st_max; ++s) {
         const int per = (kblocks + s - 1) / s;
         const int seff = (kblocks + per - 1) / per;
         if (seff != s) continue;
-        const double cost = (full / g_oz_sms) * (kblocks * t_kb + t_fixed) + (per * t_kb + t_fixed) + t_red * seff + 2000.0;
+        const double cost = (full / slots) * (kblocks * t_kb + t_fixed) + (per * t_kb + t_fixed) + t_red * seff + 2000.0;
         if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; n_full = full; }
       }
     }
@@ -809,13 +898,14 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
     }
   }
   if (ksplit == 1) n_full = tiles;
-  const int split_tiles = tiles - n_full;
+  const int split_units = tiles - n_full;
   double* partial = nullptr;
   int* counters = nullptr;
-  if (split_tiles > 0) {
+  if (split_units > 0) {
     // per-stream scratch that outlives the launch: the tile counters reset themselves (last CTA),
     // so they are zeroed once, and no allocation / memset node sits between the kernels of a chain
     OzScratch& sc = oz_scratch(st);
+    const int split_tiles = split_units * per_unit;
     const size_t pbytes = (size_t)split_tiles * ksplit * OZ_BM * OZ_BN * sizeof(double);
     if (pbytes > sc.partial_bytes) {
       if (sc.partial) RN_CHECK(cudaFreeAsync(sc.partial, st));
@@ -833,9 +923,26 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
     partial = sc.partial;
     counters = sc.counters;
   }
-  { RN_LAUNCH(ozaki_gemm_kernel, (unsigned)(n_full + split_tiles * ksplit), OZ_THREADS, OZ_SMEM, st,
-      *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, n_full, ksplit > 1 ? ksplit : 1, kb_per,
-      partial, counters, dotv, dot_partial); rn::g_launches++; }
+  const unsigned units_launched = (unsigned)(n_full + split_units * ksplit);
+  const int ks_arg = ksplit > 1 ? ksplit : 1;
+  if (!pair) {
+    { RN_LAUNCH(ozaki_gemm_kernel<false>, units_launched, OZ_THREADS, OZ_SMEM, st,
+        *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, n_full, ks_arg, kb_per,
+        partial, counters, dotv, dot_partial); rn::g_launches++; }
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * units_launched); cfg.blockDim = dim3(OZ_THREADS);
+    cfg.dynamicSmemBytes = OZ_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    RN_CHECK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<true>, *tmA, *tmB64, sA, sB, C, m, n, ldc, m, n, kblocks,
+                                nslices, tiles_m, tiles_n, n_full, ks_arg, kb_per, partial, counters, dotv, dot_partial));
+    rn::g_launches++;
+  }
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -845,11 +952,14 @@ int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const s
   if (m <= 0 || n <= 0) return 0;
   const int Kp = (K + 15) & ~15;
   CUtensorMap tmA, tmB;
-  int err = ozaki_make_map(&tmA, qA, (long)nslices * m, Kp);
+  CUtensorMap tmB64;
+  int err = ozaki_make_map(&tmA, qA, (long)nslices * m, Kp, OZ_BM);
   if (err) return err;
-  err = ozaki_make_map(&tmB, qB, (long)nslices * n, Kp);
+  err = ozaki_make_map(&tmB, qB, (long)nslices * n, Kp, OZ_BN);
   if (err) return err;
-  return launch_ozaki_gemm_maps(st, m, n, K, nslices, &tmA, sA, &tmB, sB, C, ldc, nullptr, nullptr);
+  err = ozaki_make_map(&tmB64, qB, (long)nslices * n, Kp, OZ_BN / 2);
+  if (err) return err;
+  return launch_ozaki_gemm_maps(st, m, n, K, nslices, &tmA, sA, &tmB, &tmB64, sB, C, ldc, nullptr, nullptr);
 }
 
 }  // namespace rn

@@ -462,3 +462,27 @@ def test_qr_fallback_path_subprocess():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_ozaki_gemm_cta_pair_subprocess():
+    """The opt-in cta_group::2 variant of the digit GEMM (two CTAs per 256 x 128 tile, RN_OZ_CTA2=1,
+    read once per process) gives the same product, with and without split-K."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, '.')\n"
+        "from renormalizer_b200 import ops\n"
+        "from renormalizer_b200.backend import asxp\n"
+        "rng = np.random.default_rng(2)\n"
+        "for (m, n, k) in [(300, 130, 129), (768, 4096, 512), (2048, 512, 1536), (1000, 257, 4000)]:\n"
+        "    a, b = rng.standard_normal((m, k)), rng.standard_normal((n, k))\n"
+        "    c = ops.ozaki_gemm_tn(asxp(a), asxp(b), m, n, k, k, k, nslices=7).cpu().numpy()\n"
+        "    bound = np.abs(a).max(axis=1)[:, None] * np.abs(b).max(axis=1)[None, :] * k\n"
+        "    assert (np.abs(c - a @ b.T) / bound).max() < 4e-14, (m, n, k)\n"
+        "print('pair ok')\n")
+    env = dict(os.environ, RN_OZ_CTA2="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "pair ok" in out.stdout, out.stderr[-2000:]
