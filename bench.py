@@ -337,8 +337,7 @@ def run_ours(args):
             new = m.evolve(mpo_step, args.dt)
             new.store_sites_to_host(host_out)
             torch.cuda.synchronize()
-            for a, b in zip(host_in, host_out):           # next step starts from the host result
-                a.copy_(b)
+            host_in[:], host_out[:] = host_out[:], host_in[:]   # next step starts from the host result
         for _ in range(max(1, args.warmup // 2)):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
