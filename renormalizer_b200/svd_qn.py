@@ -124,6 +124,20 @@ def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray
 
     u_nz, u_z, v_nz, v_z, s_nz, su_z, sv_z = [], [], [], [], [], [], []
     ql_nz, ql_z, qr_nz, qr_z = [], [], [], []
+    if QR and not full_matrices and not (lqn.any() or rqn.any() or qntot.any()):
+        # no conserved quantum number: one block, nothing to gather or scatter (the general code below
+        # produces exactly this; the short cut keeps the host out of the way between two kernels)
+        if system == "R":
+            bu, bq = ops.qr(mat.contiguous(), lq=True)
+            bv = bq.transpose(0, 1)
+        elif system == "L":
+            bu, br = ops.qr(mat.contiguous())
+            bv = br.transpose(0, 1)
+        else:
+            assert False
+        zero = (0,) * qn_size
+        dim = min(nl, nr)
+        return bu, [zero] * dim, bv, [zero] * dim
     for ql in _distinct_qn(lqn):
         qr_ = qntot - ql
         rset = np.where(get_qn_mask(rqn, qr_))[0]
