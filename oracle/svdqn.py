@@ -122,6 +122,29 @@ def svd_qn(coef_array, qnbigl, qnbigr, qntot, QR=False, system=None, full_matric
     return u, su, qnl_new, v, sv, qnr_new
 
 
+def eigh_qn(dm, qnbigl, qnbigr, qntot, system):
+    """Block diagonalisation of the averaged reduced density matrix of the multi-state algorithm.
+    Reference: renormalizer/mps/svd_qn.py:243-302.  Returns (U, sqrt(eigenvalues), new qn)."""
+    assert system in ("L", "R")
+    qnbig, comp = (qnbigl, qnbigr) if system == "L" else (qnbigr, qnbigl)
+    qn_size = len(qntot)
+    localqn = qnbig.reshape(-1, qn_size)
+    n = len(localqn)
+    us, ss, new_qn = [], [], []
+    for nl in set([tuple(t) for t in localqn]):
+        nr = qntot - nl
+        if np.sum(get_qn_mask(comp, nr)) == 0:
+            continue
+        lset = np.where(get_qn_mask(localqn, nl))[0]
+        block = dm.reshape(n, n)[np.ix_(lset, lset)]
+        s2, bu = scipy.linalg.eigh(block)
+        s2[s2 < 0] = 0
+        ss.append(np.sqrt(s2))
+        us.append(_scatter_rows(lset, bu, n))
+        new_qn += [nl] * len(lset)
+    return np.concatenate(us, axis=1), np.concatenate(ss), new_qn
+
+
 def select_basis(vset, sset, qnlist, compset, mmax, percent=0):
     """Pick the retained renormalised basis: `percent` of it evenly from each quantum-number
     sector, the rest by singular value.  Reference: renormalizer/mps/lib.py:265-335.

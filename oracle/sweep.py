@@ -6,7 +6,7 @@ import numpy as np
 import scipy.linalg
 
 from .contract import hop_apply, hop_diag, env_update
-from .svdqn import add_outer, get_qn_mask, svd_qn, select_basis
+from .svdqn import add_outer, get_qn_mask, svd_qn, select_basis, eigh_qn
 from .krylov import expm_krylov
 from .davidson import davidson
 
@@ -216,33 +216,65 @@ def update_mps(mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent=0.0):
     Reference: renormalizer/mps/mp.py:651-888 (_update_mps), single-state SVD branch (no OFS).
     """
     system = "L" if mps.to_right else "R"
-    u, su, qnlnew, v, sv, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, mps.qntot, system=system)
-    if mps.to_right:
-        ms, msdim, msqn, compms = select_basis(u, su, qnlnew, v, m_trunc_fixed(su, m_max), percent)
-        ms = ms.reshape(list(qnbigl.shape[:-1]) + [msdim])
-        compms = np.moveaxis(compms.reshape(list(qnbigr.shape[:-1]) + [msdim]), -1, 0)
+    multi = isinstance(cstruct, list)
+    rotated_c, averaged_ms = [], []
+    if not multi:
+        u, su, qnlnew, v, sv, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, mps.qntot, system=system)
+        if mps.to_right:
+            ms, msdim, msqn, compms = select_basis(u, su, qnlnew, v, m_trunc_fixed(su, m_max), percent)
+            ms = ms.reshape(list(qnbigl.shape[:-1]) + [msdim])
+            compms = np.moveaxis(compms.reshape(list(qnbigr.shape[:-1]) + [msdim]), -1, 0)
+        else:
+            ms, msdim, msqn, compms = select_basis(v, sv, qnrnew, u, m_trunc_fixed(sv, m_max), percent)
+            ms = np.moveaxis(ms.reshape(list(qnbigr.shape[:-1]) + [msdim]), -1, 0)
+            compms = compms.reshape(list(qnbigl.shape[:-1]) + [msdim])
     else:
-        ms, msdim, msqn, compms = select_basis(v, sv, qnrnew, u, m_trunc_fixed(sv, m_max), percent)
-        ms = np.moveaxis(ms.reshape(list(qnbigr.shape[:-1]) + [msdim]), -1, 0)
-        compms = compms.reshape(list(qnbigl.shape[:-1]) + [msdim])
+        # state-averaged method (mp.py:780-838): basis from the averaged reduced density matrix
+        nl_axes = qnbigl.ndim - 1
+        ddm = 0.0
+        for c in cstruct:
+            if mps.to_right:
+                ax = list(range(nl_axes, c.ndim))
+            else:
+                ax = list(range(nl_axes))
+            ddm = ddm + np.tensordot(c, c, axes=(ax, ax))
+        ddm = ddm / len(cstruct)
+        uset, sset, qnnew = eigh_qn(ddm, qnbigl, qnbigr, mps.qntot, system)
+        ms, msdim, msqn, _ = select_basis(uset, sset, qnnew, None, m_trunc_fixed(sset, m_max), percent)
+        if mps.to_right:
+            ms = ms.reshape(list(qnbigl.shape[:-1]) + [msdim])
+            for c in cstruct:
+                rotated_c.append(np.tensordot(ms, c, axes=(list(range(nl_axes)), list(range(nl_axes)))))
+            compms = rotated_c[0]
+        else:
+            ms = ms.reshape(list(qnbigr.shape[:-1]) + [msdim])
+            for c in cstruct:
+                rotated_c.append(np.tensordot(c, ms, axes=(list(range(nl_axes, c.ndim)),
+                                                          list(range(qnbigr.ndim - 1)))))
+            compms = rotated_c[0]
+            ms = np.moveaxis(ms, -1, 0)
     n = len(mps)
     if len(cidx) == 1:
         i = cidx[0]
         mps.sites[i] = ms
         if mps.to_right:
             if i != n - 1:
+                averaged_ms = [np.tensordot(c, mps.sites[i + 1], axes=1) for c in rotated_c]
                 mps.sites[i + 1] = np.tensordot(compms, mps.sites[i + 1], axes=1)
                 mps.qn[i + 1] = msqn
                 mps.qnidx = i + 1
             else:
+                averaged_ms = [np.tensordot(mps.sites[i], c, axes=1) for c in rotated_c]
                 mps.sites[i] = np.tensordot(mps.sites[i], compms, axes=1)
                 mps.qnidx = n - 1
         else:
             if i != 0:
+                averaged_ms = [np.tensordot(mps.sites[i - 1], c, axes=1) for c in rotated_c]
                 mps.sites[i - 1] = np.tensordot(mps.sites[i - 1], compms, axes=1)
                 mps.qn[i] = msqn
                 mps.qnidx = i - 1
             else:
+                averaged_ms = [np.tensordot(c, mps.sites[i], axes=1) for c in rotated_c]
                 mps.sites[i] = np.tensordot(compms, mps.sites[i], axes=1)
                 mps.qnidx = 0
     else:
@@ -252,7 +284,9 @@ def update_mps(mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent=0.0):
         else:
             mps.sites[cidx[1]], mps.sites[cidx[0]] = ms, compms
             mps.qnidx = cidx[0]
+        averaged_ms = rotated_c
         mps.qn[cidx[1]] = msqn
+    return averaged_ms if multi else None
 
 
 def _sign_fix(c):
@@ -267,12 +301,14 @@ def _scatter(c, mask):
     return out
 
 
-def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, stats=None):
-    """One DMRG sweep over all sites.  Reference: renormalizer/mps/gs.py:174-304 (nroots=1,
-    omega=None, algo="davidson").  Returns (micro results [(e, cidx)], res_mps)."""
+def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, stats=None, nroots=1):
+    """One DMRG sweep over all sites.  Reference: renormalizer/mps/gs.py:174-304 (omega=None,
+    algo="davidson"; nroots > 1 is the state-averaged algorithm).  Returns (micro results
+    [(e, cidx)], res_mps) with res_mps a list of Mps when nroots > 1."""
     n = len(mps)
     micro = []
     res_mps = None
+    averaged_ms = []
     for imps in mps.iter_idx_list(full=True):
         if method == "2site" and ((mps.to_right and imps == n - 1) or
                                   (not mps.to_right and imps == 0)):
@@ -300,14 +336,32 @@ def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, s
                                 optimize=True)
                 ham = ham[:, :, :, :, mask][mask, :]
             w, vec = scipy.linalg.eigh(ham)
-            e, c = w[0], _sign_fix(vec[:, 0])
+            if nroots == 1:
+                e, c = w[0], _sign_fix(vec[:, 0])
+            else:
+                e = w[:nroots]
+                c = [_sign_fix(vec[:, i]) for i in range(min(nroots, vec.shape[1]))]
             nhop = 0
         else:
             # Davidson.  Reference: gs.py:410-576
-            if len(cidx) == 1:
-                guess = mps.sites[cidx[0]]
+            if nroots == 1:
+                if len(cidx) == 1:
+                    guess = mps.sites[cidx[0]]
+                else:
+                    guess = np.tensordot(mps.sites[cidx[0]], mps.sites[cidx[1]], axes=1)
+                cguess = [guess[mask]]
             else:
-                guess = np.tensordot(mps.sites[cidx[0]], mps.sites[cidx[1]], axes=1)
+                cguess = []
+                for ms in averaged_ms:
+                    if len(cidx) == 1:
+                        raw = ms
+                    elif mps.to_right:
+                        raw = np.tensordot(ms, mps.sites[cidx[1]], axes=1)
+                    else:
+                        raw = np.tensordot(mps.sites[cidx[0]], ms, axes=1)
+                    cguess.append(raw[mask])
+                guess_dim = int(np.sum(mask))
+                cguess.extend([np.random.rand(guess_dim) - 0.5 for _ in range(len(cguess), nroots)])
             hdiag = hop_diag(ltensor, rtensor, cmo)[mask]
             count = [0]
 
@@ -317,23 +371,36 @@ def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, s
 
             def precond(x, e, *args):
                 return x / (hdiag - e + 1e-4)
-            e, c = davidson(hop, [guess[mask]], precond, max_cycle=100, nroots=1)
-            c = _sign_fix(c)
+            e, c = davidson(hop, cguess, precond, max_cycle=100, nroots=nroots)
+            if nroots == 1:
+                c = _sign_fix(c)
+            else:
+                c = [_sign_fix(ci) for ci in c]
             nhop = count[0]
         if stats is not None:
             stats.append(nhop)
+        if nroots > 1:
+            e = np.asarray(e).tolist()
         micro.append((e, cidx))
-        cstruct = _scatter(c, mask)
+        if nroots == 1:
+            cstruct = _scatter(c, mask)
+        else:
+            cstruct = [_scatter(ci, mask) for ci in c]
         if cidx == last_opt_idx:
-            res_mps = mps.copy()
-            update_mps(res_mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent)
-        update_mps(mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent)
+            if nroots == 1:
+                res_mps = mps.copy()
+                update_mps(res_mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent)
+            else:
+                res_mps = [mps.copy() for _ in cstruct]
+                for r, ci in zip(res_mps, cstruct):
+                    update_mps(r, ci, cidx, qnbigl, qnbigr, m_max, percent)
+        averaged_ms = update_mps(mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent)
     mps.switch_direction()
     return micro, res_mps
 
 
 def optimize_mps(mps, mpo, procedure, method="2site", e_rtol=1e-6, e_atol=1e-8, stats=None,
-                 micro_out=None):
+                 micro_out=None, nroots=1):
     """DMRG ground state.  Reference: renormalizer/mps/gs.py:54-171.  `mps` is overwritten.
     Returns (energy per sweep, optimised Mps)."""
     if mps.qnidx == len(mps) - 1:     # is_left_canonical
@@ -348,7 +415,7 @@ def optimize_mps(mps, mpo, procedure, method="2site", e_rtol=1e-6, e_atol=1e-8, 
     res_mps = None
     for isweep, (m_max, percent) in enumerate(procedure):
         micro, res_mps, = dmrg_single_sweep(mps, mpo, environ, method, int(m_max), percent,
-                                            opt_idx, stats)
+                                            opt_idx, stats, nroots)
         if micro_out is not None:
             micro_out.append(np.array([e for e, _ in micro]))
         opt_e = min(micro)
@@ -359,9 +426,10 @@ def optimize_mps(mps, mpo, procedure, method="2site", e_rtol=1e-6, e_atol=1e-8, 
             if np.allclose(v1, v2, rtol=e_rtol, atol=e_atol):
                 break
     assert res_mps is not None
-    res_mps.normalize_mps_only()
-    res_mps.ensure_left_canonical()
-    res_mps.canonicalise()
+    for r in (res_mps if isinstance(res_mps, list) else [res_mps]):
+        r.normalize_mps_only()
+        r.ensure_left_canonical()
+        r.canonicalise()
     return macro, res_mps
 
 

@@ -31,38 +31,16 @@ struct WCsr {
   const double* val = nullptr;
 };
 
-// Optional per-launch timing of the contraction GEMMs (bench.py's roofline leg).
-struct GemmProfile {
-  bool on = false;
-  std::vector<cudaEvent_t> ev;
-  double flops = 0.0;
-};
-static GemmProfile g_prof;
 static int g_ozaki_slices = 7;
 static double g_ozaki_min_work = 4.0e6;
 
 static int gemm_dispatch(cudaStream_t st, int path, int m, int n, int k, const double* A, long lda,
                          const double* B, long ldb, double* C, long ldc) {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_prof.on) {
-    RN_CHECK(cudaEventCreate(&e0));
-    RN_CHECK(cudaEventCreate(&e1));
-    RN_CHECK(cudaEventRecord(e0, st));
-  }
-  int err;
   // tensor-core path for contractions large enough to fill 128x128 tiles; boundary sites stay on
   // the exact DMMA kernel
   if (path == 1 && (double)m * n * k >= g_ozaki_min_work && k <= 65536)
-    err = rn_ozaki_gemm_tn(st, m, n, k, A, lda, B, ldb, C, ldc, g_ozaki_slices);
-  else
-    err = launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
-  if (g_prof.on) {
-    RN_CHECK(cudaEventRecord(e1, st));
-    g_prof.ev.push_back(e0);
-    g_prof.ev.push_back(e1);
-    g_prof.flops += 2.0 * m * n * k;
-  }
-  return err;
+    return rn_ozaki_gemm_tn(st, m, n, k, A, lda, B, ldb, C, ldc, g_ozaki_slices);
+  return launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
 }
 
 // A GEMM operand split into int8 digits, with its TMA descriptor (tcgen05 path).
@@ -97,24 +75,11 @@ static bool use_ozaki(int path, double m, double n, double k) {
 static int oz_gemm(cudaStream_t st, OzOperand& a, const double* a_fresh, long lda, OzOperand& b,
                    const double* b_fresh, long ldb, double* C, long ldc, const double* dotv = nullptr,
                    double* dot_partial = nullptr) {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
   int err;
   if (a_fresh) { err = launch_ozaki_split(st, a_fresh, lda, a.rows, a.K, a.nslices, a.q, a.scale); if (err) return err; }
   if (b_fresh) { err = launch_ozaki_split(st, b_fresh, ldb, b.rows, b.K, b.nslices, b.q, b.scale); if (err) return err; }
-  if (g_prof.on) {
-    RN_CHECK(cudaEventCreate(&e0));
-    RN_CHECK(cudaEventCreate(&e1));
-    RN_CHECK(cudaEventRecord(e0, st));
-  }
-  err = launch_ozaki_gemm_maps(st, a.rows, b.rows, a.K, a.nslices, &a.map, a.scale, &b.map, &b.map64, b.scale, C, ldc,
-                               dotv, dot_partial);
-  if (g_prof.on) {
-    RN_CHECK(cudaEventRecord(e1, st));
-    g_prof.ev.push_back(e0);
-    g_prof.ev.push_back(e1);
-    g_prof.flops += 2.0 * a.rows * b.rows * a.K;
-  }
-  return err;
+  return launch_ozaki_gemm_maps(st, a.rows, b.rows, a.K, a.nslices, &a.map, a.scale, &b.map, &b.map64, b.scale, C, ldc,
+                                dotv, dot_partial);
 }
 
 }  // namespace rn
@@ -436,32 +401,6 @@ extern "C" int rn_matmul(void* stream, int cplx, int M, int K, int N, const void
                                 (double*)out, (long)N * es);
   cudaFreeAsync(bp, st);
   return err;
-}
-
-// ---- GEMM launch profiling (used by bench.py only) ---------------------------------------------
-extern "C" int rn_profile_begin(void) {
-  g_prof.on = true;
-  g_prof.ev.clear();
-  g_prof.flops = 0.0;
-  return 0;
-}
-
-extern "C" int rn_profile_end(double* total_ms, double* total_flops, long* launches) {
-  g_prof.on = false;
-  RN_CHECK(cudaDeviceSynchronize());
-  double ms = 0.0;
-  for (size_t i = 0; i + 1 < g_prof.ev.size(); i += 2) {
-    float t = 0.f;
-    RN_CHECK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
-    ms += t;
-    cudaEventDestroy(g_prof.ev[i]);
-    cudaEventDestroy(g_prof.ev[i + 1]);
-  }
-  if (total_ms) *total_ms = ms;
-  if (total_flops) *total_flops = g_prof.flops;
-  if (launches) *launches = (long)(g_prof.ev.size() / 2);
-  g_prof.ev.clear();
-  return 0;
 }
 
 extern "C" int rn_set_ozaki(int nslices, double min_work) {

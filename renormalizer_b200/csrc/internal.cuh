@@ -40,6 +40,8 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
                            const double* sA, const CUtensorMap* tmB, const CUtensorMap* tmB64, const double* sB,
                            double* C, long ldc, const double* dotv = nullptr, double* dot_partial = nullptr);
 int ozaki_gemm_tiles(int m, int n);
+bool gemm_profile_on();
+void gemm_profile_mark(cudaStream_t st, int kind, double flops_if_end);
 int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
                       const double* sA, const signed char* qB, const double* sB, double* C, long ldc);
 

@@ -26,6 +26,7 @@
 
 #include <cuda.h>
 #include <map>
+#include <vector>
 #include <mutex>
 #include <type_traits>
 
@@ -698,6 +699,24 @@ wapply_split_kernel(WApplyParams p, int Kp, int nslices, signed char* __restrict
 // -------------------------------------------------------------------------------------- host
 static int g_oz_sms = -1;
 
+// Optional per-launch timing of the GEMM kernels (bench.py's roofline leg): between
+// rn_profile_begin and rn_profile_end every launch of the given kind is bracketed by CUDA events
+// on its own stream.  kind 1 = tcgen05 digit GEMM, kind 0 = FP64 DMMA GEMM.
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[2];
+  double flops[2] = {0.0, 0.0};
+};
+static GemmProfile g_prof;
+bool gemm_profile_on() { return g_prof.on; }
+void gemm_profile_mark(cudaStream_t st, int kind, double flops_if_end) {
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof.ev[kind].push_back(e);
+  g_prof.flops[kind] += flops_if_end;
+}
+
 // Split-K scratch (partial tiles + self-resetting tile counters), one per stream: launches on one
 // stream are ordered, so consecutive GEMMs can share it.
 struct OzScratch {
@@ -924,6 +943,7 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
     counters = sc.counters;
   }
   const unsigned units_launched = (unsigned)(n_full + split_units * ksplit);
+  if (g_prof.on) gemm_profile_mark(st, 1, 0.0);
   const int ks_arg = ksplit > 1 ? ksplit : 1;
   if (!pair) {
     { RN_LAUNCH(ozaki_gemm_kernel<false>, units_launched, OZ_THREADS, OZ_SMEM, st,
@@ -943,6 +963,7 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
                                 nslices, tiles_m, tiles_n, n_full, ks_arg, kb_per, partial, counters, dotv, dot_partial));
     rn::g_launches++;
   }
+  if (g_prof.on) gemm_profile_mark(st, 1, 2.0 * m * n * K);
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -984,5 +1005,35 @@ extern "C" int rn_ozaki_gemm_tn(void* stream, int m, int n, int k, const double*
   err = launch_ozaki_gemm(st, m, n, k, nslices, qA, sA, qB, sB, C, ldc);
   if (err) return err;
   cudaFreeAsync(qA, st); cudaFreeAsync(qB, st); cudaFreeAsync(sA, st); cudaFreeAsync(sB, st);
+  return 0;
+}
+
+// ---- GEMM launch profiling (used by bench.py only) ---------------------------------------------
+extern "C" int rn_profile_begin(void) {
+  using namespace rn;
+  g_prof.on = true;
+  for (int k = 0; k < 2; ++k) { g_prof.ev[k].clear(); g_prof.flops[k] = 0.0; }
+  return 0;
+}
+
+// Totals of the tcgen05 digit GEMM launches when there were any, else of the DMMA launches.
+extern "C" int rn_profile_end(double* total_ms, double* total_flops, long* launches) {
+  using namespace rn;
+  g_prof.on = false;
+  RN_CHECK(cudaDeviceSynchronize());
+  const int kind = g_prof.ev[1].empty() ? 0 : 1;
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.ev[kind].size(); i += 2) {
+    float t = 0.f;
+    RN_CHECK(cudaEventElapsedTime(&t, g_prof.ev[kind][i], g_prof.ev[kind][i + 1]));
+    ms += t;
+  }
+  for (int k = 0; k < 2; ++k) {
+    for (cudaEvent_t e : g_prof.ev[k]) cudaEventDestroy(e);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = g_prof.flops[kind];
+  if (launches) *launches = (long)(g_prof.ev[kind].size() / 2);
+  for (int k = 0; k < 2; ++k) g_prof.ev[k].clear();
   return 0;
 }

@@ -27,8 +27,6 @@ def optimize_mps(mps, mpo, omega: float = None):
         from .mpo import Mpo
         shifted = mpo.add(Mpo.identity_like(mpo).scale(-omega))
         mpo = shifted.squared()
-    if mps.optimize_config.nroots != 1:
-        raise NotImplementedError("state-averaged DMRG (nroots > 1) is outside the accelerated path")
     assert mps.optimize_config.method in ["2site", "1site"]
     if mps.is_left_canonical:
         mps.ensure_right_canonical()
@@ -61,14 +59,22 @@ def optimize_mps(mps, mpo, omega: float = None):
     else:
         logger.warning("DMRG did not converge! Please increase the procedure!")
     assert res_mps is not None
-    res_mps = res_mps.normalize("mps_only").ensure_left_canonical().canonicalise()
-    res_mps.compress_config = compress_config_bk
+    if mps.optimize_config.nroots == 1:
+        res_mps = res_mps.normalize("mps_only").ensure_left_canonical().canonicalise()
+        res_mps.compress_config = compress_config_bk
+    else:
+        res_mps = [mp.normalize("mps_only").ensure_left_canonical().canonicalise() for mp in res_mps]
+        for res in res_mps:
+            res.compress_config = compress_config_bk
     return macro_iteration_result, res_mps
 
 
 def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
     """gs.py:174-304."""
     method = mps.optimize_config.method
+    nroots = mps.optimize_config.nroots
+    # in a state-averaged calculation: the rotated centre tensors of every state (better guesses)
+    averaged_ms = []
     res_mps = None
     micro_iteration_result = []
     hop_counts = []
@@ -97,17 +103,34 @@ def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
             e, cstruct = eigh_direct(mps, qn_mask, ltensor, rtensor, cmo)
             nhop = 0
         else:
-            if method == "1site":
-                raw_cguess = mps[cidx[0]]
+            if nroots == 1:
+                if method == "1site":
+                    raw_cguess = [mps[cidx[0]]]
+                else:
+                    raw_cguess = [ops.tensordot1(mps[cidx[0]], mps[cidx[1]])]
             else:
-                raw_cguess = ops.tensordot1(mps[cidx[0]], mps[cidx[1]])
+                raw_cguess = []
+                for ms in averaged_ms:
+                    if method == "1site":
+                        raw_cguess.append(ms)
+                    elif mps.to_right:
+                        raw_cguess.append(ops.tensordot1(ms, mps[cidx[1]]))
+                    else:
+                        raw_cguess.append(ops.tensordot1(mps[cidx[0]], ms))
             e, cstruct, nhop = eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess)
         hop_counts.append(nhop)
+        if nroots > 1:
+            e = np.asarray(e).tolist()
         micro_iteration_result.append((e, cidx))
         if cidx == last_opt_e_idx:
-            res_mps = mps.copy()
-            res_mps._update_mps(cstruct, cidx, qnbigl, qnbigr, percent)
-        mps._update_mps(cstruct, cidx, qnbigl, qnbigr, percent)
+            if nroots == 1:
+                res_mps = mps.copy()
+                res_mps._update_mps(cstruct, cidx, qnbigl, qnbigr, percent)
+            else:
+                res_mps = [mps.copy() for _ in cstruct]
+                for r, ci in zip(res_mps, cstruct):
+                    r._update_mps(ci, cidx, qnbigl, qnbigr, percent)
+        averaged_ms = mps._update_mps(cstruct, cidx, qnbigl, qnbigr, percent)
     mps._switch_direction()
     mps.hop_counts = hop_counts
     return micro_iteration_result, res_mps, mpo
@@ -137,11 +160,16 @@ def eigh_direct(mps, qn_mask, ltensor, rtensor, cmo):
     hop.close()
     ham = asnumpy(torch.stack(cols, dim=1)) * mps.optimize_config.inverse
     w, v = scipy.linalg.eigh(ham)
-    c = v[:, 0]
-    c = c / np.sign(c[np.abs(c).argmax()])
-    cstruct = np.zeros(nfull, dtype=c.dtype)
-    cstruct[idx] = c
-    return w[0], asxp(cstruct.reshape(cshape))
+
+    def scatter(c):
+        c = c / np.sign(c[np.abs(c).argmax()])
+        cstruct = np.zeros(nfull, dtype=c.dtype)
+        cstruct[idx] = c
+        return asxp(cstruct.reshape(cshape))
+    nroots = mps.optimize_config.nroots
+    if nroots == 1:
+        return w[0], scatter(v[:, 0])
+    return w[:nroots], [scatter(v[:, i]) for i in range(min(nroots, v.shape[1]))]
 
 
 def _hdiag(ltensor, rtensor, cmo):
@@ -164,7 +192,7 @@ def eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess):
     if mps.optimize_config.algo != "davidson":
         raise NotImplementedError("only the Davidson eigensolver is accelerated")
     cshape = qn_mask.shape
-    cplx = ltensor.is_complex() or rtensor.is_complex() or raw_cguess.is_complex()
+    cplx = ltensor.is_complex() or rtensor.is_complex() or any(g.is_complex() for g in raw_cguess)
     dtype = torch.complex128 if cplx else torch.float64
     dev = ltensor.device
     mask = torch.from_numpy(qn_mask.reshape(-1)).to(dev)
@@ -185,8 +213,17 @@ def eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess):
     def precond(x, e, *args):
         return torch.where(mask, x / (hdiag - e + 1e-4).to(dtype), torch.zeros((), dtype=dtype, device=dev))
 
-    guess = raw_cguess.reshape(-1).to(dtype) * maskf
-    e, c = davidson(aop, [guess], precond, max_cycle=100, nroots=1)
+    nroots = mps.optimize_config.nroots
+    guesses = [g.reshape(-1).to(dtype) * maskf for g in raw_cguess]
+    # missing guesses are random in the allowed subspace (gs.py:268-271, same np.random stream)
+    allowed = np.nonzero(qn_mask.reshape(-1))[0]
+    for _ in range(len(guesses), nroots):
+        r = np.zeros(mask.numel())
+        r[allowed] = np.random.rand(len(allowed)) - 0.5
+        guesses.append(asxp(r).to(dtype))
+    e, c = davidson(aop, guesses, precond, max_cycle=100, nroots=nroots)
     hop.close()
+    if nroots > 1:
+        return e, [_sign_fix(ci).reshape(cshape) for ci in c], count[0]
     c = _sign_fix(c)
     return e, c.reshape(cshape), count[0]

@@ -17,7 +17,7 @@ from .configs import CompressConfig, EvolveConfig, OptimizeConfig, EvolveMethod
 from .hop_expr import hop_expr_dtype
 from .krylov import expm_krylov
 from .lib import Environ, contract_one_site
-from .svd_qn import add_outer, svd_qn, select_basis
+from .svd_qn import add_outer, svd_qn, select_basis, eigh_qn
 
 
 class Mps:
@@ -302,43 +302,78 @@ class Mps:
 
     # ------------------------------------------------------------------ centre update (DMRG)
     def _update_mps(self, cstruct, cidx, qnbigl, qnbigr, percent=0):
-        """mp.py:651-888, single-state SVD branch without on-the-fly swapping."""
-        if isinstance(cstruct, list):
-            raise NotImplementedError("state-averaged update is outside the accelerated path")
+        """mp.py:651-888 without on-the-fly swapping: single-state SVD branch, or -- when `cstruct`
+        is a list -- the state-averaged branch (basis from the averaged reduced density matrix,
+        mp.py:780-838), which returns the rotated centre tensors of every state."""
         if self.compress_config.ofs is not None:
             raise NotImplementedError("on-the-fly swapping is outside the accelerated path")
         system = "L" if self.to_right else "R"
         if self.compress_config.bonddim_should_set:
             self.compress_config.set_bonddim(len(self) + 1)
-        Uset, SUset, qnlnew, Vset, SVset, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, self.qntot, system=system)
-        if self.to_right:
-            m_trunc = self.compress_config.compute_m_trunc(SUset, cidx[0], self.to_right)
-            ms, msdim, msqn, compms = select_basis(Uset, SUset, qnlnew, Vset, m_trunc, percent=percent)
-            ms = ms.contiguous().reshape(list(qnbigl.shape[:-1]) + [msdim])
-            compms = compms.transpose(0, 1).contiguous().reshape([msdim] + list(qnbigr.shape[:-1]))
+        multi = isinstance(cstruct, list)
+        rotated_c, averaged_ms = [], []
+        if not multi:
+            Uset, SUset, qnlnew, Vset, SVset, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, self.qntot, system=system)
+            if self.to_right:
+                m_trunc = self.compress_config.compute_m_trunc(SUset, cidx[0], self.to_right)
+                ms, msdim, msqn, compms = select_basis(Uset, SUset, qnlnew, Vset, m_trunc, percent=percent)
+                ms = ms.contiguous().reshape(list(qnbigl.shape[:-1]) + [msdim])
+                compms = compms.transpose(0, 1).contiguous().reshape([msdim] + list(qnbigr.shape[:-1]))
+            else:
+                m_trunc = self.compress_config.compute_m_trunc(SVset, cidx[-1], self.to_right)
+                ms, msdim, msqn, compms = select_basis(Vset, SVset, qnrnew, Uset, m_trunc, percent=percent)
+                ms = ms.transpose(0, 1).contiguous().reshape([msdim] + list(qnbigr.shape[:-1]))
+                compms = compms.contiguous().reshape(list(qnbigl.shape[:-1]) + [msdim])
         else:
-            m_trunc = self.compress_config.compute_m_trunc(SVset, cidx[-1], self.to_right)
-            ms, msdim, msqn, compms = select_basis(Vset, SVset, qnrnew, Uset, m_trunc, percent=percent)
-            ms = ms.transpose(0, 1).contiguous().reshape([msdim] + list(qnbigr.shape[:-1]))
-            compms = compms.contiguous().reshape(list(qnbigl.shape[:-1]) + [msdim])
+            nl = int(np.prod(qnbigl.shape[:-1]))
+            nr = int(np.prod(qnbigr.shape[:-1]))
+            mats = [asxp(c).reshape(nl, nr) for c in cstruct]
+            ddm = None
+            for m2 in mats:
+                if self.to_right:
+                    term = ops.matmul(m2, m2.transpose(0, 1).contiguous())       # sum over the right indices
+                else:
+                    term = ops.matmul(m2.transpose(0, 1).contiguous(), m2)       # sum over the left indices
+                ddm = term if ddm is None else ddm + term
+            ddm = ddm / len(mats)
+            Uset, Sset, qnnew = eigh_qn(ddm, qnbigl, qnbigr, self.qntot, system)
+            m_trunc = self.compress_config.compute_m_trunc(Sset, cidx[0] if self.to_right else cidx[-1],
+                                                           self.to_right)
+            ms, msdim, msqn, _ = select_basis(Uset, Sset, qnnew, None, m_trunc, percent=percent)
+            ms = ms.contiguous()
+            if self.to_right:
+                for m2 in mats:      # tensordot(ms, c) over the left indices: (msdim, right...)
+                    rotated_c.append(ops.matmul(ms.transpose(0, 1).contiguous(), m2)
+                                     .reshape([msdim] + list(qnbigr.shape[:-1])))
+                compms = rotated_c[0]
+                ms = ms.reshape(list(qnbigl.shape[:-1]) + [msdim])
+            else:
+                for m2 in mats:      # tensordot(c, ms) over the right indices: (left..., msdim)
+                    rotated_c.append(ops.matmul(m2, ms).reshape(list(qnbigl.shape[:-1]) + [msdim]))
+                compms = rotated_c[0]
+                ms = ms.transpose(0, 1).contiguous().reshape([msdim] + list(qnbigr.shape[:-1]))
         n = self.site_num
         if len(cidx) == 1:
             i = cidx[0]
             self._mp[i] = ms
             if self.to_right:
                 if i != n - 1:
+                    averaged_ms = [ops.tensordot1(c, self._mp[i + 1]) for c in rotated_c]
                     self._mp[i + 1] = ops.tensordot1(compms, self._mp[i + 1])
                     self.qn[i + 1] = msqn
                     self.qnidx = i + 1
                 else:
+                    averaged_ms = [ops.tensordot1(self._mp[i], c) for c in rotated_c]
                     self._mp[i] = ops.tensordot1(self._mp[i], compms)
                     self.qnidx = n - 1
             else:
                 if i != 0:
+                    averaged_ms = [ops.tensordot1(self._mp[i - 1], c) for c in rotated_c]
                     self._mp[i - 1] = ops.tensordot1(self._mp[i - 1], compms)
                     self.qn[i] = msqn
                     self.qnidx = i - 1
                 else:
+                    averaged_ms = [ops.tensordot1(c, self._mp[i]) for c in rotated_c]
                     self._mp[i] = ops.tensordot1(compms, self._mp[i])
                     self.qnidx = 0
         else:
@@ -348,8 +383,9 @@ class Mps:
             else:
                 self._mp[cidx[1]], self._mp[cidx[0]] = ms, compms
                 self.qnidx = cidx[0]
+            averaged_ms = rotated_c
             self.qn[cidx[1]] = msqn
-        return None
+        return averaged_ms if multi else None
 
     # ------------------------------------------------------------------ scalars
     def dot(self, other) -> complex:

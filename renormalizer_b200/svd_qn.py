@@ -198,6 +198,38 @@ def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray
     return u, su, qnl_new, v, sv, qnr_new
 
 
+def eigh_qn(dm, qnbigl, qnbigr, qntot, system):
+    """Block diagonalisation of the averaged reduced density matrix of the multi-state algorithm
+    (svd_qn.py:243-302).  The blocks are Hermitian positive semi-definite, so their Jacobi SVD is
+    their eigen-decomposition.  Returns (U device tensor, sqrt(eigenvalues) NumPy, new qn list)."""
+    assert system in ("L", "R")
+    qnbig, comp = (qnbigl, qnbigr) if system == "L" else (qnbigr, qnbigl)
+    qn_size = len(qntot)
+    localqn = qnbig.reshape(-1, qn_size)
+    compqn = comp.reshape(-1, qn_size)
+    n = len(localqn)
+    dm = asxp(dm).reshape(n, n)
+    dev = dm.device
+    us, ss, new_qn = [], [], []
+    for nl in _distinct_qn(localqn):
+        nr = qntot - nl
+        if np.sum(get_qn_mask(compqn, nr)) == 0:
+            continue
+        lset = np.where(get_qn_mask(localqn, nl))[0]
+        trivial = len(lset) == n
+        li = None if trivial else _idx(lset, dev)
+        block = dm if trivial else dm.index_select(0, li).index_select(1, li).contiguous()
+        bu, bs, bvh = ops.svd(block)
+        bu, _ = _orthonormal_null_vectors(bu, bs, bvh)
+        s2 = bs.cpu().numpy()
+        s2[s2 < 0] = 0
+        ss.append(np.sqrt(s2))
+        us.append(_scatter_rows(li, bu.contiguous(), n, trivial))
+        new_qn += [nl] * len(lset)
+    u = torch.cat(us, dim=1) if len(us) > 1 else us[0]
+    return u, np.concatenate(ss), new_qn
+
+
 def select_basis(vset, sset, qnlist, compset, Mmax, percent=0):
     """Select the retained basis and the complementary tensor (reference lib.py:265-335).
     Index selection runs on the host over the singular values; the column gathers run on device."""

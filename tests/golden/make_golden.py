@@ -227,6 +227,18 @@ def gen_holstein():
         out[f"{method}_nsweeps"] = np.array(len(micro))
         out[f"{method}_expectation"] = np.array(opt.expectation(mpo))
         dump_mp(f"{method}_opt", opt, out)
+    # state-averaged DMRG for the three lowest states (gs.py nroots > 1, mp.py:780-838)
+    for method in ("1site", "2site"):
+        m = mps.copy()
+        m.optimize_config.procedure = procedure
+        m.optimize_config.method = method
+        m.optimize_config.nroots = 3
+        np.random.seed(99)
+        energies, opts = optimize_mps(m, mpo)
+        out[f"sa_{method}_energies"] = np.array(energies)
+        out[f"sa_{method}_expectations"] = np.array([o.expectation(mpo) for o in opts])
+        ov = np.array([[abs(a.conj().dot(b)) for b in opts] for a in opts])
+        out[f"sa_{method}_overlaps"] = ov
     # omega targeting: (H - omega)^2 with two-layer environments (gs.py:106-111, test_gs.py:66-86)
     m = mps.copy()
     m.optimize_config.procedure = procedure

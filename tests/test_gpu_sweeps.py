@@ -373,3 +373,31 @@ def test_tdvp_ps2_golden(golden):
     assert mps.bond_dims == list(g["ps2_bond_dims"])
     refT = to_device_mps(load_oracle_mps(g, "ps2_mpsT"))
     assert abs(abs(refT.conj().dot(mps)) - 1) < T_TOL
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_dmrg_state_averaged_golden(golden, method):
+    """State-averaged DMRG (nroots = 3; gs.py nroots > 1, mp.py:780-838, svd_qn.py:243 eigh_qn) against
+    the reference run from the same start state and the reference's own acceptance values
+    (mps/tests/test_gs.py:66-86)."""
+    from renormalizer_b200.gs import optimize_mps
+    from renormalizer_b200.mpo import Mpo
+    g = golden("holstein")
+    mpo = Mpo(load_mpo(g))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    mps.optimize_config.procedure = [[int(a), float(b)] for a, b in g["procedure"]]
+    mps.optimize_config.method = method
+    mps.optimize_config.nroots = 3
+    np.random.seed(99)
+    energies, opts = optimize_mps(mps, mpo)
+    assert len(opts) == 3
+    got = np.array([o.expectation(mpo) for o in opts])
+    assert np.abs(np.array(energies[-1]) - g[f"sa_{method}_energies"][-1]).max() < 1e-8
+    assert np.abs(got - g[f"sa_{method}_expectations"]).max() < 1e-8
+    std = np.array([0.08401412, 0.08449771, 0.08449801]) + float(g["gs_zpe"])
+    assert np.allclose(got, std)
+    # the three states are orthonormal
+    for i in range(3):
+        for j in range(3):
+            ov = abs(opts[i].conj().dot(opts[j]))
+            assert abs(ov - (1.0 if i == j else 0.0)) < 1e-6

@@ -166,3 +166,21 @@ def test_tdvp_ps2_spin_boson(golden):
     ov = mps.conj().dot(ref) if hasattr(mps, "conj") else None
     if ov is not None:
         assert abs(abs(ov) - 1) < 1e-8
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_dmrg_state_averaged(golden, method):
+    """State-averaged DMRG for the three lowest states (gs.py nroots > 1, mp.py:780-838, eigh_qn
+    svd_qn.py:243-302): every sweep energy of every root reproduces the reference run."""
+    g = golden("holstein")
+    mpo = load_mpo(g)
+    mps = load_oracle_mps(g, "mps0")
+    proc = [(int(a), float(b)) for a, b in g["procedure"]]
+    np.random.seed(99)
+    e, opts = optimize_mps(mps, mpo, proc, method=method, nroots=3)
+    assert np.abs(np.array(e) - g[f"sa_{method}_energies"]).max() < 1e-12
+    got = np.array([o.expectation(mpo) for o in opts])
+    assert np.abs(got - g[f"sa_{method}_expectations"]).max() < 1e-12
+    # the reference's own acceptance values (mps/tests/test_gs.py:80)
+    std = np.array([0.08401412, 0.08449771, 0.08449801]) + float(g["gs_zpe"])
+    assert np.allclose(got, std)
