@@ -147,7 +147,8 @@ class Mps:
         e0 = np.eye(1)
         for a, b in zip(self.sites, other.sites):
             e0 = np.tensordot(e0, b, 1)
-            e0 = np.tensordot(e0, a.conj(), ([0, 1], [0, 1])).T
+            phys = list(range(a.ndim - 1))       # left bond + physical (+ ancilla) indices
+            e0 = np.tensordot(e0, a.conj(), (phys, phys)).T
         return complex(e0[0, 0])
 
     @property
@@ -301,6 +302,15 @@ def _scatter(c, mask):
     return out
 
 
+class StackedMpo:
+    """Sum of Hamiltonians kept as separate MPOs.  Reference: renormalizer/mps/mpo.py:483-494;
+    consumed by gs.py:113-114 (one Environ per member) and gs.py:226-241, 321-343, 499-502
+    (H_eff and its diagonal are the sums over the members)."""
+
+    def __init__(self, mpos):
+        self.mpos = list(mpos)
+
+
 def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, stats=None, nroots=1):
     """One DMRG sweep over all sites.  Reference: renormalizer/mps/gs.py:174-304 (omega=None,
     algo="davidson"; nroots > 1 is the state-averaged algorithm).  Returns (micro results
@@ -320,21 +330,25 @@ def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, s
             lidx, cidx, ridx = imps - 1, [imps, imps + 1], imps + 2
         else:
             lidx, cidx, ridx = imps - 2, [imps - 1, imps], imps + 1
-        ltensor = environ.get_lr("L", lidx, mps, mpo, lmethod)
-        rtensor = environ.get_lr("R", ridx, mps, mpo, rmethod)
+        members = mpo.mpos if isinstance(mpo, StackedMpo) else [mpo]
+        environs = environ if isinstance(environ, list) else [environ]
+        lts = [env_i.get_lr("L", lidx, mps, op_i, lmethod) for env_i, op_i in zip(environs, members)]
+        rts = [env_i.get_lr("R", ridx, mps, op_i, rmethod) for env_i, op_i in zip(environs, members)]
+        cmos = [[op_i[i] for i in cidx] for op_i in members]
         qnbigl, qnbigr, qnmat = mps.big_qn(cidx)
         mask = get_qn_mask(qnmat, mps.qntot)
         cshape = mask.shape
-        cmo = [mpo[i] for i in cidx]
         if np.prod(cshape) < 1000:
             # direct diagonalisation.  Reference: gs.py:307-407
-            if len(cidx) == 1:
-                ham = np.einsum("abc,bdef,lfk->adlcek", ltensor, cmo[0], rtensor, optimize=True)
-                ham = ham[:, :, :, mask][mask, :]
-            else:
-                ham = np.einsum("abc,bdef,fghj,ljk->adglcehk", ltensor, cmo[0], cmo[1], rtensor,
-                                optimize=True)
-                ham = ham[:, :, :, :, mask][mask, :]
+            ham = 0
+            for ltensor, rtensor, cmo in zip(lts, rts, cmos):
+                if len(cidx) == 1:
+                    h_i = np.einsum("abc,bdef,lfk->adlcek", ltensor, cmo[0], rtensor, optimize=True)
+                    ham = ham + h_i[:, :, :, mask][mask, :]
+                else:
+                    h_i = np.einsum("abc,bdef,fghj,ljk->adglcehk", ltensor, cmo[0], cmo[1], rtensor,
+                                    optimize=True)
+                    ham = ham + h_i[:, :, :, :, mask][mask, :]
             w, vec = scipy.linalg.eigh(ham)
             if nroots == 1:
                 e, c = w[0], _sign_fix(vec[:, 0])
@@ -362,12 +376,13 @@ def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, s
                     cguess.append(raw[mask])
                 guess_dim = int(np.sum(mask))
                 cguess.extend([np.random.rand(guess_dim) - 0.5 for _ in range(len(cguess), nroots)])
-            hdiag = hop_diag(ltensor, rtensor, cmo)[mask]
+            hdiag = sum(hop_diag(l, r, c) for l, r, c in zip(lts, rts, cmos))[mask]
             count = [0]
 
             def hop(x):
                 count[0] += 1
-                return hop_apply(ltensor, rtensor, cmo, _scatter(x, mask))[mask]
+                xs = _scatter(x, mask)
+                return sum(hop_apply(l, r, c, xs) for l, r, c in zip(lts, rts, cmos))[mask]
 
             def precond(x, e, *args):
                 return x / (hdiag - e + 1e-4)
@@ -409,7 +424,10 @@ def optimize_mps(mps, mpo, procedure, method="2site", e_rtol=1e-6, e_atol=1e-8, 
     else:
         mps.ensure_left_canonical()
         env = "L"
-    environ = Environ(mps, mpo, env)
+    if isinstance(mpo, StackedMpo):
+        environ = [Environ(mps, item, env) for item in mpo.mpos]       # gs.py:113-114
+    else:
+        environ = Environ(mps, mpo, env)
     macro = []
     opt_idx = None
     res_mps = None

@@ -24,7 +24,9 @@ def optimize_mps(mps, mpo, omega: float = None):
         # gs.py:106-111: the variational function (H - omega)^2.  The reference keeps two MPO layers
         # in 4-index environments; here the same operator is ONE MPO whose bonds are the merged
         # pairs (mpo.squared), so environments, H_eff and the sweep run on the one-layer kernels.
-        from .mpo import Mpo
+        from .mpo import Mpo, StackedMpo
+        if isinstance(mpo, StackedMpo):
+            raise NotImplementedError("StackedMPO + omega is not implemented yet")     # as gs.py:107-108
         shifted = mpo.add(Mpo.identity_like(mpo).scale(-omega))
         mpo = shifted.squared()
     assert mps.optimize_config.method in ["2site", "1site"]
@@ -35,7 +37,11 @@ def optimize_mps(mps, mpo, omega: float = None):
         mps.ensure_left_canonical()
         env = "L"
     compress_config_bk = mps.compress_config
-    environ = Environ(mps, mpo, env)
+    from .mpo import StackedMpo as _Stacked
+    if isinstance(mpo, _Stacked):
+        environ = [Environ(mps, item, env) for item in mpo.mpos]      # gs.py:113-114
+    else:
+        environ = Environ(mps, mpo, env)
     macro_iteration_result = []
     opt_e_idx = None
     res_mps = None
@@ -92,12 +98,20 @@ def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
             lidx, cidx, ridx = imps - 1, [imps, imps + 1], imps + 2
         else:
             lidx, cidx, ridx = imps - 2, [imps - 1, imps], imps + 1
-        ltensor = environ.GetLR("L", lidx, mps, mpo, itensor=None, method=lmethod)
-        rtensor = environ.GetLR("R", ridx, mps, mpo, itensor=None, method=rmethod)
+        stacked = isinstance(environ, list)
+        if stacked:      # gs.py:226-228, 239-240: one environment / centre MPO list per member
+            ltensor = [env_i.GetLR("L", lidx, mps, op_i, itensor=None, method=lmethod)
+                       for env_i, op_i in zip(environ, mpo.mpos)]
+            rtensor = [env_i.GetLR("R", ridx, mps, op_i, itensor=None, method=rmethod)
+                       for env_i, op_i in zip(environ, mpo.mpos)]
+            cmo = [[op_i[idx] for idx in cidx] for op_i in mpo.mpos]
+        else:
+            ltensor = environ.GetLR("L", lidx, mps, mpo, itensor=None, method=lmethod)
+            rtensor = environ.GetLR("R", ridx, mps, mpo, itensor=None, method=rmethod)
+            cmo = [mpo[idx] for idx in cidx]
         qnbigl, qnbigr, qnmat = mps._get_big_qn(cidx)
         qn_mask = get_qn_mask(qnmat, mps.qntot)
         cshape = qn_mask.shape
-        cmo = [mpo[idx] for idx in cidx]
         use_direct_eigh = np.prod(cshape) < 1000 or mps.optimize_config.algo == "direct"
         if use_direct_eigh:
             e, cstruct = eigh_direct(mps, qn_mask, ltensor, rtensor, cmo)
@@ -146,18 +160,24 @@ def eigh_direct(mps, qn_mask, ltensor, rtensor, cmo):
     """gs.py:307-407: tiny centre tensors are diagonalised densely.  The dense H_eff is assembled
     by applying the device H_eff to the unit vectors of the symmetry-allowed subspace."""
     cshape = qn_mask.shape
-    dtype = torch.complex128 if (ltensor.is_complex() or rtensor.is_complex()) else torch.float64
-    hop = hop_expr_dtype(ltensor, rtensor, cmo, cshape, dtype)
+    if not isinstance(ltensor, list):
+        ltensor, rtensor, cmo = [ltensor], [rtensor], [cmo]
+    dtype = torch.complex128 if any(t.is_complex() for t in ltensor + rtensor) else torch.float64
+    hops = [hop_expr_dtype(l, r, c, cshape, dtype) for l, r, c in zip(ltensor, rtensor, cmo)]
     idx = np.nonzero(qn_mask.reshape(-1))[0]
     nfull = int(np.prod(cshape))
-    dev = ltensor.device
+    dev = ltensor[0].device
     cols = []
     sel = torch.from_numpy(idx).to(dev)
     for i in idx:
         x = torch.zeros(nfull, dtype=dtype, device=dev)
         x[i] = 1
-        cols.append(hop(x.reshape(cshape)).reshape(-1).index_select(0, sel))
-    hop.close()
+        y = hops[0](x.reshape(cshape))
+        for h in hops[1:]:
+            y = y + h(x.reshape(cshape))
+        cols.append(y.reshape(-1).index_select(0, sel))
+    for h in hops:
+        h.close()
     ham = asnumpy(torch.stack(cols, dim=1)) * mps.optimize_config.inverse
     w, v = scipy.linalg.eigh(ham)
 
@@ -192,18 +212,29 @@ def eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess):
     if mps.optimize_config.algo != "davidson":
         raise NotImplementedError("only the Davidson eigensolver is accelerated")
     cshape = qn_mask.shape
-    cplx = ltensor.is_complex() or rtensor.is_complex() or any(g.is_complex() for g in raw_cguess)
+    if not isinstance(ltensor, list):
+        ltensor, rtensor, cmo = [ltensor], [rtensor], [cmo]
+    cplx = any(t.is_complex() for t in ltensor + rtensor) or any(g.is_complex() for g in raw_cguess)
     dtype = torch.complex128 if cplx else torch.float64
-    dev = ltensor.device
+    dev = ltensor[0].device
     mask = torch.from_numpy(qn_mask.reshape(-1)).to(dev)
     maskf = mask.to(dtype)
-    hdiag = (_hdiag(ltensor, rtensor, cmo).real.reshape(-1) * inverse)
-    hop = hop_expr_dtype(ltensor, rtensor, cmo, cshape, dtype)
+    # a stacked Hamiltonian is the sum of its members' effective Hamiltonians (gs.py:499-502)
+    hdiag = sum(_hdiag(l, r, c).real.reshape(-1) for l, r, c in zip(ltensor, rtensor, cmo)) * inverse
+    hops = [hop_expr_dtype(l, r, c, cshape, dtype) for l, r, c in zip(ltensor, rtensor, cmo)]
     count = [0]
+
+    class _Sum:
+        def close(self):
+            for h in hops:
+                h.close()
+    hop = _Sum()
 
     def aop(x):
         count[0] += 1
-        y = hop(x.reshape(cshape)).reshape(-1)
+        y = hops[0](x.reshape(cshape)).reshape(-1)
+        for h in hops[1:]:
+            y = y + h(x.reshape(cshape)).reshape(-1)
         y *= maskf
         if inverse != 1.0:
             y *= inverse

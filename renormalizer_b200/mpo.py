@@ -79,6 +79,15 @@ class Mpo:
         return sum(s.array.nbytes for s in self._sites)
 
 
+class StackedMpo:
+    """Sum of Hamiltonians kept as separate MPOs (block-diagonal sparse form, mpo.py:483-494):
+    `optimize_mps(mps, StackedMpo([mpo1, mpo2, ...]))` sums the effective Hamiltonians of the
+    members at every site."""
+
+    def __init__(self, mpos):
+        self.mpos = list(mpos)
+
+
 def two_layer_site(upper, lower):
     """W2[(b,c), up, down, (g,i)] = sum_f upper[b, up, f, g] lower[c, f, down, i]."""
     b, d, _, g = upper.shape

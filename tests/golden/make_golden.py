@@ -316,8 +316,189 @@ def gen_sbm():
     np.savez_compressed(os.path.join(HERE, "sbm.npz"), **out)
 
 
+def gen_stacked():
+    """StackedMpo (mps/mpo.py:483-494, gs.py:113-114,226-241): mps/tests/test_gs.py:148-158
+    (H + H as two stacked members) and a genuinely split Hamiltonian (on-site part + hopping)."""
+    from renormalizer.mps.gs import construct_mps_mpo, optimize_mps
+    from renormalizer.mps import Mpo, StackedMpo
+    from renormalizer.model import Model
+    from renormalizer.tests.parameter import holstein_model
+    out = {}
+    procedure = [[10, 0.4], [20, 0.2], [30, 0.1], [40, 0], [40, 0]]
+    np.random.seed(2026)
+    model = holstein_model.switch_scheme(1)
+    mps, mpo = construct_mps_mpo(model, procedure[0][0], 1)
+    dump_mp("mpo", mpo, out)
+    dump_mp("mps0", mps, out)
+    dump_mps_meta("mps0", mps, out)
+    out["procedure"] = np.array(procedure, dtype=float)
+    for method in ("1site", "2site"):
+        m = mps.copy()
+        m.optimize_config.procedure = procedure
+        m.optimize_config.method = method
+        np.random.seed(99)
+        e1, _ = optimize_mps(m.copy(), mpo)
+        np.random.seed(99)
+        e2, opt2 = optimize_mps(m.copy(), StackedMpo([mpo, mpo]))
+        out[f"{method}_single_energies"] = np.array(e1)
+        out[f"{method}_double_energies"] = np.array(e2)
+    # split Hamiltonian: terms touching one dof / terms touching several
+    terms_a = [t for t in model.ham_terms if len(t.dofs) == 1]
+    terms_b = [t for t in model.ham_terms if len(t.dofs) != 1]
+    mpo_a = Mpo(Model(model.basis, terms_a))
+    mpo_b = Mpo(Model(model.basis, terms_b))
+    dump_mp("mpo_a", mpo_a, out)
+    dump_mp("mpo_b", mpo_b, out)
+    m = mps.copy()
+    m.optimize_config.procedure = procedure
+    m.optimize_config.method = "2site"
+    np.random.seed(99)
+    e3, opt3 = optimize_mps(m.copy(), StackedMpo([mpo_a, mpo_b]))
+    out["split_energies"] = np.array(e3)
+    out["split_expectation"] = np.array(opt3.expectation(mpo))
+    np.savez_compressed(os.path.join(HERE, "stacked.npz"), **out)
+
+
+def gen_qc():
+    """Ab initio DMRG on the reference's own H6 / STO-3G FCIDUMP (mps/tests/test_gs.py:103-145,
+    the small sibling of example/h2o_qc.py): two conserved quantum numbers (alpha, beta electron
+    counts), M = 30, two-site sweeps.  fci_e is the reference test's acceptance value."""
+    from renormalizer.mps.gs import optimize_mps
+    from renormalizer.mps import Mpo, Mps
+    from renormalizer.model import Model, h_qc
+    out = {}
+    ref_dir = "/root/reference/renormalizer/mps/tests"
+    h1e, h2e, nuc = h_qc.read_fcidump(os.path.join(ref_dir, "H6.txt"), 6)
+    basis, ham_terms = h_qc.qc_model(h1e, h2e)
+    model = Model(basis, ham_terms)
+    mpo = Mpo(model)
+    nelec = [3, 3]
+    M = 30
+    procedure = [[M, 0.4], [M, 0.2], [M, 0.1], [M, 0], [M, 0], [M, 0], [M, 0]]
+    np.random.seed(2023)
+    mps = Mps.random(model, nelec, M, percent=1.0)
+    hf = Mps.hartree_product_state(model, {i: 1 for i in range(sum(nelec))})
+    mps = mps.scale(1e-8) + hf
+    dump_mp("mpo", mpo, out)
+    dump_mp("mps0", mps, out)
+    dump_mps_meta("mps0", mps, out)
+    out["procedure"] = np.array(procedure, dtype=float)
+    out["fci_e"] = np.array(-3.23747673055271 - nuc)
+    out["hf_e"] = np.array(mps.expectation(mpo))
+    m = mps.copy()
+    m.optimize_config.procedure = procedure
+    m.optimize_config.method = "2site"
+    np.random.seed(99)
+    energies, opt = optimize_mps(m, mpo)
+    out["energies"] = np.array(energies)
+    out["expectation"] = np.array(opt.expectation(mpo))
+    out["bond_dims"] = np.array(opt.bond_dims)
+    np.savez_compressed(os.path.join(HERE, "qc_h6.npz"), **out)
+
+
+def gen_exciton():
+    """FMO-like exciton dynamics (example/fmo.py in miniature): HolsteinModel with a full
+    long-range J matrix, one conserved exciton, TDVP-PS at fixed bond dimension -- the
+    quantum-number-blocked TDVP case; plus the same evolution of a density operator (MpDm,
+    ancilla index riding along: hop_expr.py:83-117) started from the maximally entangled state."""
+    from renormalizer.model import Phonon, Mol, HolsteinModel
+    from renormalizer.model.op import Op
+    from renormalizer.mps import Mps, Mpo, MpDm
+    from renormalizer.utils import Quantity, CompressConfig, EvolveConfig, EvolveMethod, \
+        CompressCriteria
+    out = {}
+    jm = np.array([[0.31, -0.098, 0.006, -0.006],
+                   [-0.098, 0.23, 0.030, 0.007],
+                   [0.006, 0.030, 0.0, -0.059],
+                   [-0.006, 0.007, -0.059, 0.18]])
+    phs = [Phonon.simple_phonon(Quantity(o), Quantity(d), 4)
+           for o, d in zip([0.12, 0.25], [1.1, 0.6])]
+    mols = [Mol(Quantity(e), phs) for e in np.diag(jm)]
+    model = HolsteinModel(mols, jm)
+    mpo = Mpo(model)
+    np.random.seed(777)
+    gs = Mps.ground_state(model, False)
+    mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ gs
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    mps = mps.expand_bond_dimension(mpo, include_ex=False)
+    dump_mp("mpo", mpo, out)
+    dump_mp("mps0", mps, out)
+    dump_mps_meta("mps0", mps, out)
+    out["mps0_coeff"] = np.array(mps.coeff)
+    occ_ops = [Mpo(model, Op(r"a^\dagger a", i)) for i in range(len(mols))]
+    for i, o in enumerate(occ_ops):
+        dump_mp(f"occ{i}", o, out)
+    out["nmol"] = np.array(len(mols))
+    dt, nsteps = 2.0, 5
+    occ = [[mps.expectation(o) for o in occ_ops]]
+    en = [mps.expectation(mpo)]
+    for i in range(nsteps):
+        mps = mps.evolve(mpo, dt)
+        occ.append([mps.expectation(o) for o in occ_ops])
+        en.append(mps.expectation(mpo))
+    out["dt"] = np.array(dt)
+    out["nsteps"] = np.array(nsteps)
+    out["occ_t"] = np.array(occ)
+    out["energy_t"] = np.array(en)
+    out["bond_dims"] = np.array(mps.bond_dims)
+    dump_mp("mpsT", mps, out)
+    # density operator: infinite-temperature state with one exciton, real-time TDVP-PS
+    np.random.seed(778)
+    dm = MpDm.max_entangled_ex(model)
+    dm.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=8)
+    dm.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    dm = dm.expand_bond_dimension(mpo, include_ex=False)
+    dump_mp("dm0", dm, out)
+    dump_mps_meta("dm0", dm, out)
+    out["dm0_coeff"] = np.array(dm.coeff)
+    docc = [[dm.expectation(o) for o in occ_ops]]
+    den = [dm.expectation(mpo)]
+    for i in range(3):
+        dm = dm.evolve(mpo, dt)
+        docc.append([dm.expectation(o) for o in occ_ops])
+        den.append(dm.expectation(mpo))
+    out["dm_nsteps"] = np.array(3)
+    out["dm_occ_t"] = np.array(docc)
+    out["dm_energy_t"] = np.array(den)
+    dump_mp("dmT", dm, out)
+    np.savez_compressed(os.path.join(HERE, "exciton.npz"), **out)
+
+
+def gen_two_spin():
+    """The README quickstart (README.md:36-58): two half spins, sigma+ sigma- exchange, 10 steps
+    of Mps.evolve with dt = 0.05, <Z_0> after every step -- with the default propagate-and-
+    compress RK4 integrator (the README's own call) and with TDVP-PS."""
+    from renormalizer import Mps, Mpo, Op, Model, BasisHalfSpin
+    from renormalizer.utils import EvolveConfig, EvolveMethod
+    out = {}
+    basis = [BasisHalfSpin(0), BasisHalfSpin(1)]
+    ham_terms = Op("sigma_+ sigma_-", [0, 1]) + Op("sigma_+ sigma_-", [1, 0])
+    model = Model(basis, ham_terms)
+    mpo = Mpo(model)
+    z_op = Mpo(model, Op("Z", 0))
+    dump_mp("mpo", mpo, out)
+    dump_mp("z", z_op, out)
+    for tag, cfg in (("pc", None), ("ps", EvolveConfig(EvolveMethod.tdvp_ps)),
+                     ("ps2", EvolveConfig(EvolveMethod.tdvp_ps2))):
+        mps = Mps.hartree_product_state(model, condition={0: [0, 1]})
+        if cfg is not None:
+            mps.evolve_config = cfg
+        if tag == "pc":
+            dump_mp("mps0", mps, out)
+            dump_mps_meta("mps0", mps, out)
+        zs = []
+        for i in range(10):
+            mps = mps.evolve(mpo, 0.05)
+            zs.append(mps.expectation(z_op))
+        out[f"{tag}_z_t"] = np.array(zs)
+        out[f"{tag}_bond_dims"] = np.array(mps.bond_dims)
+    np.savez_compressed(os.path.join(HERE, "two_spin.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm"]
+    which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm", "stacked", "qc", "exciton",
+                             "two_spin"]
     for name in which:
         print("generating", name, flush=True)
         globals()["gen_" + name]()

@@ -401,3 +401,153 @@ def test_dmrg_state_averaged_golden(golden, method):
         for j in range(3):
             ov = abs(opts[i].conj().dot(opts[j]))
             assert abs(ov - (1.0 if i == j else 0.0)) < 1e-6
+
+
+# ---------------------------------------------------------------- BASELINE.json parity cases
+def _device_dmrg(g, mpo, method, **cfg):
+    from renormalizer_b200.gs import optimize_mps
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    mps.optimize_config.procedure = [[int(a), float(b)] for a, b in g["procedure"]]
+    mps.optimize_config.method = method
+    for k, v in cfg.items():
+        setattr(mps.optimize_config, k, v)
+    np.random.seed(99)
+    return optimize_mps(mps, mpo)
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_dmrg_stacked_mpo_golden(golden, method):
+    """optimize_mps(mps, StackedMpo([H, H])) (mpo.py:483-494, mps/tests/test_gs.py:148-158): twice
+    the single-MPO energies, and the reference's own stacked trajectory."""
+    from renormalizer_b200.mpo import Mpo, StackedMpo
+    g = golden("stacked")
+    mpo = Mpo(load_mpo(g))
+    e2, _ = _device_dmrg(g, StackedMpo([mpo, mpo]), method)
+    ref = g[f"{method}_double_energies"]
+    assert len(e2) == len(ref)
+    assert abs(e2[-1] - ref[-1]) < 1e-9
+    assert np.abs(np.array(e2) - ref).max() < 1e-6
+    assert np.abs(np.array(e2) - 2 * g[f"{method}_single_energies"]).max() < 1e-6
+
+
+def test_dmrg_stacked_split_hamiltonian_golden(golden):
+    """A Hamiltonian split into its on-site and its coupling part, each member an MPO of its own."""
+    from renormalizer_b200.mpo import Mpo, StackedMpo
+    g = golden("stacked")
+    stacked = StackedMpo([Mpo(load_mpo(g, "mpo_a")), Mpo(load_mpo(g, "mpo_b"))])
+    e, opt = _device_dmrg(g, stacked, "2site")
+    assert abs(e[-1] - g["split_energies"][-1]) < 1e-9
+    assert np.abs(np.array(e) - g["split_energies"]).max() < 1e-6
+    assert abs(opt.expectation(Mpo(load_mpo(g))) - float(g["split_expectation"])) < 1e-9
+
+
+def test_dmrg_stacked_omega_raises(golden):
+    from renormalizer_b200.mpo import Mpo, StackedMpo
+    from renormalizer_b200.gs import optimize_mps
+    g = golden("stacked")
+    mpo = Mpo(load_mpo(g))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    with pytest.raises(NotImplementedError):
+        optimize_mps(mps, StackedMpo([mpo, mpo]), omega=0.1)
+
+
+def _check_qc(g, mpo, e, opt):
+    ref = g["energies"]
+    assert len(e) == len(ref)
+    # the start state is a Hartree-Fock product state plus 1e-8 noise: the first two sweeps grow
+    # the bonds out of null-space completions (arbitrary in LAPACK and here), so they are compared
+    # loosely; from the third sweep on the trajectory is the reference's
+    e, ref = np.array(e), np.array(ref)
+    assert np.abs(e[:2] - ref[:2]).max() < 1e-2
+    assert np.abs(e[2:] - ref[2:]).max() < 1e-6
+    assert abs(e[-1] - ref[-1]) < 1e-9
+    assert abs(opt.expectation(mpo) - float(g["expectation"])) < 1e-8
+    assert np.allclose(min(e), float(g["fci_e"]), atol=5e-3)           # test_gs.py:145
+    assert max(opt.bond_dims) <= 30
+
+
+def test_dmrg_qc_h6_golden(golden):
+    """BASELINE configs[4] in miniature: ab initio DMRG on the reference's H6 FCIDUMP
+    (mps/tests/test_gs.py:103-145) -- two conserved quantum numbers, M = 30, two-site sweeps."""
+    from renormalizer_b200.mpo import Mpo
+    g = golden("qc_h6")
+    mpo = Mpo(load_mpo(g))
+    e, opt = _device_dmrg(g, mpo, "2site")
+    _check_qc(g, mpo, e, opt)
+
+
+def test_dmrg_qc_h6_golden_tensor_path(golden, tensor_path):
+    """The same run with every contraction on the tcgen05 digit path."""
+    from renormalizer_b200.mpo import Mpo
+    g = golden("qc_h6")
+    mpo = Mpo(load_mpo(g))
+    e, opt = _device_dmrg(g, mpo, "2site")
+    _check_qc(g, mpo, e, opt)
+
+
+def _device_mps_with_coeff(g, prefix):
+    om = load_oracle_mps(g, prefix, meta=prefix)
+    from renormalizer_b200.mps import Mps
+    return Mps(om.sites, om.qn, om.sigmaqn, om.qntot, om.qnidx, om.to_right,
+               coeff=complex(g[prefix + "_coeff"]))
+
+
+def _exciton_run(g, mps, nsteps):
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig, EvolveMethod
+    from renormalizer_b200.mpo import Mpo
+    mpo = Mpo(load_mpo(g))
+    occ = [Mpo(load_mpo(g, f"occ{i}")) for i in range(int(g["nmol"]))]
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    occs, es = [[mps.expectation(o) for o in occ]], [mps.expectation(mpo)]
+    for _ in range(nsteps):
+        mps = mps.evolve(mpo, float(g["dt"]))
+        occs.append([mps.expectation(o) for o in occ])
+        es.append(mps.expectation(mpo))
+    return mps, np.array(occs), np.array(es)
+
+
+def test_tdvp_ps_exciton_golden(golden):
+    """BASELINE configs[3] in miniature (example/fmo.py): long-range J matrix, one conserved
+    exciton -- the quantum-number-blocked TDVP-PS case."""
+    g = golden("exciton")
+    mps, occs, es = _exciton_run(g, _device_mps_with_coeff(g, "mps0"), int(g["nsteps"]))
+    assert np.abs(occs - g["occ_t"]).max() < E_TOL
+    assert np.abs(es - g["energy_t"]).max() < E_TOL
+    assert abs(occs[-1].sum() - 1) < E_TOL
+    assert mps.bond_dims == list(g["bond_dims"])
+    refT = to_device_mps(load_oracle_mps(g, "mpsT"))
+    assert abs(abs(refT.conj().dot(mps)) - 1) < T_TOL
+
+
+def test_tdvp_ps_density_operator_golden(golden):
+    """The same evolution for a density operator (MpDm: every site carries an ancilla index,
+    hop_expr.py:83-117, lib.py:213-262) started from the maximally entangled one-exciton state."""
+    g = golden("exciton")
+    dm0 = _device_mps_with_coeff(g, "dm0")
+    assert dm0[0].ndim == 4
+    dm, occs, es = _exciton_run(g, dm0, int(g["dm_nsteps"]))
+    assert np.abs(occs - g["dm_occ_t"]).max() < E_TOL
+    assert np.abs(es - g["dm_energy_t"]).max() < E_TOL
+    ref = to_device_mps(load_oracle_mps(g, "dmT", meta="dm0"))
+    assert abs(abs(ref.conj().dot(dm)) - 1) < T_TOL
+
+
+def test_two_spin_quickstart_golden(golden):
+    """BASELINE configs[0], the README quickstart (README.md:36-58) through Mps.evolve: the
+    two-site sweep integrator reproduces the reference's tdvp_ps2 run, the values the README's
+    own (propagate-and-compress) loop prints to that integrator's error, and -cos(2t)."""
+    from renormalizer_b200.configs import EvolveConfig, EvolveMethod
+    from renormalizer_b200.mpo import Mpo
+    g = golden("two_spin")
+    mpo, z = Mpo(load_mpo(g)), Mpo(load_mpo(g, "z"))
+    mps = to_device_mps(load_oracle_mps(g, "mps0"))
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps2)
+    zs = []
+    for _ in range(10):
+        mps = mps.evolve(mpo, 0.05)
+        zs.append(mps.expectation(z))
+    assert np.abs(np.array(zs) - g["ps2_z_t"]).max() < E_TOL
+    assert np.abs(np.array(zs) - g["pc_z_t"]).max() < 1e-6
+    assert np.abs(np.array(zs) + np.cos(2 * 0.05 * np.arange(1, 11))).max() < 1e-6
+    assert mps.bond_dims == list(g["ps2_bond_dims"])

@@ -184,3 +184,100 @@ def test_dmrg_state_averaged(golden, method):
     # the reference's own acceptance values (mps/tests/test_gs.py:80)
     std = np.array([0.08401412, 0.08449771, 0.08449801]) + float(g["gs_zpe"])
     assert np.allclose(got, std)
+
+
+# ---------------------------------------------------------------- BASELINE.json parity cases
+def _run_oracle_dmrg(g, mpo, method, prefix="mps0", **kw):
+    from oracle.sweep import optimize_mps
+    mps = load_oracle_mps(g, prefix)
+    np.random.seed(99)
+    return optimize_mps(mps, mpo, [tuple(p) for p in g["procedure"]], method=method, **kw)
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_dmrg_stacked_mpo(golden, method):
+    """StackedMpo (mpo.py:483-494; mps/tests/test_gs.py:148-158): H + H as two members gives twice
+    the energies; the trajectory reproduces the reference's."""
+    from oracle.sweep import StackedMpo
+    g = golden("stacked")
+    mpo = load_mpo(g)
+    e2, _ = _run_oracle_dmrg(g, StackedMpo([mpo, mpo]), method)
+    assert np.abs(np.array(e2) - g[f"{method}_double_energies"]).max() < 1e-12
+    assert np.abs(np.array(e2) - 2 * g[f"{method}_single_energies"]).max() < 1e-8   # test_gs.py:158
+
+
+def test_dmrg_stacked_split_hamiltonian(golden):
+    from oracle.sweep import StackedMpo
+    g = golden("stacked")
+    e, opt = _run_oracle_dmrg(g, StackedMpo([load_mpo(g, "mpo_a"), load_mpo(g, "mpo_b")]), "2site")
+    assert np.abs(np.array(e) - g["split_energies"]).max() < 1e-12
+    assert abs(opt.expectation(load_mpo(g)) - float(g["split_expectation"])) < 1e-12
+
+
+def test_dmrg_qc_h6_two_quantum_numbers(golden):
+    """BASELINE configs[4] in miniature: ab initio DMRG from the reference's H6 FCIDUMP
+    (mps/tests/test_gs.py:103-145), two conserved quantum numbers, M = 30."""
+    g = golden("qc_h6")
+    mpo = load_mpo(g)
+    assert load_oracle_mps(g, "mps0").qntot.shape == (2,)
+    e, opt = _run_oracle_dmrg(g, mpo, "2site")
+    assert np.abs(np.array(e) - g["energies"]).max() < 1e-10
+    assert abs(opt.expectation(mpo) - float(g["expectation"])) < 1e-10
+    assert np.allclose(min(e), float(g["fci_e"]), atol=5e-3)                          # test_gs.py:145
+
+
+def _load_with_coeff(g, prefix):
+    mps = load_oracle_mps(g, prefix, meta=prefix)
+    mps.coeff = complex(g[prefix + "_coeff"])
+    return mps
+
+
+def test_tdvp_ps_exciton_qn_blocked(golden):
+    """BASELINE configs[3] in miniature (example/fmo.py): long-range J, one conserved exciton."""
+    g = golden("exciton")
+    mpo = load_mpo(g)
+    occ = [load_mpo(g, f"occ{i}") for i in range(int(g["nmol"]))]
+    mps = _load_with_coeff(g, "mps0")
+    occs, es = [[mps.expectation(o) for o in occ]], [mps.expectation(mpo)]
+    for _ in range(int(g["nsteps"])):
+        mps = evolve_tdvp_ps(mps, mpo, float(g["dt"]))
+        occs.append([mps.expectation(o) for o in occ])
+        es.append(mps.expectation(mpo))
+    assert np.abs(np.array(occs) - g["occ_t"]).max() < 1e-10
+    assert np.abs(np.array(es) - g["energy_t"]).max() < 1e-10
+    assert abs(np.sum(occs[-1]) - 1) < 1e-10
+    assert mps.bond_dims == list(g["bond_dims"])
+
+
+def test_tdvp_ps_density_operator(golden):
+    """MpDm sites carry an ancilla index (hop_expr.py:83-117, lib.py:213-262)."""
+    g = golden("exciton")
+    mpo = load_mpo(g)
+    occ = [load_mpo(g, f"occ{i}") for i in range(int(g["nmol"]))]
+    dm = _load_with_coeff(g, "dm0")
+    assert dm.sites[0].ndim == 4
+    occs, es = [[dm.expectation(o) for o in occ]], [dm.expectation(mpo)]
+    for _ in range(int(g["dm_nsteps"])):
+        dm = evolve_tdvp_ps(dm, mpo, float(g["dt"]))
+        occs.append([dm.expectation(o) for o in occ])
+        es.append(dm.expectation(mpo))
+    assert np.abs(np.array(occs) - g["dm_occ_t"]).max() < 1e-10
+    assert np.abs(np.array(es) - g["dm_energy_t"]).max() < 1e-10
+
+
+def test_two_spin_quickstart(golden):
+    """BASELINE configs[0], the README quickstart (README.md:36-58): two half spins, 10 steps of
+    dt = 0.05.  The README's own integrator (propagate-and-compress RK4) is outside the sweep
+    path; the two-site TDVP sweep reproduces the reference's tdvp_ps2 run to 1e-12, the README's
+    printed values to the RK4 error, and both follow -cos(2t)."""
+    from oracle.sweep import evolve_tdvp_ps2
+    g = golden("two_spin")
+    mpo, z = load_mpo(g), load_mpo(g, "z")
+    mps = load_oracle_mps(g, "mps0")
+    zs = []
+    for _ in range(10):
+        mps = evolve_tdvp_ps2(mps, mpo, 0.05, 32)
+        zs.append(mps.expectation(z))
+    assert np.abs(np.array(zs) - g["ps2_z_t"]).max() < 1e-12
+    assert np.abs(np.array(zs) - g["pc_z_t"]).max() < 1e-6
+    assert np.abs(np.array(zs) + np.cos(2 * 0.05 * np.arange(1, 11))).max() < 1e-6
