@@ -507,8 +507,38 @@ def evolve_tdvp_ps(mps_in, mpo, dt, normalize=True, stats=None):
                 mps.sites[imps] = mps_t
         mps.switch_direction()
     if normalize:
+        # mps.py:657-661: "mps_and_coeff" for imaginary time, "mps_only" for real time; the site
+        # tensors are scaled by 1/norm either way (coeff / |coeff| is not tracked here)
         mps.normalize_mps_only()
     return mps
+
+
+def evolve_adaptive_tdvp_ps(mps_in, mpo, target_t, guess_dt, rtol=5e-4):
+    """Step-size control around the one-site integrator by step doubling.  Reference:
+    renormalizer/mps/mps.py:46-115 (adaptive_tdvp) + mps.py:644-662 (normalisation in evolve).
+    Returns (new Mps, new guess_dt)."""
+    p_restart, p_min, p_max = 0.5, 0.1, 2.0
+    cur = mps_in
+    evolved = 0
+    while True:
+        rest = target_t - evolved
+        dt = guess_dt if abs(guess_dt) < abs(rest) else rest
+        half1 = evolve_tdvp_ps(cur, mpo, dt / 2, normalize=False)
+        half2 = evolve_tdvp_ps(half1, mpo, dt / 2, normalize=False)
+        full = evolve_tdvp_ps(cur, mpo, dt, normalize=False)
+        l1, l2, l12 = full.dot_conj(full), half2.dot_conj(half2), full.dot_conj(half2)
+        dis = np.sqrt(max((l1 + l2 - l12 - np.conj(l12)).real, 0.0))      # mp.py:1009-1023
+        p = (0.75 * rtol / (dis / half2.mp_norm + 1e-30)) ** (1.0 / 3)
+        p = min(max(p, p_min), p_max)
+        if p < p_restart:
+            guess_dt = dt * p
+            continue
+        evolved += dt
+        if np.allclose(evolved, target_t):
+            half2.normalize_mps_only()
+            return half2, guess_dt
+        guess_dt *= p
+        cur = half2
 
 
 def evolve_tdvp_ps2(mps_in, mpo, dt, m_max, normalize=True, stats=None):

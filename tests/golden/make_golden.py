@@ -465,6 +465,90 @@ def gen_exciton():
     np.savez_compressed(os.path.join(HERE, "exciton.npz"), **out)
 
 
+def _exciton_model():
+    from renormalizer.model import Phonon, Mol, HolsteinModel
+    from renormalizer.utils import Quantity
+    jm = np.array([[0.31, -0.098, 0.006, -0.006],
+                   [-0.098, 0.23, 0.030, 0.007],
+                   [0.006, 0.030, 0.0, -0.059],
+                   [-0.006, 0.007, -0.059, 0.18]])
+    phs = [Phonon.simple_phonon(Quantity(o), Quantity(d), 4)
+           for o, d in zip([0.12, 0.25], [1.1, 0.6])]
+    mols = [Mol(Quantity(e), phs) for e in np.diag(jm)]
+    return HolsteinModel(mols, jm), len(mols)
+
+
+def gen_thermal():
+    """Finite temperature (BASELINE configs[3]): imaginary-time TDVP-PS of a density operator from
+    the maximally entangled one-exciton state down to beta (what mps/thermalprop.py:96-98 does each
+    step: MpDm.evolve(h_mpo, -i dbeta/2), here with a fixed energy offset), followed by real-time
+    steps of the thermal state; and the adaptive step-size controller (mps.py:46-115) on the
+    zero-temperature exciton run."""
+    from renormalizer.model.op import Op
+    from renormalizer.mps import Mps, Mpo, MpDm
+    from renormalizer.utils import CompressConfig, EvolveConfig, EvolveMethod, CompressCriteria
+    out = {}
+    model, nmol = _exciton_model()
+    mpo = Mpo(model)
+    occ_ops = [Mpo(model, Op(r"a^\dagger a", i)) for i in range(nmol)]
+    dump_mp("mpo", mpo, out)
+    for i, o in enumerate(occ_ops):
+        dump_mp(f"occ{i}", o, out)
+    out["nmol"] = np.array(nmol)
+    np.random.seed(1234)
+    dm = MpDm.max_entangled_ex(model)
+    dm.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=8)
+    dm.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    dm = dm.expand_bond_dimension(mpo, include_ex=False)
+    dump_mp("dm0", dm, out)
+    dump_mps_meta("dm0", dm, out)
+    out["dm0_coeff"] = np.array(dm.coeff)
+    beta, nbeta = 8.0, 4
+    dbeta = beta / nbeta
+    occ = [[dm.expectation(o) for o in occ_ops]]
+    en = [dm.expectation(mpo)]
+    coeffs = [dm.coeff]
+    for i in range(nbeta):
+        dm = dm.evolve(mpo, -0.5j * dbeta)
+        occ.append([dm.expectation(o) for o in occ_ops])
+        en.append(dm.expectation(mpo))
+        coeffs.append(dm.coeff)
+    out["beta"] = np.array(beta)
+    out["nbeta"] = np.array(nbeta)
+    out["imag_occ"] = np.array(occ)
+    out["imag_energy"] = np.array(en)
+    out["imag_coeff"] = np.array(coeffs)
+    dump_mp("dm_beta", dm, out)
+    # real-time evolution of the thermal state
+    rocc, ren = [], []
+    for i in range(2):
+        dm = dm.evolve(mpo, 2.0)
+        rocc.append([dm.expectation(o) for o in occ_ops])
+        ren.append(dm.expectation(mpo))
+    out["real_occ"] = np.array(rocc)
+    out["real_energy"] = np.array(ren)
+    # adaptive TDVP-PS on the pure-state run
+    np.random.seed(777)
+    gs = Mps.ground_state(model, False)
+    mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ gs
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=True, guess_dt=1.0,
+                                     adaptive_rtol=5e-4)
+    mps = mps.expand_bond_dimension(mpo, include_ex=False)
+    dump_mp("mps0", mps, out)
+    dump_mps_meta("mps0", mps, out)
+    out["mps0_coeff"] = np.array(mps.coeff)
+    aocc, guess = [], []
+    for i in range(3):
+        mps = mps.evolve(mpo, 4.0)
+        aocc.append([mps.expectation(o) for o in occ_ops])
+        guess.append(mps.evolve_config.guess_dt)
+    out["adaptive_occ"] = np.array(aocc)
+    out["adaptive_guess_dt"] = np.array(guess)
+    dump_mp("adaptive_mpsT", mps, out)
+    np.savez_compressed(os.path.join(HERE, "thermal.npz"), **out)
+
+
 def gen_two_spin():
     """The README quickstart (README.md:36-58): two half spins, sigma+ sigma- exchange, 10 steps
     of Mps.evolve with dt = 0.05, <Z_0> after every step -- with the default propagate-and-
@@ -498,7 +582,7 @@ def gen_two_spin():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm", "stacked", "qc", "exciton",
-                             "two_spin"]
+                             "two_spin", "thermal"]
     for name in which:
         print("generating", name, flush=True)
         globals()["gen_" + name]()

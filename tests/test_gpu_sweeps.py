@@ -551,3 +551,64 @@ def test_two_spin_quickstart_golden(golden):
     assert np.abs(np.array(zs) - g["pc_z_t"]).max() < 1e-6
     assert np.abs(np.array(zs) + np.cos(2 * 0.05 * np.arange(1, 11))).max() < 1e-6
     assert mps.bond_dims == list(g["ps2_bond_dims"])
+
+
+def test_thermal_imaginary_then_real_time_golden(golden):
+    """Finite temperature (BASELINE configs[3]): imaginary-time TDVP-PS of a density operator
+    (mps/thermalprop.py:96-98: MpDm.evolve(h_mpo, -i dbeta/2); real Krylov exponent, "mps_and_coeff"
+    normalisation), then real-time steps of the thermal state.  Imaginary time amplifies rounding
+    differences by exp(dbeta * spectral width) per step (the CPU restatement itself agrees with the
+    reference to 1.4e-10 after four steps), hence 1e-9 on this leg."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig, EvolveMethod
+    from renormalizer_b200.mpo import Mpo
+    g = golden("thermal")
+    mpo = Mpo(load_mpo(g))
+    occ = [Mpo(load_mpo(g, f"occ{i}")) for i in range(int(g["nmol"]))]
+    dm = _device_mps_with_coeff(g, "dm0")
+    dm.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=8)
+    dm.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    dbeta = float(g["beta"]) / int(g["nbeta"])
+    occs, es = [[dm.expectation(o) for o in occ]], [dm.expectation(mpo)]
+    for _ in range(int(g["nbeta"])):
+        dm = dm.evolve(mpo, -0.5j * dbeta)
+        assert not dm.is_complex                       # real MPDM stays real in imaginary time
+        assert abs(dm.mp_norm - 1) < 1e-12 and dm.coeff == 1
+        occs.append([dm.expectation(o) for o in occ])
+        es.append(dm.expectation(mpo))
+    assert np.abs(np.array(occs) - g["imag_occ"]).max() < 1e-9
+    assert np.abs(np.array(es) - g["imag_energy"]).max() < 1e-9
+    assert np.abs(np.array(occs[1]) - g["imag_occ"][1]).max() < E_TOL
+    ref = to_device_mps(load_oracle_mps(g, "dm_beta", meta="dm0"))
+    assert abs(abs(ref.conj().dot(dm)) - 1) < T_TOL
+    rocc, ren = [], []
+    for _ in range(2):
+        dm = dm.evolve(mpo, 2.0)
+        rocc.append([dm.expectation(o) for o in occ])
+        ren.append(dm.expectation(mpo))
+    assert np.abs(np.array(rocc) - g["real_occ"]).max() < 1e-9
+    assert np.abs(np.array(ren) - g["real_energy"]).max() < 1e-9
+
+
+def test_adaptive_tdvp_ps_golden(golden):
+    """adaptive_tdvp (mps.py:46-115) through Mps.evolve: the controller accepts the same sub-steps
+    and ends on the same guess_dt; observables agree to the local solver's own stopping tolerance
+    once the step has doubled to dt = 4 (see the oracle test), to 1e-10 on the first call."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig, EvolveMethod
+    from renormalizer_b200.mpo import Mpo
+    g = golden("thermal")
+    mpo = Mpo(load_mpo(g))
+    occ = [Mpo(load_mpo(g, f"occ{i}")) for i in range(int(g["nmol"]))]
+    mps = _device_mps_with_coeff(g, "mps0")
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=True, guess_dt=1.0,
+                                     adaptive_rtol=5e-4)
+    occs, guesses = [], []
+    for _ in range(3):
+        mps = mps.evolve(mpo, 4.0)
+        occs.append([mps.expectation(o) for o in occ])
+        guesses.append(mps.evolve_config.guess_dt)
+    assert np.allclose(guesses, g["adaptive_guess_dt"], rtol=1e-6)
+    assert np.abs(np.array(occs[0]) - g["adaptive_occ"][0]).max() < E_TOL
+    assert np.abs(np.array(occs) - g["adaptive_occ"]).max() < 1e-7
+    refT = to_device_mps(load_oracle_mps(g, "adaptive_mpsT", meta="mps0"))
+    assert abs(abs(refT.conj().dot(mps)) - 1) < 1e-6
