@@ -74,6 +74,262 @@ jacobi_round_kernel(typename std::conditional<CPLX, double2, double>::type* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Block one-sided Jacobi on PAIRS OF COLUMN BLOCKS (2 x 16 columns), three kernels per round:
+//
+// The scalar kernel above needs n-1 launches per sweep, each touching every column once for three
+// dot products and once for the rotation.  Here, for every block pair of a round,
+//   1. jb_gram_kernel forms the Gram matrix G = Xc^H Xc of the 32 columns (row slices in parallel,
+//      shared-memory row chunks, 4 entries of G per thread),
+//   2. jb_rotate_kernel runs ONE cyclic sweep of two-sided Jacobi on G in shared memory (31 rounds
+//      x 16 disjoint pairs; thread (i, j) owns the 2x2 sub-block {p_i,q_i} x {p_j,q_j}, so a round
+//      is a rotation set-up by 16 threads and one conflict-free update), accumulating J,
+//   3. jb_apply_kernel applies Xc <- Xc J and Vc <- Vc J (row slices in parallel).
+// In exact arithmetic this is the scalar algorithm with the pairs visited block by block (the
+// rotation of a pair is computed from a, b, g exactly as above; G is updated by the same rotations
+// instead of being recomputed from the columns).  Demmel & Veselic's relative accuracy of Jacobi on
+// G = D A D carries over because G is formed from the current columns at every visit.  A sweep is
+// n/16 - 1 launches instead of n - 1, and every column is read twice and written once per launch.
+constexpr int JB = 16;            // columns per block
+constexpr int JK = 2 * JB;        // columns per CTA
+constexpr int JBT = 256;          // threads
+
+__device__ __forceinline__ double jb_mul(double a, double b) { return a * b; }
+__device__ __forceinline__ double2 jb_mul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double jb_cmul(double a, double b) { return a * b; }          // conj(a) * b
+__device__ __forceinline__ double2 jb_cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double jb_add(double a, double b) { return a + b; }
+__device__ __forceinline__ double2 jb_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double jb_sub(double a, double b) { return a - b; }
+__device__ __forceinline__ double2 jb_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double jb_scale(double c, double a) { return c * a; }
+__device__ __forceinline__ double2 jb_scale(double c, double2 a) { return make_double2(c * a.x, c * a.y); }
+__device__ __forceinline__ void jb_fma(double& acc, double a, double b) { acc = fma(a, b, acc); }
+__device__ __forceinline__ void jb_fma(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void jb_cfma(double& acc, double a, double b) { acc = fma(a, b, acc); }   // += conj(a) b
+__device__ __forceinline__ void jb_cfma(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+template <typename T> __device__ __forceinline__ T jb_zero();
+template <> __device__ __forceinline__ double jb_zero<double>() { return 0.0; }
+template <> __device__ __forceinline__ double2 jb_zero<double2>() { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ double jb_real(double a) { return a; }
+__device__ __forceinline__ double jb_real(double2 a) { return a.x; }
+__device__ __forceinline__ double jb_abs(double a) { return fabs(a); }
+__device__ __forceinline__ double jb_abs(double2 a) { return sqrt(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ double jb_conj(double a) { return a; }
+__device__ __forceinline__ double2 jb_conj(double2 a) { return make_double2(a.x, -a.y); }
+
+template <bool CPLX> struct JBCfg { static constexpr int RC = CPLX ? 32 : 64; };   // rows per chunk
+constexpr int JB_MAXSLICE = 8;    // row slices per block pair (CTAs working on the same 32 columns)
+
+// block pair of CTA `bx` in round `round` of the round-robin tournament over NB (even) blocks
+__device__ __forceinline__ void jb_pair(int bx, int round, int NB, int& P, int& Q) {
+  if (bx == 0) { P = NB - 1; Q = round; }
+  else { P = (round + bx) % (NB - 1); Q = (round - bx + (NB - 1)) % (NB - 1); }
+  if (P > Q) { const int t = P; P = Q; Q = t; }
+}
+__device__ __forceinline__ int jb_col(int c, int P, int Q, int nb, int n) {
+  const int blk = c < JB ? P : Q;
+  const int idx = blk * JB + (c & (JB - 1));
+  return (blk < nb && idx < n) ? idx : -1;
+}
+
+// 1. partial Gram matrices: CTA (pair, slice) -> Gp[(pair * nslice + slice) * JK * JK]
+template <bool CPLX>
+__global__ void __launch_bounds__(JBT)
+jb_gram_kernel(const typename std::conditional<CPLX, double2, double>::type* __restrict__ At,
+               int m, int n, long ldt, int round, int NB, int nb, int rows_per_slice,
+               typename std::conditional<CPLX, double2, double>::type* __restrict__ Gp) {
+  pdl_wait();
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  constexpr int RC = JBCfg<CPLX>::RC, LDT = RC + 1;
+  __shared__ T tile[JK * LDT];
+  __shared__ int col[JK];
+  const int tid = threadIdx.x;
+  int P, Q;
+  jb_pair(blockIdx.x, round, NB, P, Q);
+  if (P >= nb) return;
+  if (tid < JK) col[tid] = jb_col(tid, P, Q, nb, n);
+  __syncthreads();
+  const int rbeg = blockIdx.y * rows_per_slice;
+  const int rend = min(m, rbeg + rows_per_slice);
+  const int gi = tid >> 3, gj = (tid & 7) * 4;
+  T acc[4] = {jb_zero<T>(), jb_zero<T>(), jb_zero<T>(), jb_zero<T>()};
+  for (int r0 = rbeg; r0 < rend; r0 += RC) {
+    for (int e = tid; e < JK * RC; e += JBT) {
+      const int c = e / RC, r = e % RC, gr = r0 + r;
+      const int cc = col[c];
+      tile[c * LDT + r] = (cc >= 0 && gr < rend) ? At[(long)cc * ldt + gr] : jb_zero<T>();
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < RC; ++r) {
+      const T xi = tile[gi * LDT + r];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) jb_cfma(acc[jj], xi, tile[(gj + jj) * LDT + r]);
+    }
+    __syncthreads();
+  }
+  T* out = Gp + ((long)blockIdx.x * gridDim.y + blockIdx.y) * (JK * JK);
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) out[gi * JK + gj + jj] = acc[jj];
+}
+
+// 2. G = sum of the slices (fixed order); one cyclic sweep of two-sided Jacobi on G in shared
+//    memory; the accumulated rotation J and a "rotated" flag per pair go to global memory.
+template <bool CPLX>
+__global__ void __launch_bounds__(JBT)
+jb_rotate_kernel(const typename std::conditional<CPLX, double2, double>::type* __restrict__ Gp, int nslice,
+                 int round, int NB, int nb, double tol,
+                 typename std::conditional<CPLX, double2, double>::type* __restrict__ Jg,
+                 int* __restrict__ pair_rot, int* __restrict__ rotated) {
+  pdl_wait();
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  __shared__ T G[JK * JK];
+  __shared__ T J[JK * JK];
+  __shared__ int rp[JB], rq[JB];
+  __shared__ double rc[JB];
+  __shared__ T rs[JB];
+  __shared__ int any_rot;
+  const int tid = threadIdx.x;
+  int P, Q;
+  jb_pair(blockIdx.x, round, NB, P, Q);
+  if (P >= nb) return;
+  if (tid == 0) any_rot = 0;
+  for (int e = tid; e < JK * JK; e += JBT) {
+    T g = jb_zero<T>();
+    for (int sl = 0; sl < nslice; ++sl) g = jb_add(g, Gp[((long)blockIdx.x * nslice + sl) * (JK * JK) + e]);
+    G[e] = g;
+    T one = jb_zero<T>();
+    if ((e / JK) == (e % JK)) { if constexpr (CPLX) one.x = 1.0; else one = 1.0; }
+    J[e] = one;
+  }
+  __syncthreads();
+  const int ti = tid >> 4, tj = tid & 15;
+  for (int lr = 0; lr < JK - 1; ++lr) {
+    if (tid < JB) {
+      int p, q;
+      if (tid == 0) { p = JK - 1; q = lr; }
+      else { p = (lr + tid) % (JK - 1); q = (lr - tid + (JK - 1)) % (JK - 1); }
+      if (p > q) { const int t = p; p = q; q = t; }
+      const double a = jb_real(G[p * JK + p]), b = jb_real(G[q * JK + q]);
+      const T g = G[p * JK + q];
+      const double gabs = jb_abs(g);
+      double c = 1.0;
+      T sph = jb_zero<T>();
+      if (a > 0.0 && b > 0.0 && gabs > 0.0 && gabs > tol * sqrt(a) * sqrt(b)) {
+        const double zeta = (b - a) / (2.0 * gabs);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        c = rsqrt(1.0 + t * t);
+        sph = jb_scale(c * t / gabs, g);              // s * phase, phase = g / |g|
+        any_rot = 1;
+      }
+      rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = sph;
+    }
+    __syncthreads();
+    {
+      const int p = rp[ti], q = rq[ti], u = rp[tj], v = rq[tj];
+      const double ci = rc[ti], cj = rc[tj];
+      const T si = rs[ti], sj = rs[tj];
+      const T gpu = G[p * JK + u], gpv = G[p * JK + v], gqu = G[q * JK + u], gqv = G[q * JK + v];
+      // columns: xu' = cj xu - conj(sj) xv ; xv' = sj xu + cj xv
+      const T pu = jb_sub(jb_scale(cj, gpu), jb_cmul(sj, gpv)), pv = jb_add(jb_mul(sj, gpu), jb_scale(cj, gpv));
+      const T qu = jb_sub(jb_scale(cj, gqu), jb_cmul(sj, gqv)), qv = jb_add(jb_mul(sj, gqu), jb_scale(cj, gqv));
+      // rows (R^H from the left): p' = ci p - si q ; q' = conj(si) p + ci q
+      T npu = jb_sub(jb_scale(ci, pu), jb_mul(si, qu)), npv = jb_sub(jb_scale(ci, pv), jb_mul(si, qv));
+      T nqu = jb_add(jb_cmul(si, pu), jb_scale(ci, qu)), nqv = jb_add(jb_cmul(si, pv), jb_scale(ci, qv));
+      if (ti == tj) {                                  // the rotated pair itself: exactly diagonal
+        npv = jb_zero<T>(); nqu = jb_zero<T>();
+        if constexpr (CPLX) { npu.y = 0.0; nqv.y = 0.0; }
+      }
+      G[p * JK + u] = npu; G[p * JK + v] = npv; G[q * JK + u] = nqu; G[q * JK + v] = nqv;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int rr = ti + h * JB;
+        const T ju = J[rr * JK + u], jv = J[rr * JK + v];
+        J[rr * JK + u] = jb_sub(jb_scale(cj, ju), jb_cmul(sj, jv));
+        J[rr * JK + v] = jb_add(jb_mul(sj, ju), jb_scale(cj, jv));
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    pair_rot[blockIdx.x] = any_rot;
+    if (any_rot) *rotated = 1;
+  }
+  if (!any_rot) return;
+  T* out = Jg + (long)blockIdx.x * (JK * JK);
+  for (int e = tid; e < JK * JK; e += JBT) out[e] = J[e];
+}
+
+// 3. Xc <- Xc J (blockIdx.z == 0) and Vc <- Vc J (blockIdx.z == 1), one CTA per row slice
+template <bool CPLX>
+__global__ void __launch_bounds__(JBT)
+jb_apply_kernel(typename std::conditional<CPLX, double2, double>::type* __restrict__ At,
+                typename std::conditional<CPLX, double2, double>::type* __restrict__ Vw,
+                int m, int n, int nv, long ldt, long ldv, int round, int NB, int nb,
+                int rows_per_slice_x, int rows_per_slice_v,
+                const typename std::conditional<CPLX, double2, double>::type* __restrict__ Jg,
+                const int* __restrict__ pair_rot) {
+  pdl_wait();
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  constexpr int RC = JBCfg<CPLX>::RC, LDT = RC + 1;
+  __shared__ T tile[JK * LDT];
+  __shared__ T J[JK * JK];
+  __shared__ int col[JK];
+  const int tid = threadIdx.x;
+  int P, Q;
+  jb_pair(blockIdx.x, round, NB, P, Q);
+  if (P >= nb) return;
+  if (!pair_rot[blockIdx.x]) return;
+  if (tid < JK) col[tid] = jb_col(tid, P, Q, nb, n);
+  for (int e = tid; e < JK * JK; e += JBT) J[e] = Jg[(long)blockIdx.x * (JK * JK) + e];
+  __syncthreads();
+  T* M = blockIdx.z == 0 ? At : Vw;
+  const long ld = blockIdx.z == 0 ? ldt : ldv;
+  const int rows = blockIdx.z == 0 ? m : nv;
+  const int rps = blockIdx.z == 0 ? rows_per_slice_x : rows_per_slice_v;
+  const int rbeg = blockIdx.y * rps;
+  const int rend = min(rows, rbeg + rps);
+  constexpr int NG = JBT / RC, NC = JK / NG;           // column groups, columns per thread
+  const int r = tid % RC, cg = (tid / RC) * NC;
+  for (int r0 = rbeg; r0 < rend; r0 += RC) {
+    for (int e = tid; e < JK * RC; e += JBT) {
+      const int c = e / RC, rr = e % RC, gr = r0 + rr;
+      const int cc = col[c];
+      tile[c * LDT + rr] = (cc >= 0 && gr < rend) ? M[(long)cc * ld + gr] : jb_zero<T>();
+    }
+    __syncthreads();
+    T acc[NC];
+#pragma unroll
+    for (int jj = 0; jj < NC; ++jj) acc[jj] = jb_zero<T>();
+#pragma unroll 4
+    for (int c = 0; c < JK; ++c) {
+      const T x = tile[c * LDT + r];
+#pragma unroll
+      for (int jj = 0; jj < NC; ++jj) jb_fma(acc[jj], x, J[c * JK + cg + jj]);
+    }
+    if (r0 + r < rend) {
+#pragma unroll
+      for (int jj = 0; jj < NC; ++jj) {
+        const int cc = col[cg + jj];
+        if (cc >= 0) M[(long)cc * ld + r0 + r] = acc[jj];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // S[c] = |At[c]|, At[c] /= S[c]
 template <bool CPLX>
 __global__ void __launch_bounds__(J_THREADS)
@@ -136,9 +392,42 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
   const int N = (nt + 1) & ~1;  // even number of players
   const double tol = sqrt((double)mt) * 2.220446049250313e-16;
   int sweeps = 0;
+  static int block_on = -1;                 // RN_SVD_BLOCK=0 keeps the scalar kernel (diagnostics)
+  if (block_on < 0) {
+    const char* e = getenv("RN_SVD_BLOCK");
+    block_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool blocked = block_on && nt >= 2 * JK;
+  const int nb = (int)ceil_div(nt, JB), NB = (nb + 1) & ~1;
+  constexpr int RC = JBCfg<CPLX>::RC;
+  // row slices: whole chunks of RC rows, at most JB_MAXSLICE CTAs per block pair
+  auto slices = [&](int rows, int& rps) {
+    int ns = (int)ceil_div(rows, RC);
+    if (ns > JB_MAXSLICE) ns = JB_MAXSLICE;
+    rps = (int)ceil_div(ceil_div(rows, ns), RC) * RC;
+    return (int)ceil_div(rows, rps);
+  };
+  int rps_x = 0, rps_v = 0;
+  const int ns_x = slices(mt, rps_x), ns_v = slices(nt, rps_v);
+  T *Gp = nullptr, *Jg = nullptr;
+  int* pair_rot = nullptr;
+  if (blocked) {
+    RN_CHECK(cudaMallocAsync((void**)&Gp, sizeof(T) * (size_t)(NB / 2) * ns_x * JK * JK, st));
+    RN_CHECK(cudaMallocAsync((void**)&Jg, sizeof(T) * (size_t)(NB / 2) * JK * JK, st));
+    RN_CHECK(cudaMallocAsync((void**)&pair_rot, sizeof(int) * (size_t)(NB / 2), st));
+  }
   if (nt > 1) {
     for (; sweeps < max_sweeps; ++sweeps) {
       RN_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+      if (blocked) {
+        for (int round = 0; round < NB - 1; ++round) {
+          RN_LAUNCH(jb_gram_kernel<CPLX>, dim3(NB / 2, ns_x), JBT, 0, st, At, mt, nt, ldt, round, NB, nb, rps_x, Gp);
+          RN_LAUNCH(jb_rotate_kernel<CPLX>, NB / 2, JBT, 0, st, Gp, ns_x, round, NB, nb, tol, Jg, pair_rot, flag);
+          RN_LAUNCH(jb_apply_kernel<CPLX>, dim3(NB / 2, ns_x > ns_v ? ns_x : ns_v, 2), JBT, 0, st, At, Vw, mt, nt, nt,
+                    ldt, ldv, round, NB, nb, rps_x, rps_v, Jg, pair_rot);
+          rn::g_launches += 3;
+        }
+      } else
       for (int round = 0; round < N - 1; ++round)
         { RN_LAUNCH(jacobi_round_kernel<CPLX>, N / 2, J_THREADS, 0, st, At, Vw, mt, nt, nt, ldt, ldv, round, N, tol, flag); rn::g_launches++; }
       RN_LAUNCH_CHECK();
@@ -166,6 +455,9 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
   RN_CHECK(cudaFreeAsync(At, st));
   RN_CHECK(cudaFreeAsync(Vw, st));
   RN_CHECK(cudaFreeAsync(flag, st));
+  if (Gp) RN_CHECK(cudaFreeAsync(Gp, st));
+  if (Jg) RN_CHECK(cudaFreeAsync(Jg, st));
+  if (pair_rot) RN_CHECK(cudaFreeAsync(pair_rot, st));
   return 0;
 }
 
