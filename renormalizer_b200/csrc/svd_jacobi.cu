@@ -126,6 +126,8 @@ __device__ __forceinline__ double jb_real(double a) { return a; }
 __device__ __forceinline__ double jb_real(double2 a) { return a.x; }
 __device__ __forceinline__ double jb_abs(double a) { return fabs(a); }
 __device__ __forceinline__ double jb_abs(double2 a) { return sqrt(a.x * a.x + a.y * a.y); }
+__device__ __forceinline__ double jb_abs2(double a) { return a * a; }
+__device__ __forceinline__ double jb_abs2(double2 a) { return a.x * a.x + a.y * a.y; }
 __device__ __forceinline__ double jb_conj(double a) { return a; }
 __device__ __forceinline__ double2 jb_conj(double2 a) { return make_double2(a.x, -a.y); }
 
@@ -224,14 +226,20 @@ jb_rotate_kernel(const typename std::conditional<CPLX, double2, double>::type* _
       if (p > q) { const int t = p; p = q; q = t; }
       const double a = jb_real(G[p * JK + p]), b = jb_real(G[q * JK + q]);
       const T g = G[p * JK + q];
-      const double gabs = jb_abs(g);
+      const double g2 = jb_abs2(g);                   // |g|^2
       double c = 1.0;
       T sph = jb_zero<T>();
-      if (a > 0.0 && b > 0.0 && gabs > 0.0 && gabs > tol * sqrt(a) * sqrt(b)) {
-        const double zeta = (b - a) / (2.0 * gabs);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        c = rsqrt(1.0 + t * t);
-        sph = jb_scale(c * t / gabs, g);              // s * phase, phase = g / |g|
+      // |g| > tol sqrt(a b), tested on the squares; the rotation with zeta = (b - a) / (2 |g|),
+      // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) is evaluated as t = sign(d) 2|g| w with
+      // w = 1 / (|d| + sqrt(d^2 + 4 |g|^2)), d = b - a: one square root, one reciprocal and one
+      // reciprocal square root on the critical path of a round
+      if (a > 0.0 && b > 0.0 && g2 > 0.0 && g2 > tol * tol * a * b) {
+        const double d = b - a;
+        const double w = 1.0 / (fabs(d) + sqrt(fma(d, d, 4.0 * g2)));
+        const double tg = (d >= 0.0 ? 2.0 : -2.0) * w;     // t / |g|
+        const double t2 = tg * tg * g2;                    // t^2
+        c = rsqrt(1.0 + t2);
+        sph = jb_scale(c * tg, g);                    // s * phase = c t g / |g|
         any_rot = 1;
       }
       rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = sph;

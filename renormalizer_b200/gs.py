@@ -12,7 +12,7 @@ from .configs import CompressConfig, CompressCriteria
 from .davidson import davidson
 from .hop_expr import hop_expr_dtype
 from .lib import Environ
-from .svd_qn import get_qn_mask
+from .svd_qn import get_qn_mask, qn_mask_outer
 
 logger = logging.getLogger(__name__)
 
@@ -109,8 +109,8 @@ def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
             ltensor = environ.GetLR("L", lidx, mps, mpo, itensor=None, method=lmethod)
             rtensor = environ.GetLR("R", ridx, mps, mpo, itensor=None, method=rmethod)
             cmo = [mpo[idx] for idx in cidx]
-        qnbigl, qnbigr, qnmat = mps._get_big_qn(cidx)
-        qn_mask = get_qn_mask(qnmat, mps.qntot)
+        qnbigl, qnbigr, _ = mps._get_big_qn(cidx, need_mat=False)
+        qn_mask = qn_mask_outer(qnbigl, qnbigr, mps.qntot)
         cshape = qn_mask.shape
         use_direct_eigh = np.prod(cshape) < 1000 or mps.optimize_config.algo == "direct"
         if use_direct_eigh:

@@ -13,11 +13,11 @@ import torch
 
 from . import ops
 from .backend import backend, asxp, asnumpy
-from .configs import CompressConfig, EvolveConfig, OptimizeConfig, EvolveMethod
+from .configs import CompressConfig, CompressCriteria, EvolveConfig, OptimizeConfig, EvolveMethod
 from .hop_expr import hop_expr_dtype
 from .krylov import expm_krylov
 from .lib import Environ, contract_one_site
-from .svd_qn import add_outer, svd_qn, select_basis, eigh_qn
+from .svd_qn import add_outer, svd_qn, select_basis, eigh_qn, economic_rank
 
 
 class Mps:
@@ -156,8 +156,10 @@ class Mps:
             self.qnidx = 0
             self.to_right = True
 
-    def _get_big_qn(self, cidx: List[int]):
-        """mp.py:308-352: quantum numbers of the super-L / super-R blocks and of the centre."""
+    def _get_big_qn(self, cidx: List[int], need_mat: bool = True):
+        """mp.py:308-352: quantum numbers of the super-L / super-R blocks and of the centre.
+        `need_mat=False` skips the (left x right) outer sum, which only the eigensolver's mask
+        needs (16.7 M entries for a two-site centre at M = 512); None is returned in its place."""
         if len(cidx) == 2:
             cidx = sorted(cidx)
             assert cidx[0] + 1 == cidx[1]
@@ -174,7 +176,7 @@ class Mps:
                 qnbigl, qnbigr = qnl, add_outer(sigmaqn[0], qnr)
         else:
             qnbigl, qnbigr = add_outer(qnl, sigmaqn[0]), add_outer(sigmaqn[1], qnr)
-        return qnbigl, qnbigr, add_outer(qnbigl, qnbigr)
+        return qnbigl, qnbigr, (add_outer(qnbigl, qnbigr) if need_mat else None)
 
     # ------------------------------------------------------------------ canonical form
     def check_left_canonical(self, rtol=None, atol=None):
@@ -251,7 +253,7 @@ class Mps:
 
     def _push_cano(self, idx):
         """mp.py:890-908: move the canonical centre one site on with a QR."""
-        qnbigl, qnbigr, _ = self._get_big_qn([idx])
+        qnbigl, qnbigr, _ = self._get_big_qn([idx], need_mat=False)
         system = "L" if self.to_right else "R"
         u, qnlset, v, qnrset = svd_qn(self._mp[idx], qnbigl, qnbigr, self.qntot, QR=True,
                                       system=system, full_matrices=False)
@@ -281,7 +283,7 @@ class Mps:
         system = "L" if self.to_right else "R"
         s_list = []
         for idx in self.iter_idx_list(full=False):
-            qnbigl, qnbigr, _ = self._get_big_qn([idx])
+            qnbigl, qnbigr, _ = self._get_big_qn([idx], need_mat=False)
             u, sigma, qnlset, v, sigma, qnrset = svd_qn(self._mp[idx], qnbigl, qnbigr, self.qntot,
                                                         system=system, full_matrices=False)
             s_list.append(sigma)
@@ -313,7 +315,17 @@ class Mps:
         multi = isinstance(cstruct, list)
         rotated_c, averaged_ms = [], []
         if not multi:
-            Uset, SUset, qnlnew, Vset, SVset, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, self.qntot, system=system)
+            # The reference always asks for full matrices (mp.py:741) and lets select_basis ignore the
+            # null-space columns it does not need.  They can only be selected when percent != 0 or
+            # when the bond limit exceeds the number of economic singular vectors, so in every other
+            # case the completion (random vectors, two projections and a QR per block) is skipped:
+            # select_basis returns the same vectors.
+            bond = cidx[0] + 1 if self.to_right else cidx[-1]
+            need_full = percent != 0 or (
+                self.compress_config.criteria is not CompressCriteria.threshold
+                and int(self.compress_config.max_dims[bond]) > economic_rank(qnbigl, qnbigr, self.qntot))
+            Uset, SUset, qnlnew, Vset, SVset, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, self.qntot, system=system,
+                                                              full_matrices=need_full)
             if self.to_right:
                 m_trunc = self.compress_config.compute_m_trunc(SUset, cidx[0], self.to_right)
                 ms, msdim, msqn, compms = select_basis(Uset, SUset, qnlnew, Vset, m_trunc, percent=percent)
@@ -535,7 +547,7 @@ class Mps:
                 hop.close()
                 local_steps.append(j)
                 mps_t = mps_t.reshape(shape)
-                qnbigl, qnbigr, _ = mps._get_big_qn([imps])
+                qnbigl, qnbigr, _ = mps._get_big_qn([imps], need_mat=False)
                 u, qnlset, v, qnrset = svd_qn(mps_t, qnbigl, qnbigr, mps.qntot, QR=True,
                                               system=system, full_matrices=False)
                 vt = v.transpose(0, 1).contiguous()
@@ -598,7 +610,7 @@ class Mps:
                 mps_t, j = expm_krylov(hop, -1j * evolve_dt / 2, ms2.reshape(-1))
                 hop.close()
                 local_steps.append(j)
-                qnbigl, qnbigr, _ = mps._get_big_qn([cidx0, cidx1])
+                qnbigl, qnbigr, _ = mps._get_big_qn([cidx0, cidx1], need_mat=False)
                 mps._update_mps(mps_t.reshape(shape2), [cidx0, cidx1], qnbigl, qnbigr)
                 if imps == last_idx:
                     continue

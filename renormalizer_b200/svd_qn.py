@@ -24,6 +24,31 @@ def get_qn_mask(qnmat: np.ndarray, qntot):
     return np.all(qnmat == np.array(qntot), axis=-1)
 
 
+def qn_mask_outer(qnbigl: np.ndarray, qnbigr: np.ndarray, qntot):
+    """get_qn_mask(add_outer(qnbigl, qnbigr), qntot) without materialising the int64 outer sum:
+    one narrow-integer comparison per quantum-number component."""
+    sl, sr = qnbigl.shape[:-1], qnbigr.shape[:-1]
+    l = qnbigl.reshape(-1, qnbigl.shape[-1])
+    r = np.asarray(qntot).reshape(1, -1) - qnbigr.reshape(-1, qnbigr.shape[-1])
+    lo, hi = min(l.min(initial=0), r.min(initial=0)), max(l.max(initial=0), r.max(initial=0))
+    dt = np.int8 if -128 <= lo and hi < 128 else np.int32
+    l, r = l.astype(dt), r.astype(dt)
+    mask = l[:, None, 0] == r[None, :, 0]
+    for k in range(1, l.shape[1]):
+        mask &= l[:, None, k] == r[None, :, k]
+    return mask.reshape(sl + sr)
+
+
+def economic_rank(qnbigl: np.ndarray, qnbigr: np.ndarray, qntot):
+    """Number of singular vectors svd_qn returns with full_matrices=False: the sum over the
+    quantum-number blocks of min(rows, columns)."""
+    nq = qnbigl.shape[-1]
+    lq, lc = np.unique(qnbigl.reshape(-1, nq), axis=0, return_counts=True)
+    rq, rc = np.unique(np.asarray(qntot).reshape(1, -1) - qnbigr.reshape(-1, nq), axis=0, return_counts=True)
+    right = {tuple(q): c for q, c in zip(rq, rc)}
+    return int(sum(min(c, right.get(tuple(q), 0)) for q, c in zip(lq, lc)))
+
+
 def _distinct_qn(lqn):
     """The reference iterates `set([tuple(t) for t in lqn])` (svd_qn.py:140); a set's layout depends
     only on the sequence of DISTINCT insertions, so inserting the first occurrences in order gives
