@@ -102,13 +102,19 @@ int rn_env_update(void* stream, int cplx, int domain, const void* env, int Ea, i
  *   rn_qr : A = Q R,  Q (m x k) orthonormal columns, R (k x n) upper trapezoidal (LAPACK signs)
  *   rn_lq : A = L Q,  L (m x k) lower trapezoidal,   Q (k x n) orthonormal rows
  *   rn_svd_jacobi : A = U diag(S) Vh, U (m x k), Vh (k x n); S is NOT sorted; *sweeps_out (host
- *                   int, may be NULL) receives the number of Jacobi sweeps. */
+ *                   int, may be NULL) receives the number of Jacobi sweeps.  The bare iteration.
+ *   rn_svd        : the same decomposition, QR-preconditioned (norm-ordered QR, QR of R^H, Jacobi
+ *                   on the k x k factor): what scipy.linalg.svd(..., lapack_driver="gesdd") is
+ *                   replaced by in optimized_svd (svd_qn.py:13-49) for every block that is not
+ *                   tiny; `path` selects the GEMM path of the two back-multiplications. */
 int rn_qr(void* stream, int cplx, int m, int n, const void* A, long lda, void* Q, long ldq,
           void* R, long ldr);
 int rn_lq(void* stream, int cplx, int m, int n, const void* A, long lda, void* L, long ldl,
           void* Q, long ldq);
 int rn_svd_jacobi(void* stream, int cplx, int m, int n, const void* A, long lda, void* U,
                   long ldu, double* S, void* Vh, long ldvh, int max_sweeps, int* sweeps_out);
+int rn_svd(void* stream, int cplx, int m, int n, const void* A, long lda, void* U, long ldu,
+           double* S, void* Vh, long ldvh, int max_sweeps, int path, int* sweeps_out);
 
 /* ---- Krylov / Davidson vector kernels -------------------------------------------------------
  * (renormalizer/lib/krylov/krylov.py:55-83, renormalizer/lib/davidson/davidson.py:56-70,493-500)

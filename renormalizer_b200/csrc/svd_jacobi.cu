@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "rn_b200.h"
 #include "internal.cuh"
+#include <algorithm>
+#include <vector>
 
 namespace rn {
 
@@ -373,26 +375,15 @@ __global__ void jacobi_eye_kernel(typename std::conditional<CPLX, double2, doubl
   }
 }
 
-// Economic SVD of A (m x n row-major, lda): U (m x k, ldu), S (k), Vh (k x n, ldvh), k = min(m,n).
-// Singular values are NOT sorted.  Returns the number of sweeps in *sweeps_out (host int).
+// Jacobi iteration on nt columns of length mt held as rows of At (ldt); on return row c of At is the
+// normalised left vector u_c, S[c] its singular value and row c of Vw (nt x nt, ldv) column c of V.
 template <bool CPLX>
-static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, void* U, long ldu,
-                      double* S, void* Vh, long ldvh, int max_sweeps, int* sweeps_out) {
+static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditional<CPLX, double2, double>::type* At,
+                       long ldt, typename std::conditional<CPLX, double2, double>::type* Vw, long ldv,
+                       double* S, int max_sweeps, int* sweeps_out) {
   using T = typename std::conditional<CPLX, double2, double>::type;
-  const int es = CPLX ? 2 : 1;
-  const bool wide = m < n;
-  const int mt = wide ? n : m;   // tall problem: mt x nt
-  const int nt = wide ? m : n;
-  const long ldt = mt, ldv = nt;
-  T *At = nullptr, *Vw = nullptr;
   int* flag = nullptr;
-  RN_CHECK(cudaMallocAsync((void**)&At, sizeof(T) * (size_t)nt * ldt, st));
-  RN_CHECK(cudaMallocAsync((void**)&Vw, sizeof(T) * (size_t)nt * ldv, st));
   RN_CHECK(cudaMallocAsync((void**)&flag, sizeof(int), st));
-  int err;
-  if (!wide) err = launch_pack(st, CPLX, 0, 0, n, m, A, 1, lda, (double*)At, ldt * es);   // At = A^T
-  else err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, m, n, A, lda, 1, (double*)At, ldt * es);  // At = conj(A)
-  if (err) return err;
   int nbe = (int)ceil_div((long)nt * nt, 256);
   if (nbe > 1184) nbe = 1184;
   { RN_LAUNCH(jacobi_eye_kernel<CPLX>, nbe, 256, 0, st, Vw, nt, ldv); rn::g_launches++; }
@@ -435,9 +426,10 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
                     ldt, ldv, round, NB, nb, rps_x, rps_v, Jg, pair_rot);
           rn::g_launches += 3;
         }
-      } else
-      for (int round = 0; round < N - 1; ++round)
-        { RN_LAUNCH(jacobi_round_kernel<CPLX>, N / 2, J_THREADS, 0, st, At, Vw, mt, nt, nt, ldt, ldv, round, N, tol, flag); rn::g_launches++; }
+      } else {
+        for (int round = 0; round < N - 1; ++round)
+          { RN_LAUNCH(jacobi_round_kernel<CPLX>, N / 2, J_THREADS, 0, st, At, Vw, mt, nt, nt, ldt, ldv, round, N, tol, flag); rn::g_launches++; }
+      }
       RN_LAUNCH_CHECK();
       int h = 0;
       RN_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -448,6 +440,32 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
   if (sweeps_out) *sweeps_out = sweeps;
   { RN_LAUNCH(jacobi_finalize_kernel<CPLX>, nt, J_THREADS, 0, st, At, mt, ldt, S); rn::g_launches++; }
   RN_LAUNCH_CHECK();
+  RN_CHECK(cudaFreeAsync(flag, st));
+  if (Gp) RN_CHECK(cudaFreeAsync(Gp, st));
+  if (Jg) RN_CHECK(cudaFreeAsync(Jg, st));
+  if (pair_rot) RN_CHECK(cudaFreeAsync(pair_rot, st));
+  return 0;
+}
+
+// Economic SVD of A (m x n row-major, lda): U (m x k, ldu), S (k), Vh (k x n, ldvh), k = min(m,n).
+// Singular values are NOT sorted.  Returns the number of sweeps in *sweeps_out (host int).
+template <bool CPLX>
+static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, void* U, long ldu,
+                      double* S, void* Vh, long ldvh, int max_sweeps, int* sweeps_out) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  const int es = CPLX ? 2 : 1;
+  const bool wide = m < n;
+  const int mt = wide ? n : m;   // tall problem: mt x nt
+  const int nt = wide ? m : n;
+  const long ldt = mt, ldv = nt;
+  T *At = nullptr, *Vw = nullptr;
+  RN_CHECK(cudaMallocAsync((void**)&At, sizeof(T) * (size_t)nt * ldt, st));
+  RN_CHECK(cudaMallocAsync((void**)&Vw, sizeof(T) * (size_t)nt * ldv, st));
+  int err;
+  if (!wide) err = launch_pack(st, CPLX, 0, 0, n, m, A, 1, lda, (double*)At, ldt * es);   // At = A^T
+  else err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, m, n, A, lda, 1, (double*)At, ldt * es);  // At = conj(A)
+  if (err) return err;
+  if ((err = jacobi_core<CPLX>(st, mt, nt, At, ldt, Vw, ldv, S, max_sweeps, sweeps_out))) return err;
   if (!wide) {
     // U[r][c] = At[c][r];  Vh[c][j] = conj(V[j][c]) = conj(Vw[c][j])
     err = launch_pack(st, CPLX, 0, 0, m, nt, At, 1, ldt, (double*)U, ldu * es);
@@ -462,10 +480,152 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
   if (err) return err;
   RN_CHECK(cudaFreeAsync(At, st));
   RN_CHECK(cudaFreeAsync(Vw, st));
-  RN_CHECK(cudaFreeAsync(flag, st));
-  if (Gp) RN_CHECK(cudaFreeAsync(Gp, st));
-  if (Jg) RN_CHECK(cudaFreeAsync(Jg, st));
-  if (pair_rot) RN_CHECK(cudaFreeAsync(pair_rot, st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Preconditioned SVD (Drmac & Veselic, SIAM J. Matrix Anal. Appl. 29, 1322): with T the tall
+// orientation of A (T = A or A^H, mt x k) and P the ordering of T's columns by decreasing norm,
+//     T P = Q1 R1,   R1^H = Q2 R2,   X = R2^H = Ux S Vx^H  (Jacobi on the k x k factor)
+//     =>  T P = (Q1 Ux) S (Q2 Vx)^H.
+// Bond matrices of a converged state are strongly graded; the bare iteration on T does not converge
+// in 40 sweeps on them and loses the orthogonality of the vectors of the small singular values,
+// while X needs 6-9 sweeps over columns of length k.
+template <bool CPLX>
+__global__ void __launch_bounds__(J_THREADS)
+col_norm2_kernel(const typename std::conditional<CPLX, double2, double>::type* __restrict__ At, int m, long ldt,
+                 double* __restrict__ out) {
+  pdl_wait();
+  __shared__ double scratch[32];
+  const auto* x = At + (long)blockIdx.x * ldt;
+  double ss[1] = {0.0};
+  for (int r = threadIdx.x; r < m; r += blockDim.x) {
+    if constexpr (CPLX) { const double2 a = x[r]; ss[0] += a.x * a.x + a.y * a.y; }
+    else { const double a = x[r]; ss[0] += a * a; }
+  }
+  block_sum<1>(ss, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = ss[0];
+}
+
+// dst[r * ldd + j] = src[perm[j] * lds + r]   (rows of `src` gathered and transposed), 32 x 32 tiles
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+gather_rows_t_kernel(const typename std::conditional<CPLX, double2, double>::type* __restrict__ src, long lds,
+                     const int* __restrict__ perm, int nrows_src, int len,
+                     typename std::conditional<CPLX, double2, double>::type* __restrict__ dst, long ldd) {
+  pdl_wait();
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  __shared__ T tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j0 = blockIdx.y * 32, r0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + ty + 8 * i, r = r0 + tx;
+    if (j < nrows_src && r < len) tile[ty + 8 * i][tx] = src[(long)perm[j] * lds + r];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, j = j0 + tx;
+    if (j < nrows_src && r < len) dst[(long)r * ldd + j] = tile[tx][ty + 8 * i];
+  }
+}
+
+// mode 0: dst[c * ldd + perm[j]] = conj(src[j * k + c])   (Vh of a tall problem)
+// mode 1: dst[perm[j] * ldd + c] = src[j * k + c]         (U of a wide problem)
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+perm_scatter_kernel(const typename std::conditional<CPLX, double2, double>::type* __restrict__ src, int k,
+                    const int* __restrict__ perm, int mode,
+                    typename std::conditional<CPLX, double2, double>::type* __restrict__ dst, long ldd) {
+  pdl_wait();
+  const long total = (long)k * k;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int j, c;
+    if (mode == 0) { c = (int)(i / k); j = (int)(i % k); }     // consecutive threads: consecutive j
+    else { j = (int)(i / k); c = (int)(i % k); }
+    auto v = src[(long)j * k + c];
+    if (mode == 0) {
+      if constexpr (CPLX) v.y = -v.y;
+      dst[(long)c * ldd + perm[j]] = v;
+    } else {
+      dst[(long)perm[j] * ldd + c] = v;
+    }
+  }
+}
+
+template <bool CPLX>
+static int svd_precond_driver(cudaStream_t st, int m, int n, const void* A, long lda, void* U, long ldu,
+                              double* S, void* Vh, long ldvh, int max_sweeps, int path, int* sweeps_out) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  const int es = CPLX ? 2 : 1;
+  const bool wide = m < n;
+  const int mt = wide ? n : m, k = wide ? m : n;
+  T *Tt = nullptr, *Ts = nullptr, *Q1 = nullptr, *R1 = nullptr, *B = nullptr, *Q2 = nullptr, *R2 = nullptr,
+    *Vw = nullptr, *W = nullptr, *UT = nullptr;
+  double* nrm = nullptr;
+  int* perm = nullptr;
+  const size_t tall = sizeof(T) * (size_t)mt * k, sq = sizeof(T) * (size_t)k * k;
+  RN_CHECK(cudaMallocAsync((void**)&Tt, tall, st));
+  RN_CHECK(cudaMallocAsync((void**)&Ts, tall, st));
+  RN_CHECK(cudaMallocAsync((void**)&Q1, tall, st));
+  RN_CHECK(cudaMallocAsync((void**)&UT, tall, st));
+  RN_CHECK(cudaMallocAsync((void**)&R1, sq, st));
+  RN_CHECK(cudaMallocAsync((void**)&B, sq, st));
+  RN_CHECK(cudaMallocAsync((void**)&Q2, sq, st));
+  RN_CHECK(cudaMallocAsync((void**)&R2, sq, st));
+  RN_CHECK(cudaMallocAsync((void**)&Vw, sq, st));
+  RN_CHECK(cudaMallocAsync((void**)&W, sq, st));
+  RN_CHECK(cudaMallocAsync((void**)&nrm, sizeof(double) * k, st));
+  RN_CHECK(cudaMallocAsync((void**)&perm, sizeof(int) * k, st));
+  int err;
+  // Tt[c][r] = T[r][c]: rows of Tt are the columns of the tall orientation
+  if (!wide) err = launch_pack(st, CPLX, 0, 0, n, m, A, 1, lda, (double*)Tt, (long)mt * es);
+  else err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, m, n, A, lda, 1, (double*)Tt, (long)mt * es);
+  if (err) return err;
+  { RN_LAUNCH(col_norm2_kernel<CPLX>, k, J_THREADS, 0, st, Tt, mt, (long)mt, nrm); rn::g_launches++; }
+  RN_LAUNCH_CHECK();
+  {
+    std::vector<double> hn(k);
+    std::vector<int> hp(k);
+    RN_CHECK(cudaMemcpyAsync(hn.data(), nrm, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+    RN_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < k; ++i) hp[i] = i;
+    std::stable_sort(hp.begin(), hp.end(), [&](int a, int b) { return hn[a] > hn[b]; });
+    RN_CHECK(cudaMemcpyAsync(perm, hp.data(), sizeof(int) * k, cudaMemcpyHostToDevice, st));
+    RN_CHECK(cudaStreamSynchronize(st));          // hp goes out of scope
+  }
+  // Ts = T P (row-major mt x k)
+  { RN_LAUNCH(gather_rows_t_kernel<CPLX>, dim3((unsigned)ceil_div(mt, 32), (unsigned)ceil_div(k, 32)), 256, 0, st,
+              Tt, (long)mt, perm, k, mt, Ts, (long)k); rn::g_launches++; }
+  RN_LAUNCH_CHECK();
+  if ((err = rn_qr(st, CPLX, mt, k, Ts, k, Q1, k, R1, k))) return err;                       // T P = Q1 R1
+  if ((err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, k, k, R1, 1, k, (double*)B, (long)k * es))) return err;   // B = R1^H
+  if ((err = rn_qr(st, CPLX, k, k, B, k, Q2, k, R2, k))) return err;                         // R1^H = Q2 R2
+  // columns of X = R2^H are the conjugated rows of R2: Xt = conj(R2), same layout
+  T* Xt = R2;
+  if (CPLX) { if ((err = launch_pack(st, 1, 0, 1, k, k, R2, k, 1, (double*)B, (long)k * es))) return err; Xt = B; }
+  if ((err = jacobi_core<CPLX>(st, k, k, Xt, (long)k, Vw, (long)k, S, max_sweeps, sweeps_out))) return err;
+  // U_T = Q1 Ux, Ux[r][c] = Xt[c][r];   V_Ts = Q2 Vx, Vx[r][c] = Vw[c][r]
+  if ((err = launch_pack(st, CPLX, 0, 0, k, k, Xt, 1, k, (double*)W, (long)k * es))) return err;
+  T* ut_out = (!wide && ldu == k) ? (T*)U : UT;
+  if ((err = rn_matmul(st, CPLX, mt, k, k, Q1, W, ut_out, path))) return err;
+  if ((err = launch_pack(st, CPLX, 0, 0, k, k, Vw, 1, k, (double*)W, (long)k * es))) return err;
+  if ((err = rn_matmul(st, CPLX, k, k, k, Q2, W, R1, path))) return err;                      // R1 <- V_Ts
+  int nbs = (int)ceil_div((long)k * k, 256);
+  if (nbs > 1184) nbs = 1184;
+  if (!wide) {
+    if (ut_out != (T*)U && (err = launch_pack(st, CPLX, 0, 0, m, k, UT, k, 1, (double*)U, ldu * es))) return err;
+    { RN_LAUNCH(perm_scatter_kernel<CPLX>, nbs, 256, 0, st, R1, k, perm, 0, (T*)Vh, ldvh); rn::g_launches++; }
+  } else {
+    // A = T^H = V_T S U_T^H:  U[perm[j]][c] = V_Ts[j][c];  Vh[c][r] = conj(U_T[r][c])
+    { RN_LAUNCH(perm_scatter_kernel<CPLX>, nbs, 256, 0, st, R1, k, perm, 1, (T*)U, ldu); rn::g_launches++; }
+    if ((err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, k, mt, UT, 1, k, (double*)Vh, ldvh * es))) return err;
+  }
+  RN_LAUNCH_CHECK();
+  for (void* ptr : {(void*)Tt, (void*)Ts, (void*)Q1, (void*)UT, (void*)R1, (void*)B, (void*)Q2, (void*)R2, (void*)Vw,
+                    (void*)W, (void*)nrm, (void*)perm})
+    RN_CHECK(cudaFreeAsync(ptr, st));
   return 0;
 }
 
@@ -480,4 +640,14 @@ extern "C" int rn_svd_jacobi(void* stream, int cplx, int m, int n, const void* A
                                      max_sweeps, sweeps_out)
               : rn::svd_driver<false>((cudaStream_t)stream, m, n, A, lda, U, ldu, S, Vh, ldvh,
                                       max_sweeps, sweeps_out);
+}
+
+extern "C" int rn_svd(void* stream, int cplx, int m, int n, const void* A, long lda, void* U, long ldu,
+                      double* S, void* Vh, long ldvh, int max_sweeps, int path, int* sweeps_out) {
+  if (m <= 0 || n <= 0) return 0;
+  if (max_sweeps <= 0) max_sweeps = 40;
+  return cplx ? rn::svd_precond_driver<true>((cudaStream_t)stream, m, n, A, lda, U, ldu, S, Vh, ldvh,
+                                             max_sweeps, path, sweeps_out)
+              : rn::svd_precond_driver<false>((cudaStream_t)stream, m, n, A, lda, U, ldu, S, Vh, ldvh,
+                                              max_sweeps, path, sweeps_out);
 }

@@ -304,31 +304,6 @@ def qr(a, lq=False):
     return l, q
 
 
-def _svd_jacobi(a, max_sweeps=40):
-    """rn_svd_jacobi on a 2-D device tensor: (U, S, Vh), S not sorted."""
-    lib = _lib.get()
-    a = a.contiguous()
-    _check_dev(a)
-    m, n = a.shape
-    k = min(m, n)
-    cplx = _is_cplx(a)
-    u = torch.empty((m, k), dtype=a.dtype, device=a.device)
-    s = torch.empty((k,), dtype=torch.float64, device=a.device)
-    vh = torch.empty((k, n), dtype=a.dtype, device=a.device)
-    sweeps = ctypes.c_int(0)
-    check(lib.rn_svd_jacobi(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(u), k, _ptr(s), _ptr(vh), n,
-                            max_sweeps, ctypes.byref(sweeps)), "rn_svd_jacobi")
-    nn = (k + 1) // 2 * 2
-    LaunchCounter.add(sweeps.value * max(nn - 1, 0) + 5)
-    svd.last_sweeps = sweeps.value
-    return u, s, vh
-
-
-def _ct(x):
-    """Conjugate transpose as a contiguous tensor."""
-    return x.conj().transpose(0, 1).contiguous()
-
-
 # below this many columns the bare Jacobi iteration is cheaper than the two QR factorisations
 SVD_PRECONDITION_MIN = 48
 
@@ -336,33 +311,31 @@ SVD_PRECONDITION_MIN = 48
 def svd(a, max_sweeps=40, sort=True, precondition=None):
     """SVD of a bond-matrix block; returns (U, S, Vh) with S sorted descending when sort.
 
-    One-sided Jacobi, preconditioned as in Drmac & Veselic (SIAM J. Matrix Anal. Appl. 29, 1322):
-    the columns of the tall orientation T are ordered by decreasing norm, T P = Q1 R1, R1^H = Q2 R2,
-    and the Jacobi rotations run on X = R2^H (k x k) instead of T.  Bond matrices of a converged
-    state are strongly graded (singular values decay exponentially); on those the bare iteration
-    needs > 40 sweeps over the long columns of T while X needs 6-8 sweeps over columns of length k.
-    T = Q1 Vx S (P Q2 Ux)^H with X = Ux S Vx^H."""
+    rn_svd: one-sided Jacobi, preconditioned as in Drmac & Veselic (SIAM J. Matrix Anal. Appl. 29,
+    1322): the columns of the tall orientation T are ordered by decreasing norm, T P = Q1 R1,
+    R1^H = Q2 R2, and the (block) Jacobi rotations run on X = R2^H (k x k) instead of T.  Bond
+    matrices of a converged state are strongly graded (singular values decay exponentially); on
+    those the bare iteration (rn_svd_jacobi, `precondition=False`) needs > 40 sweeps over the long
+    columns of T while X needs 6-9 sweeps over columns of length k."""
+    lib = _lib.get()
     a = a.contiguous()
+    _check_dev(a)
     m, n = a.shape
+    k = min(m, n)
+    cplx = _is_cplx(a)
     if precondition is None:
-        precondition = min(m, n) >= SVD_PRECONDITION_MIN
-    if not precondition:
-        u, s, vh = _svd_jacobi(a, max_sweeps)
+        precondition = k >= SVD_PRECONDITION_MIN
+    u = torch.empty((m, k), dtype=a.dtype, device=a.device)
+    s = torch.empty((k,), dtype=torch.float64, device=a.device)
+    vh = torch.empty((k, n), dtype=a.dtype, device=a.device)
+    sweeps = ctypes.c_int(0)
+    if precondition:
+        check(lib.rn_svd(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(u), k, _ptr(s), _ptr(vh), n,
+                         max_sweeps, backend.gemm_path, ctypes.byref(sweeps)), "rn_svd")
     else:
-        wide = m < n
-        t = _ct(a) if wide else a                                    # tall: mt x k
-        order = torch.argsort(torch.linalg.vector_norm(t, dim=0), descending=True)
-        q1, r1 = qr(t.index_select(1, order))                        # T P = Q1 R1
-        q2, r2 = qr(_ct(r1))                                         # R1^H = Q2 R2
-        ux, s, vxh = _svd_jacobi(_ct(r2), max_sweeps)                # X = R2^H = Ux S Vx^H
-        # R1 = R2^H Q2^H = Ux S (Q2 Vx)^H  ->  T P = (Q1 Ux) S (Q2 Vx)^H
-        ut = matmul(q1, ux)
-        vt = torch.empty_like(q2)
-        vt.index_copy_(0, order, matmul(q2, _ct(vxh)))               # rows back to T's column order
-        if wide:                                                     # A = T^H = Vt S Ut^H
-            u, vh = vt, _ct(ut)
-        else:
-            u, vh = ut, _ct(vt)
+        check(lib.rn_svd_jacobi(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(u), k, _ptr(s), _ptr(vh), n,
+                                max_sweeps, ctypes.byref(sweeps)), "rn_svd_jacobi")
+    svd.last_sweeps = sweeps.value
     if sort:
         order = torch.argsort(s, descending=True)
         u, s, vh = u.index_select(1, order), s.index_select(0, order), vh.index_select(0, order)
