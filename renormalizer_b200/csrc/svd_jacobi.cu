@@ -84,9 +84,11 @@ jacobi_round_kernel(typename std::conditional<CPLX, double2, double>::type* __re
 // dot products and once for the rotation.  Here, for every block pair of a round,
 //   1. jb_gram_kernel forms the Gram matrix G = Xc^H Xc of the 32 columns (row slices in parallel,
 //      shared-memory row chunks, 4 entries of G per thread),
-//   2. jb_rotate_kernel runs ONE cyclic sweep of two-sided Jacobi on G in shared memory (31 rounds
-//      x 16 disjoint pairs; thread (i, j) owns the 2x2 sub-block {p_i,q_i} x {p_j,q_j}, so a round
-//      is a rotation set-up by 16 threads and one conflict-free update), accumulating J,
+//   2. jb_rotate_kernel runs ONE cyclic sweep of two-sided Jacobi on G in shared memory (16 disjoint
+//      pairs per round: 31 rounds in the first block round of a sweep, which also rotates the pairs
+//      inside each block, 16 rounds joining the two blocks otherwise; thread (i, j) owns the 2x2
+//      sub-block {p_i,q_i} x {p_j,q_j}, so a round is a rotation set-up by 16 threads and one
+//      conflict-free update), accumulating J,
 //   3. jb_apply_kernel applies Xc <- Xc J and Vc <- Vc J (row slices in parallel).
 // In exact arithmetic this is the scalar algorithm with the pairs visited block by block (the
 // rotation of a pair is computed from a, b, g exactly as above; G is updated by the same rotations
@@ -194,7 +196,7 @@ jb_gram_kernel(const typename std::conditional<CPLX, double2, double>::type* __r
 template <bool CPLX>
 __global__ void __launch_bounds__(JBT)
 jb_rotate_kernel(const typename std::conditional<CPLX, double2, double>::type* __restrict__ Gp, int nslice,
-                 int round, int NB, int nb, double tol,
+                 int round, int NB, int nb, double tol, int full,
                  typename std::conditional<CPLX, double2, double>::type* __restrict__ Jg,
                  int* __restrict__ pair_rot, int* __restrict__ rotated) {
   pdl_wait();
@@ -220,10 +222,15 @@ jb_rotate_kernel(const typename std::conditional<CPLX, double2, double>::type* _
   }
   __syncthreads();
   const int ti = tid >> 4, tj = tid & 15;
-  for (int lr = 0; lr < JK - 1; ++lr) {
+  // full: all 496 pairs of the 32 columns (31 rounds).  Otherwise only the 256 pairs that join the
+  // two blocks (16 rounds): the pairs inside a block are rotated once per sweep, in its first round,
+  // where every block takes part in exactly one block pair.
+  const int nrounds = full ? JK - 1 : JB;
+  for (int lr = 0; lr < nrounds; ++lr) {
     if (tid < JB) {
       int p, q;
-      if (tid == 0) { p = JK - 1; q = lr; }
+      if (!full) { p = tid; q = JB + ((tid + lr) & (JB - 1)); }
+      else if (tid == 0) { p = JK - 1; q = lr; }
       else { p = (lr + tid) % (JK - 1); q = (lr - tid + (JK - 1)) % (JK - 1); }
       if (p > q) { const int t = p; p = q; q = t; }
       const double a = jb_real(G[p * JK + p]), b = jb_real(G[q * JK + q]);
@@ -421,7 +428,8 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
       if (blocked) {
         for (int round = 0; round < NB - 1; ++round) {
           RN_LAUNCH(jb_gram_kernel<CPLX>, dim3(NB / 2, ns_x), JBT, 0, st, At, mt, nt, ldt, round, NB, nb, rps_x, Gp);
-          RN_LAUNCH(jb_rotate_kernel<CPLX>, NB / 2, JBT, 0, st, Gp, ns_x, round, NB, nb, tol, Jg, pair_rot, flag);
+          RN_LAUNCH(jb_rotate_kernel<CPLX>, NB / 2, JBT, 0, st, Gp, ns_x, round, NB, nb, tol, round == 0 ? 1 : 0, Jg,
+                    pair_rot, flag);
           RN_LAUNCH(jb_apply_kernel<CPLX>, dim3(NB / 2, ns_x > ns_v ? ns_x : ns_v, 2), JBT, 0, st, At, Vw, mt, nt, nt,
                     ldt, ldv, round, NB, nb, rps_x, rps_v, Jg, pair_rot);
           rn::g_launches += 3;
