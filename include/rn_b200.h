@@ -164,6 +164,10 @@ int rn_env_update_host(int cplx, int domain, const void* env, int Ea, int Eb, in
                        const void* bra, const void* ket, int d, int g, int Mf, int Mh,
                        const double* W, int Wb, int Wf, void* out, int path);
 
+/* scipy.linalg.svd(a, full_matrices=False) of optimized_svd (renormalizer/mps/svd_qn.py:13-49) with
+ * HOST buffers: A (m x n) row-major in, U (m x k), S (k, descending), Vh (k x n) out. */
+int rn_svd_host(int cplx, int m, int n, const void* A, void* U, double* S, void* Vh, int path);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------
  * Between rn_profile_begin and rn_profile_end every contraction GEMM launch is bracketed by CUDA
  * events on its own stream; rn_profile_end returns the summed launch time, the summed

@@ -36,6 +36,7 @@ SIGNATURES = {
     "rn_qr": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _l]),
     "rn_lq": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _l]),
     "rn_svd_jacobi": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _vp, _l, _i, POINTER(_i)]),
+    "rn_svd_host": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i]),
     "rn_svd": (_i, [_vp, _i, _i, _i, _vp, _l, _vp, _l, _vp, _vp, _l, _i, _i, POINTER(_i)]),
     "rn_multi_dot": (_i, [_vp, _i, _l, _i, _vp, _l, _vp, _vp, _vp]),
     "rn_lanczos_update": (_i, [_vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1,5 +1,7 @@
 // Library bring-up and the host-buffer entry points (copy in, run the device path, copy out).
 #include "common.cuh"
+#include <algorithm>
+#include <string.h>
 #include "rn_b200.h"
 #include "internal.cuh"
 
@@ -140,5 +142,43 @@ extern "C" int rn_env_update_host(int cplx, int domain, const void* env, int Ea,
   free_csr(st, c);
   cudaFreeAsync(dE, st); cudaFreeAsync(dB, st); cudaFreeAsync(dK, st); cudaFreeAsync(dO, st);
   RN_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// scipy.linalg.svd(a, full_matrices=False) for a HOST matrix (optimized_svd, svd_qn.py:13-49):
+// upload, rn_svd, download; the singular values come back sorted (descending) like LAPACK's.
+extern "C" int rn_svd_host(int cplx, int m, int n, const void* A, void* U, double* S, void* Vh, int path) {
+  if (m <= 0 || n <= 0) return 0;
+  cudaStream_t st = 0;
+  const size_t eb = cplx ? 16 : 8;
+  const int k = m < n ? m : n;
+  void *dA, *dU, *dV;
+  double* dS;
+  int err;
+  if ((err = to_device(st, A, eb * (size_t)m * n, &dA))) return err;
+  RN_CHECK(cudaMallocAsync(&dU, eb * (size_t)m * k, st));
+  RN_CHECK(cudaMallocAsync(&dV, eb * (size_t)k * n, st));
+  RN_CHECK(cudaMallocAsync((void**)&dS, sizeof(double) * k, st));
+  if (k >= 48) err = rn_svd(st, cplx, m, n, dA, n, dU, k, dS, dV, n, 40, path, nullptr);
+  else err = rn_svd_jacobi(st, cplx, m, n, dA, n, dU, k, dS, dV, n, 40, nullptr);
+  if (err) return err;
+  std::vector<char> hu(eb * (size_t)m * k), hv(eb * (size_t)k * n);
+  std::vector<double> hs(k);
+  RN_CHECK(cudaMemcpyAsync(hu.data(), dU, hu.size(), cudaMemcpyDeviceToHost, st));
+  RN_CHECK(cudaMemcpyAsync(hv.data(), dV, hv.size(), cudaMemcpyDeviceToHost, st));
+  RN_CHECK(cudaMemcpyAsync(hs.data(), dS, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+  cudaFreeAsync(dA, st); cudaFreeAsync(dU, st); cudaFreeAsync(dV, st); cudaFreeAsync(dS, st);
+  RN_CHECK(cudaStreamSynchronize(st));
+  std::vector<int> order(k);
+  for (int i = 0; i < k; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hs[a] > hs[b]; });
+  char* uo = (char*)U;
+  char* vo = (char*)Vh;
+  for (int j = 0; j < k; ++j) {
+    S[j] = hs[order[j]];
+    memcpy(vo + eb * (size_t)j * n, hv.data() + eb * (size_t)order[j] * n, eb * (size_t)n);
+    for (int r = 0; r < m; ++r)
+      memcpy(uo + eb * ((size_t)r * k + j), hu.data() + eb * ((size_t)r * k + order[j]), eb);
+  }
   return 0;
 }

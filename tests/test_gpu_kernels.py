@@ -267,6 +267,31 @@ def test_host_buffer_entry_points(golden):
             assert relerr(out, g[f"{t}_{name}"]) < TOL
 
 
+@pytest.mark.parametrize("cplx", [0, 1])
+@pytest.mark.parametrize("m,n", [(20, 12), (90, 200), (260, 130)])
+def test_svd_host_entry_point(cplx, m, n):
+    """rn_svd_host: the scipy.linalg.svd(a, full_matrices=False) call of optimized_svd
+    (svd_qn.py:13-49) with NumPy buffers -- sorted singular values, A = U S Vh."""
+    import ctypes
+    from renormalizer_b200 import _lib
+    lib = _lib.get()
+    rng = np.random.default_rng(m + n + cplx)
+    k = min(m, n)
+    u0, _, v0 = np.linalg.svd(rnd(rng, (m, n), bool(cplx)), full_matrices=False)
+    s0 = np.exp(-0.1 * np.arange(k))
+    a = np.ascontiguousarray((u0 * s0) @ v0)
+    u = np.zeros((m, k), dtype=a.dtype)
+    s = np.zeros(k)
+    vh = np.zeros((k, n), dtype=a.dtype)
+    p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    assert lib.rn_svd_host(cplx, m, n, p(a), p(u), p(s), p(vh), 1) == 0
+    assert np.all(np.diff(s) <= 0)
+    assert np.abs(s - np.linalg.svd(a, compute_uv=False)).max() < 1e-13
+    assert relerr((u * s) @ vh, a) < 1e-12
+    assert np.abs(u.conj().T @ u - np.eye(k)).max() < 1e-11
+    assert np.abs(vh @ vh.conj().T - np.eye(k)).max() < 1e-11
+
+
 @pytest.mark.parametrize("m,n,k", [(128, 128, 128), (1, 1, 1), (100, 37, 50), (256, 384, 1000),
                                    (300, 130, 129), (768, 4096, 512), (2048, 512, 1536)])
 @pytest.mark.parametrize("nslices", [7, 8])
