@@ -252,7 +252,7 @@ def run_ours(args):
     from renormalizer_b200.mps import Mps
     from renormalizer_b200.gs import single_sweep
     from renormalizer_b200.lib import Environ
-    from renormalizer_b200.configs import CompressConfig, CompressCriteria
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig, EvolveMethod
     _lib.get()
     backend.gemm_path = args.path
 
@@ -263,7 +263,9 @@ def run_ours(args):
     mpo = Mpo(mpo_host)
 
     def fresh_mps(sites):
-        return Mps(sites, meta["qn"], meta["sigmaqn"], meta["qntot"], meta["qnidx"], meta["to_right"])
+        m = Mps(sites, meta["qn"], meta["sigmaqn"], meta["qntot"], meta["qnidx"], meta["to_right"])
+        m.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps)       # the workload's integrator
+        return m
 
     state = {"mps": fresh_mps(work["sites"])}
     if work["kind"] == "dmrg":

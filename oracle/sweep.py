@@ -590,3 +590,153 @@ def evolve_tdvp_ps2(mps_in, mpo, dt, m_max, normalize=True, stats=None):
     if normalize:
         mps.normalize_mps_only()
     return mps
+
+
+# ------------------------------------------------------------------------------------------------
+# Propagate-and-compress, the default integrator of Mps.evolve
+# ------------------------------------------------------------------------------------------------
+class Mpo:
+    """MPO site tensors with the quantum numbers Mpo.apply needs.  Reference: mps/mpo.py:221-329."""
+
+    def __init__(self, sites, qn, qntot, qnidx):
+        self.sites = [np.asarray(s) for s in sites]
+        self.qn = [np.asarray(q) for q in qn]
+        self.qntot = np.asarray(qntot)
+        self.qnidx = int(qnidx)
+
+    def __len__(self):
+        return len(self.sites)
+
+    def __getitem__(self, i):
+        return self.sites[i]
+
+
+class CompressSpec:
+    """The part of CompressConfig the truncation reads.  Reference: utils/configs.py:128-220."""
+
+    def __init__(self, criteria="threshold", threshold=1e-3, max_bonddim=32):
+        self.criteria, self.threshold, self.max_bonddim = criteria, threshold, max_bonddim
+
+    def both(self):
+        """mps.py:808-811: a threshold criterion is tightened to `both` while contracting."""
+        return CompressSpec("both", self.threshold, self.max_bonddim) if self.criteria == "threshold" else self
+
+    def m_trunc(self, sigma):
+        thr = m_trunc_threshold(sigma, self.threshold)
+        fix = m_trunc_fixed(sigma, self.max_bonddim)
+        return {"threshold": thr, "fixed": fix, "both": min(thr, fix)}[self.criteria]
+
+
+def mps_scale(mps, val, inplace=False):
+    """mp.py:983-994: multiply the site at the quantum-number centre."""
+    new = mps if inplace else mps.copy()
+    if np.iscomplex(val):
+        new.sites = [s.astype(np.complex128) for s in new.sites]
+    else:
+        val = np.real(val)
+    new.sites[new.qnidx] = new.sites[new.qnidx] * val
+    return new
+
+
+def mpo_apply(mpo, mps):
+    """mpo @ mps without compression.  Reference: mps/mpo.py:331-389."""
+    new = mps.copy()
+    for i, (w, a) in enumerate(zip(mpo.sites, mps.sites)):
+        if a.ndim == 3:      # "apqb,cqd->acpbd"
+            mt = np.moveaxis(np.tensordot(w, a, axes=([2], [1])), 3, 1)
+            new.sites[i] = mt.reshape(w.shape[0] * a.shape[0], w.shape[1], w.shape[-1] * a.shape[-1])
+        else:                # "apqb,cqrd->acprbd"
+            mt = np.moveaxis(np.tensordot(w, a, axes=([2], [1])), [-3, -2], [1, 3])
+            new.sites[i] = mt.reshape(w.shape[0] * a.shape[0], w.shape[1], a.shape[2],
+                                      w.shape[-1] * a.shape[-1])
+    orig = new.qnidx
+    new.move_qnidx(mpo.qnidx)
+    nq = len(new.qntot)
+    new.qn = [add_outer(np.array(qo), np.array(qm)).reshape(-1, nq) for qo, qm in zip(mpo.qn, new.qn)]
+    new.qntot = new.qntot + mpo.qntot
+    new.move_qnidx(orig)
+    return new
+
+
+def mps_add(a, b):
+    """Direct sum of two MPS / MPDM.  Reference: mp.py:374-436 (equal coeff, mps.py:1802-1808)."""
+    assert np.all(a.qntot == b.qntot) and len(a) == len(b) and np.allclose(a.coeff, b.coeff)
+    cplx = any(np.iscomplexobj(s) for s in a.sites + b.sites)
+    dt = np.complex128 if cplx else np.float64
+    n = len(a)
+    new = a.copy()
+    for i, (x, y) in enumerate(zip(a.sites, b.sites)):
+        if i == 0:
+            new.sites[i] = np.concatenate([x, y], axis=-1).astype(dt)
+        elif i == n - 1:
+            new.sites[i] = np.concatenate([x, y], axis=0).astype(dt)
+        else:
+            t = np.zeros((x.shape[0] + y.shape[0],) + x.shape[1:-1] + (x.shape[-1] + y.shape[-1],), dtype=dt)
+            t[:x.shape[0], ..., :x.shape[-1]] = x
+            t[x.shape[0]:, ..., x.shape[-1]:] = y
+            new.sites[i] = t
+    new.move_qnidx(b.qnidx)
+    new.to_right = b.to_right
+    new.qn = [np.concatenate([q1, q2]) for q1, q2 in zip(new.qn, b.qn)]
+    new.qn[0] = np.zeros((1, new.qn[0].shape[1]), dtype=int)
+    new.qn[-1] = np.zeros((1, new.qn[0].shape[1]), dtype=int)
+    return new
+
+
+def compress(mps, spec):
+    """SVD truncation sweep of a canonicalised MPS, in place.  Reference: mp.py:437-511 with
+    _update_ms (mp.py:245-295)."""
+    assert mps.qnidx == (0 if mps.to_right else len(mps) - 1)
+    system = "L" if mps.to_right else "R"
+    for idx in mps.iter_idx_list(full=False):
+        shape = mps.sites[idx].shape
+        qnbigl, qnbigr, _ = mps.big_qn([idx])
+        u, sigma, qnlset, v, sigma, qnrset = svd_qn(mps.sites[idx], qnbigl, qnbigr, mps.qntot,
+                                                    system=system, full_matrices=False)
+        vt = v.T
+        m = min(spec.m_trunc(sigma), len(sigma))
+        u, vt, sigma = u[:, :m], vt[:m, :], sigma[:m]
+        if mps.to_right:
+            vt = sigma[:, None] * vt
+            mps.sites[idx + 1] = np.tensordot(vt, mps.sites[idx + 1], axes=1)
+            mps.sites[idx] = u.reshape(shape[:-1] + (m,))
+            mps.qn[idx + 1] = np.array(qnlset[:m])
+            mps.qnidx = idx + 1
+        else:
+            u = u * sigma[None, :]
+            mps.sites[idx - 1] = np.tensordot(mps.sites[idx - 1], u, axes=1)
+            mps.sites[idx] = vt.reshape((m,) + shape[1:])
+            mps.qn[idx] = np.array(qnrset[:m])
+            mps.qnidx = idx - 1
+    mps.switch_direction()
+    return mps
+
+
+def compressed_sum(terms, spec, batchsize=5):
+    """lib.py:417-439."""
+    queue = list(terms)
+    if len(queue) == 1:
+        return compress(queue[0].canonicalise(), spec)
+    while len(queue) != 1:
+        batch, queue = queue[:batchsize], queue[batchsize:]
+        s = batch[0]
+        for t in batch[1:]:
+            s = mps_add(s, t)
+        queue.append(compress(s.canonicalise(), spec))
+    return queue[0]
+
+
+def evolve_prop_and_compress(mps, mpo, dt, spec, order=4, normalize=True):
+    """One step of the propagate-and-compress integrator, fixed step.  Reference: mps.py:796-884
+    (Taylor expansion of exp(-i H dt) to `order`, utils/rk.py:28-34; every H^k psi through
+    Mpo.contract = apply + canonicalise + compress, mpo.py:415-419) and mps.py:657-661."""
+    from math import factorial
+    terms = [mps.copy()]
+    while len(terms) < order + 1:
+        terms.append(compress(mpo_apply(mpo, terms[-1]).canonicalise(), spec.both()))
+    for k, t in enumerate(terms):
+        mps_scale(t, (-1.0j * dt) ** k / factorial(k), inplace=True)
+    new = compressed_sum(terms, spec)
+    if normalize:
+        new.normalize_mps_only()
+    return new

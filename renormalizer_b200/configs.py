@@ -76,6 +76,16 @@ class CompressConfig:
             new.max_dims = self.max_dims.copy()
         return new
 
+    def update(self, other):
+        """configs.py:221-235: the stricter of the two."""
+        if self.criteria != other.criteria:
+            raise ValueError("Can't update configs with different standard")
+        self.threshold = min(self.threshold, other.threshold)
+        if self.max_dims is None:
+            self.max_dims = other.max_dims
+        elif other.max_dims is not None:
+            self.max_dims = np.maximum(self.max_dims, other.max_dims)
+
 
 class OptimizeConfig:
     def __init__(self, procedure=None):
@@ -96,12 +106,15 @@ class OptimizeConfig:
 
 
 class EvolveConfig:
-    def __init__(self, method=EvolveMethod.tdvp_ps, adaptive=False, guess_dt=1e-1,
-                 adaptive_rtol=5e-4, ivp_solver="krylov"):
+    def __init__(self, method=EvolveMethod.prop_and_compress, adaptive=False, guess_dt=1e-1,
+                 adaptive_rtol=5e-4, taylor_order=None, ivp_solver="krylov"):
         if isinstance(method, str):
             method = EvolveMethod[method]
         self.method = method
         self.adaptive = adaptive
+        if taylor_order is None:                    # configs.py:364-368
+            taylor_order = 5 if adaptive else 4
+        self.taylor_order = taylor_order
         self.guess_dt = guess_dt
         self.adaptive_rtol = adaptive_rtol
         self.ivp_solver = ivp_solver
@@ -110,6 +123,15 @@ class EvolveConfig:
     @property
     def is_tdvp(self):
         return self.method is not EvolveMethod.prop_and_compress
+
+    def check_valid_dt(self, evolve_dt):
+        """configs.py:394-402."""
+        info = f"in config: {self.guess_dt}, in arg: {evolve_dt}"
+        if np.iscomplex(evolve_dt) ^ np.iscomplex(self.guess_dt):
+            raise ValueError("real and imag not compatible. " + info)
+        if (np.iscomplex(evolve_dt) and evolve_dt.imag * self.guess_dt.imag < 0) or \
+                (not np.iscomplex(evolve_dt) and evolve_dt * self.guess_dt < 0):
+            raise ValueError("evolve into wrong direction. " + info)
 
     def copy(self):
         new = self.__class__.__new__(self.__class__)

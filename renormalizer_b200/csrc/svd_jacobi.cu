@@ -608,26 +608,41 @@ static int svd_precond_driver(cudaStream_t st, int m, int n, const void* A, long
               Tt, (long)mt, perm, k, mt, Ts, (long)k); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   if ((err = rn_qr(st, CPLX, mt, k, Ts, k, Q1, k, R1, k))) return err;                       // T P = Q1 R1
-  if ((err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, k, k, R1, 1, k, (double*)B, (long)k * es))) return err;   // B = R1^H
-  if ((err = rn_qr(st, CPLX, k, k, B, k, Q2, k, R2, k))) return err;                         // R1^H = Q2 R2
-  // columns of X = R2^H are the conjugated rows of R2: Xt = conj(R2), same layout
-  T* Xt = R2;
-  if (CPLX) { if ((err = launch_pack(st, 1, 0, 1, k, k, R2, k, 1, (double*)B, (long)k * es))) return err; Xt = B; }
-  if ((err = jacobi_core<CPLX>(st, k, k, Xt, (long)k, Vw, (long)k, S, max_sweeps, sweeps_out))) return err;
-  // U_T = Q1 Ux, Ux[r][c] = Xt[c][r];   V_Ts = Q2 Vx, Vx[r][c] = Vw[c][r]
-  if ((err = launch_pack(st, CPLX, 0, 0, k, k, Xt, 1, k, (double*)W, (long)k * es))) return err;
+  static int qr2_on = -1;                   // RN_SVD_QR2=0: one factorisation only, Jacobi on R1^H (diagnostics)
+  if (qr2_on < 0) { const char* e = getenv("RN_SVD_QR2"); qr2_on = (e && e[0] == '0') ? 0 : 1; }
   T* ut_out = (!wide && ldu == k) ? (T*)U : UT;
-  if ((err = rn_matmul(st, CPLX, mt, k, k, Q1, W, ut_out, path))) return err;
-  if ((err = launch_pack(st, CPLX, 0, 0, k, k, Vw, 1, k, (double*)W, (long)k * es))) return err;
-  if ((err = rn_matmul(st, CPLX, k, k, k, Q2, W, R1, path))) return err;                      // R1 <- V_Ts
+  T* VTs = nullptr;                         // right vectors of T P, row-major k x k
+  if (qr2_on) {
+    if ((err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, k, k, R1, 1, k, (double*)B, (long)k * es))) return err;   // B = R1^H
+    if ((err = rn_qr(st, CPLX, k, k, B, k, Q2, k, R2, k))) return err;                       // R1^H = Q2 R2
+    // columns of X = R2^H are the conjugated rows of R2: Xt = conj(R2), same layout
+    T* Xt = R2;
+    if (CPLX) { if ((err = launch_pack(st, 1, 0, 1, k, k, R2, k, 1, (double*)B, (long)k * es))) return err; Xt = B; }
+    if ((err = jacobi_core<CPLX>(st, k, k, Xt, (long)k, Vw, (long)k, S, max_sweeps, sweeps_out))) return err;
+    // U_T = Q1 Ux, Ux[r][c] = Xt[c][r];   V_Ts = Q2 Vx, Vx[r][c] = Vw[c][r]
+    if ((err = launch_pack(st, CPLX, 0, 0, k, k, Xt, 1, k, (double*)W, (long)k * es))) return err;
+    if ((err = rn_matmul(st, CPLX, mt, k, k, Q1, W, ut_out, path))) return err;
+    if ((err = launch_pack(st, CPLX, 0, 0, k, k, Vw, 1, k, (double*)W, (long)k * es))) return err;
+    if ((err = rn_matmul(st, CPLX, k, k, k, Q2, W, R1, path))) return err;                    // R1 <- V_Ts
+    VTs = R1;
+  } else {
+    // X = R1^H = Ux S Vx^H  =>  T P = (Q1 Vx) S Ux^H;  Xt = conj(R1), same layout
+    T* Xt = R1;
+    if (CPLX) { if ((err = launch_pack(st, 1, 0, 1, k, k, R1, k, 1, (double*)B, (long)k * es))) return err; Xt = B; }
+    if ((err = jacobi_core<CPLX>(st, k, k, Xt, (long)k, Vw, (long)k, S, max_sweeps, sweeps_out))) return err;
+    if ((err = launch_pack(st, CPLX, 0, 0, k, k, Vw, 1, k, (double*)W, (long)k * es))) return err;
+    if ((err = rn_matmul(st, CPLX, mt, k, k, Q1, W, ut_out, path))) return err;               // U_T = Q1 Vx
+    if ((err = launch_pack(st, CPLX, 0, 0, k, k, Xt, 1, k, (double*)R2, (long)k * es))) return err;   // V_Ts = Ux
+    VTs = R2;
+  }
   int nbs = (int)ceil_div((long)k * k, 256);
   if (nbs > 1184) nbs = 1184;
   if (!wide) {
     if (ut_out != (T*)U && (err = launch_pack(st, CPLX, 0, 0, m, k, UT, k, 1, (double*)U, ldu * es))) return err;
-    { RN_LAUNCH(perm_scatter_kernel<CPLX>, nbs, 256, 0, st, R1, k, perm, 0, (T*)Vh, ldvh); rn::g_launches++; }
+    { RN_LAUNCH(perm_scatter_kernel<CPLX>, nbs, 256, 0, st, VTs, k, perm, 0, (T*)Vh, ldvh); rn::g_launches++; }
   } else {
     // A = T^H = V_T S U_T^H:  U[perm[j]][c] = V_Ts[j][c];  Vh[c][r] = conj(U_T[r][c])
-    { RN_LAUNCH(perm_scatter_kernel<CPLX>, nbs, 256, 0, st, R1, k, perm, 1, (T*)U, ldu); rn::g_launches++; }
+    { RN_LAUNCH(perm_scatter_kernel<CPLX>, nbs, 256, 0, st, VTs, k, perm, 1, (T*)U, ldu); rn::g_launches++; }
     if ((err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, k, mt, UT, 1, k, (double*)Vh, ldvh * es))) return err;
   }
   RN_LAUNCH_CHECK();

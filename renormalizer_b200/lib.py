@@ -75,3 +75,22 @@ class Environ:
 
     def read(self, domain, siteidx):
         return self._virtual_disk[(domain, siteidx)]
+
+
+def compressed_sum(mps_list, batchsize=5, temp_m_trunc=None):
+    """lib.py:417-439: sum in batches, canonicalise and compress after every batch."""
+    assert len(mps_list) != 0
+    queue = list(mps_list)
+    if len(queue) == 1:
+        new = queue[0].canonicalise()
+        new.compress(temp_m_trunc=temp_m_trunc)
+        return new
+    while len(queue) != 1:
+        batch, queue = queue[:batchsize], queue[batchsize:]
+        s = batch[0]
+        for t in batch[1:]:
+            s = s.add(t)
+        s.canonicalise()
+        s.compress(temp_m_trunc=temp_m_trunc)
+        queue.append(s)
+    return queue[0]

@@ -8,9 +8,15 @@ from .ops import MpoSite
 
 
 class Mpo:
-    def __init__(self, site_tensors, offset=0.0):
+    def __init__(self, site_tensors, offset=0.0, qn=None, qntot=None, qnidx=None):
+        """`qn` (one array per bond), `qntot` and `qnidx` are the operator's quantum numbers
+        (mp.py:34-80); only `apply` / `contract` read them, and an operator that conserves every
+        quantum number (all zero, the default) needs none."""
         self._sites = [w if isinstance(w, MpoSite) else MpoSite(w) for w in site_tensors]
         self.offset = offset
+        self.qn = None if qn is None else [np.asarray(q) for q in qn]
+        self.qntot = None if qntot is None else np.asarray(qntot)
+        self.qnidx = len(self._sites) - 1 if qnidx is None else int(qnidx)
 
     def __len__(self):
         return len(self._sites)
@@ -77,6 +83,46 @@ class Mpo:
     @property
     def nbytes(self):
         return sum(s.array.nbytes for s in self._sites)
+
+    # ---- operator application (propagate-and-compress, mps.py:796-884) ---------------------------
+    def apply(self, mps, canonicalise: bool = False):
+        """mpo @ mps (or @ mpdm) without compression, mpo.py:331-389:
+        new[(a,c), p, (b,d)] = sum_q W[a,p,q,b] A[c,q,d] as one device GEMM per site."""
+        from . import ops
+        from .svd_qn import add_outer
+        assert self.site_num == mps.site_num
+        new = mps.metacopy()
+        for i, (site, a) in enumerate(zip(self._sites, mps)):
+            w = site.dense                                         # (a, p, q, b) on the device
+            wa, wp, wq, wb = w.shape
+            assert wq == a.shape[1]
+            w2 = w.permute(0, 1, 3, 2).reshape(wa * wp * wb, wq)
+            rest = tuple(a.shape[2:-1])                            # () for an MPS, (r,) for an MPDM
+            nrest = int(np.prod(rest)) if rest else 1
+            a2 = a.movedim(1, 0).reshape(wq, a.shape[0] * nrest * a.shape[-1])
+            m = ops.matmul(w2.to(a.dtype) if a.is_complex() else w2, a2)
+            m = m.reshape(wa, wp, wb, a.shape[0], nrest, a.shape[-1]).permute(0, 3, 1, 4, 2, 5)
+            new[i] = m.reshape((wa * a.shape[0], wp) + rest + (wb * a.shape[-1],)).contiguous()
+        nq = len(new.qntot)
+        qn = self.qn if self.qn is not None else [np.zeros((d, nq), dtype=int) for d in self.bond_dims]
+        qntot = self.qntot if self.qntot is not None else np.zeros(nq, dtype=int)
+        orig_idx = new.qnidx
+        new.move_qnidx(self.qnidx)
+        new.qn = [add_outer(np.array(qo), np.array(qm)).reshape(-1, nq) for qo, qm in zip(qn, new.qn)]
+        new.qntot = new.qntot + qntot
+        new.move_qnidx(orig_idx)
+        if canonicalise:
+            new.canonicalise()
+        return new
+
+    def contract(self, mps, algo="svd"):
+        """An approximation of mpo @ mps: apply -> canonicalise -> compress (mpo.py:391-425)."""
+        if algo != "svd":
+            raise NotImplementedError("variational compression is outside the accelerated path (mp.py:513)")
+        new = self.apply(mps)
+        new.canonicalise()
+        new.compress()
+        return new
 
 
 class StackedMpo:

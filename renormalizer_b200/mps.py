@@ -470,13 +470,75 @@ class Mps:
         return float(np.sqrt(d2)) if d2 > 0 else 0.0
 
     # ------------------------------------------------------------------ time evolution
+    def add(self, other):
+        """Direct sum of the bond spaces, mp.py:374-436 with the coeff rule of mps.py:1802-1808."""
+        if not np.allclose(self.coeff, other.coeff):
+            self.scale(self.coeff, inplace=True)
+            other.scale(other.coeff, inplace=True)
+            self.coeff = 1
+            other.coeff = 1
+        assert np.all(self.qntot == other.qntot) and self.site_num == other.site_num
+        new = self.metacopy()
+        new.compress_config.update(self.compress_config)
+        dtype = torch.complex128 if (self.is_complex or other.is_complex) else torch.float64
+        n = self.site_num
+        for i, (a, b) in enumerate(zip(self._mp, other._mp)):
+            if i == 0:
+                new._mp[i] = torch.cat([a.to(dtype), b.to(dtype)], dim=-1)
+            elif i == n - 1:
+                new._mp[i] = torch.cat([a.to(dtype), b.to(dtype)], dim=0)
+            else:
+                t = torch.zeros((a.shape[0] + b.shape[0],) + tuple(a.shape[1:-1]) + (a.shape[-1] + b.shape[-1],),
+                                dtype=dtype, device=a.device)
+                t[:a.shape[0], ..., :a.shape[-1]] = a
+                t[a.shape[0]:, ..., a.shape[-1]:] = b
+                new._mp[i] = t
+        new.move_qnidx(other.qnidx)
+        new.to_right = other.to_right
+        new.qn = [np.concatenate([q1, q2]) for q1, q2 in zip(new.qn, other.qn)]
+        new.qn[0] = np.zeros((1, new.qn[0].shape[1]), dtype=int)
+        new.qn[-1] = np.zeros((1, new.qn[0].shape[1]), dtype=int)
+        return new
+
+    def _evolve_prop_and_compress(self, mpo, evolve_dt):
+        """Propagate and compress with a fixed step, mps.py:796-884: the 4th-order Taylor expansion
+        of exp(-i H dt); every H^k psi is Mpo.contract (apply + canonicalise + compress, with a
+        threshold criterion tightened to `both` while contracting), the scaled terms are summed and
+        compressed once more.  The truncations are the SVD path of this library."""
+        from math import factorial
+        from .lib import compressed_sum
+        config = self.evolve_config
+        if config.adaptive:
+            raise NotImplementedError("adaptive propagate-and-compress (mps.py:826-880) is not accelerated")
+        order = config.taylor_order
+        termlist = [self]
+        orig = self.compress_config
+        contract_config = self.compress_config.copy()
+        if contract_config.criteria is CompressCriteria.threshold:
+            contract_config.criteria = CompressCriteria.both
+        self.compress_config = contract_config
+        while len(termlist) < order + 1:
+            termlist.append(mpo.contract(termlist[-1]))
+        for t in termlist:
+            t.compress_config = orig
+        scaled = [term.scale((-1.0j * evolve_dt) ** idx / factorial(idx), inplace=idx > 0)
+                  for idx, term in enumerate(termlist)]
+        return compressed_sum(scaled)
+
     def evolve(self, mpo, evolve_dt, normalize=True):
-        """mps.py:644-662.  Only the projector-splitting integrator is accelerated."""
+        """mps.py:644-662: propagate-and-compress (the default) and the projector-splitting
+        integrators TDVP-PS / TDVP-PS2; the variational mean-field TDVP variants are not sweeps over
+        H_eff and stay outside the accelerated path."""
         method = self.evolve_config.method
+        if method is EvolveMethod.prop_and_compress:
+            new_mps = self._evolve_prop_and_compress(mpo, evolve_dt)
+            if normalize:
+                new_mps.normalize("mps_and_coeff" if np.iscomplex(evolve_dt) else "mps_only")
+            return new_mps
         if method not in (EvolveMethod.tdvp_ps, EvolveMethod.tdvp_ps2):
             raise NotImplementedError(
                 f"evolve method {method} is outside the accelerated path "
-                "(the projector-splitting integrators TDVP-PS / TDVP-PS2, mps.py:1268,1407, are)")
+                "(propagate-and-compress, TDVP-PS and TDVP-PS2, mps.py:796,1268,1407, are)")
         if self.evolve_config.ivp_solver != "krylov":
             raise NotImplementedError("only the Krylov local solver is accelerated")
         if method is EvolveMethod.tdvp_ps2:

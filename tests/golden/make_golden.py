@@ -180,6 +180,14 @@ def dump_mp(prefix, mp, out):
         out[f"{prefix}_{i}"] = np.asarray(mt.array)
 
 
+def dump_mpo_meta(prefix, mpo, out):
+    """Quantum numbers of an MPO (needed by Mpo.apply, mpo.py:375-382)."""
+    out[prefix + "_qntot"] = np.array(mpo.qntot)
+    out[prefix + "_qnidx"] = np.array(mpo.qnidx)
+    for i, q in enumerate(mpo.qn):
+        out[f"{prefix}_qn_{i}"] = np.array(q)
+
+
 def dump_mps_meta(prefix, mps, out):
     out[prefix + "_qntot"] = np.array(mps.qntot)
     out[prefix + "_qnidx"] = np.array(mps.qnidx)
@@ -549,6 +557,45 @@ def gen_thermal():
     np.savez_compressed(os.path.join(HERE, "thermal.npz"), **out)
 
 
+def gen_pc():
+    """Propagate-and-compress, the default integrator of Mps.evolve (mps.py:796-884: 4th-order
+    Taylor expansion of the propagator, every H^k psi by Mpo.contract = apply + canonicalise +
+    compress, compressed_sum of the scaled terms) on the exciton model with its conserved exciton."""
+    from renormalizer.model.op import Op
+    from renormalizer.mps import Mps, Mpo
+    from renormalizer.utils import CompressConfig, CompressCriteria
+    out = {}
+    model, nmol = _exciton_model()
+    mpo = Mpo(model)
+    occ_ops = [Mpo(model, Op(r"a^\dagger a", i)) for i in range(nmol)]
+    dump_mp("mpo", mpo, out)
+    dump_mpo_meta("mpo", mpo, out)
+    for i, o in enumerate(occ_ops):
+        dump_mp(f"occ{i}", o, out)
+    out["nmol"] = np.array(nmol)
+    for tag, cfg in (("thr", CompressConfig(CompressCriteria.threshold, threshold=1e-5)),
+                     ("fix", CompressConfig(CompressCriteria.fixed, max_bonddim=12))):
+        np.random.seed(777)
+        gs = Mps.ground_state(model, False)
+        mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ gs
+        mps.compress_config = cfg
+        if tag == "thr":
+            dump_mp("mps0", mps, out)
+            dump_mps_meta("mps0", mps, out)
+            out["mps0_coeff"] = np.array(mps.coeff)
+        occ, en, dims = [], [], []
+        for i in range(4):
+            mps = mps.evolve(mpo, 1.0)
+            occ.append([mps.expectation(o) for o in occ_ops])
+            en.append(mps.expectation(mpo))
+            dims.append(mps.bond_dims)
+        out[f"{tag}_occ"] = np.array(occ)
+        out[f"{tag}_energy"] = np.array(en)
+        out[f"{tag}_bond_dims"] = np.array(dims)
+        dump_mp(f"{tag}_mpsT", mps, out)
+    np.savez_compressed(os.path.join(HERE, "pc.npz"), **out)
+
+
 def gen_two_spin():
     """The README quickstart (README.md:36-58): two half spins, sigma+ sigma- exchange, 10 steps
     of Mps.evolve with dt = 0.05, <Z_0> after every step -- with the default propagate-and-
@@ -562,6 +609,7 @@ def gen_two_spin():
     mpo = Mpo(model)
     z_op = Mpo(model, Op("Z", 0))
     dump_mp("mpo", mpo, out)
+    dump_mpo_meta("mpo", mpo, out)
     dump_mp("z", z_op, out)
     for tag, cfg in (("pc", None), ("ps", EvolveConfig(EvolveMethod.tdvp_ps)),
                      ("ps2", EvolveConfig(EvolveMethod.tdvp_ps2))):
@@ -582,7 +630,7 @@ def gen_two_spin():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm", "stacked", "qc", "exciton",
-                             "two_spin", "thermal"]
+                             "two_spin", "thermal", "pc"]
     for name in which:
         print("generating", name, flush=True)
         globals()["gen_" + name]()

@@ -18,3 +18,10 @@ def load_oracle_mps(g, prefix, meta="mps0"):
 def relerr(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def load_oracle_mpo(g, prefix="mpo"):
+    from oracle.sweep import Mpo
+    n = int(g[prefix + "_n"])
+    return Mpo([g[f"{prefix}_{i}"] for i in range(n)], [g[f"{prefix}_qn_{i}"] for i in range(n + 1)],
+               g[prefix + "_qntot"], int(g[prefix + "_qnidx"]))

@@ -7,6 +7,7 @@ import pytest
 torch = pytest.importorskip("torch")
 
 from helpers import load_mpo, load_oracle_mps, relerr
+from renormalizer_b200.configs import EvolveConfig, EvolveMethod
 
 pytestmark = pytest.mark.gpu
 
@@ -24,8 +25,11 @@ def host(t):
 
 
 def to_device_mps(om):
+    from renormalizer_b200.configs import EvolveConfig, EvolveMethod
     from renormalizer_b200.mps import Mps
-    return Mps(om.sites, om.qn, om.sigmaqn, om.qntot, om.qnidx, om.to_right)
+    m = Mps(om.sites, om.qn, om.sigmaqn, om.qntot, om.qnidx, om.to_right)
+    m.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps)     # the sweep integrator these tests exercise
+    return m
 
 
 @pytest.mark.parametrize("t", ["r", "c"])
@@ -231,6 +235,7 @@ def test_tdvp_ps_vs_oracle_midsize():
     sq = [np.zeros((s.shape[1], 1), dtype=int) for s in sites]
     om = osw.Mps(sites, qn, sq, [0], n - 1, False)
     dm = Mps(sites, qn, sq, [0], n - 1, False)
+    dm.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps)
     o1 = osw.evolve_tdvp_ps(om, w, 0.05)
     d1 = dm.evolve(Mpo(w), 0.05)
     ref = Mps(o1.sites, o1.qn, o1.sigmaqn, o1.qntot, o1.qnidx, o1.to_right)
@@ -252,6 +257,7 @@ def test_tdvp_roundtrip_time_reversal():
     mpo = Mpo(models.spin_boson_mpo(0.0, 1.0, omega, gcoup, d))
     sites = models.random_mps_sites([2] + [d] * nmodes, M, rng, dtype=np.complex128)
     m0 = Mps.without_qn(sites)
+    m0.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps)
     m1 = m0.evolve(mpo, 0.02)
     m2 = m1.evolve(mpo, -0.02)
     assert abs(abs(m0.conj().dot(m2)) - 1) < 1e-9
@@ -612,3 +618,54 @@ def test_adaptive_tdvp_ps_golden(golden):
     assert np.abs(np.array(occs) - g["adaptive_occ"]).max() < 1e-7
     refT = to_device_mps(load_oracle_mps(g, "adaptive_mpsT", meta="mps0"))
     assert abs(abs(refT.conj().dot(mps)) - 1) < 1e-6
+
+
+def _device_mpo_with_qn(g, prefix="mpo"):
+    from renormalizer_b200.mpo import Mpo
+    n = int(g[prefix + "_n"])
+    return Mpo(load_mpo(g, prefix), qn=[g[f"{prefix}_qn_{i}"] for i in range(n + 1)],
+               qntot=g[prefix + "_qntot"], qnidx=int(g[prefix + "_qnidx"]))
+
+
+@pytest.mark.parametrize("tag", ["thr", "fix"])
+def test_prop_and_compress_exciton_golden(golden, tag):
+    """Mps.evolve with its default configuration (propagate-and-compress, mps.py:796-884) on the
+    exciton model with a conserved exciton: Mpo.apply, Mps.add, canonicalise and the SVD compression
+    on the device -- occupations, energy and the bond dimensions the truncation chooses."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria
+    from renormalizer_b200.mpo import Mpo
+    g = golden("pc")
+    mpo = _device_mpo_with_qn(g)
+    occ = [Mpo(load_mpo(g, f"occ{i}")) for i in range(int(g["nmol"]))]
+    mps = _device_mps_with_coeff(g, "mps0")
+    assert mps.evolve_config.method is EvolveMethod.prop_and_compress          # the reference's default
+    mps.compress_config = CompressConfig(CompressCriteria.threshold, threshold=1e-5) if tag == "thr" \
+        else CompressConfig(CompressCriteria.fixed, max_bonddim=12)
+    occs, es, dims = [], [], []
+    for _ in range(4):
+        mps = mps.evolve(mpo, 1.0)
+        occs.append([mps.expectation(o) for o in occ])
+        es.append(mps.expectation(mpo))
+        dims.append(mps.bond_dims)
+    assert np.array_equal(np.array(dims), g[f"{tag}_bond_dims"])
+    assert np.abs(np.array(occs) - g[f"{tag}_occ"]).max() < E_TOL
+    assert np.abs(np.array(es) - g[f"{tag}_energy"]).max() < E_TOL
+    ref = to_device_mps(load_oracle_mps(g, f"{tag}_mpsT", meta="mps0"))
+    assert abs(abs(ref.conj().dot(mps)) - 1) < T_TOL
+
+
+def test_two_spin_quickstart_default_integrator_golden(golden):
+    """The README quickstart exactly as printed (README.md:36-58): default Mps.evolve, ten steps of
+    0.05, <Z_0> after each -- the values the reference prints."""
+    from renormalizer_b200.mpo import Mpo
+    from renormalizer_b200.mps import Mps
+    g = golden("two_spin")
+    mpo, z = _device_mpo_with_qn(g), Mpo(load_mpo(g, "z"))
+    om = load_oracle_mps(g, "mps0")
+    mps = Mps(om.sites, om.qn, om.sigmaqn, om.qntot, om.qnidx, om.to_right)
+    zs = []
+    for _ in range(10):
+        mps = mps.evolve(mpo, 0.05)
+        zs.append(mps.expectation(z))
+    assert np.abs(np.array(zs) - g["pc_z_t"]).max() < E_TOL
+    assert mps.bond_dims == list(g["pc_bond_dims"])

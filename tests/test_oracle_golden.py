@@ -331,3 +331,43 @@ def test_adaptive_tdvp_ps(golden):
     # the agreement of two evaluations of the recurrence; the first (dt = 1, 2) step agrees to 1e-10
     assert np.abs(np.array(occs[0]) - g["adaptive_occ"][0]).max() < 1e-10
     assert np.abs(np.array(occs) - g["adaptive_occ"]).max() < 1e-7
+
+
+@pytest.mark.parametrize("tag", ["thr", "fix"])
+def test_prop_and_compress_exciton(golden, tag):
+    """Propagate-and-compress (the default Mps.evolve, mps.py:796-884) with a conserved exciton:
+    occupations, energy and the bond dimensions the truncation chooses, step by step."""
+    from helpers import load_oracle_mpo
+    from oracle.sweep import evolve_prop_and_compress, CompressSpec
+    g = golden("pc")
+    mpo = load_oracle_mpo(g)
+    occ = [load_mpo(g, f"occ{i}") for i in range(int(g["nmol"]))]
+    mps = _load_with_coeff(g, "mps0")
+    spec = CompressSpec("threshold", threshold=1e-5) if tag == "thr" else CompressSpec("fixed", max_bonddim=12)
+    occs, es, dims = [], [], []
+    for _ in range(4):
+        mps = evolve_prop_and_compress(mps, mpo, 1.0, spec)
+        occs.append([mps.expectation(o) for o in occ])
+        es.append(mps.expectation(mpo.sites))
+        dims.append(mps.bond_dims)
+    assert np.array_equal(np.array(dims), g[f"{tag}_bond_dims"])
+    assert np.abs(np.array(occs) - g[f"{tag}_occ"]).max() < 1e-10
+    assert np.abs(np.array(es) - g[f"{tag}_energy"]).max() < 1e-10
+    ref = load_oracle_mps(g, f"{tag}_mpsT", meta="mps0")
+    assert abs(abs(ref.dot_conj(mps)) - 1) < 1e-10
+
+
+def test_two_spin_quickstart_default_integrator(golden):
+    """The README quickstart exactly as printed: Mps.evolve with the default (propagate-and-compress)
+    configuration, ten steps of 0.05 -- the values the reference prints."""
+    from helpers import load_oracle_mpo
+    from oracle.sweep import evolve_prop_and_compress, CompressSpec
+    g = golden("two_spin")
+    mpo, z = load_oracle_mpo(g), load_mpo(g, "z")
+    mps = load_oracle_mps(g, "mps0")
+    zs = []
+    for _ in range(10):
+        mps = evolve_prop_and_compress(mps, mpo, 0.05, CompressSpec())
+        zs.append(mps.expectation(z))
+    assert np.abs(np.array(zs) - g["pc_z_t"]).max() < 1e-12
+    assert mps.bond_dims == list(g["pc_bond_dims"])

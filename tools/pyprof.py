@@ -14,6 +14,8 @@ w = bench.make_workload(args, 1234)
 meta = w["meta"]
 mps = Mps(w["sites"], meta["qn"], meta["sigmaqn"], meta["qntot"], meta["qnidx"], meta["to_right"])
 mpo = Mpo(w["mpo"])
+from renormalizer_b200.configs import EvolveConfig, EvolveMethod
+mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps)
 for _ in range(2):
     mps = mps.evolve(mpo, 0.05)
 torch.cuda.synchronize()
