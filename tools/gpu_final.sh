@@ -2,6 +2,8 @@
 # End-of-round measurement pass (1 GPU): parity tests, smoke, bench line (default workload + Holstein
 # DMRG M=512), H_eff roofline at three bond dimensions, ncu --set full of the GEMM at M=1024 and of the
 # block-Jacobi kernels, ncu launch list of one timed bench step.
+# Budget: everything up to the last step takes ~4 min; the launch list (8.5 k launches under ncu) takes
+# ~12 min on its own -- run it as a separate gpurun call when fewer than 20 GPU-minutes are left.
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/f_pytest.log 2>&1
 tail -4 gpurun_out/f_pytest.log
