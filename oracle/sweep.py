@@ -659,8 +659,14 @@ def mpo_apply(mpo, mps):
 
 
 def mps_add(a, b):
-    """Direct sum of two MPS / MPDM.  Reference: mp.py:374-436 (equal coeff, mps.py:1802-1808)."""
-    assert np.all(a.qntot == b.qntot) and len(a) == len(b) and np.allclose(a.coeff, b.coeff)
+    """Direct sum of two MPS / MPDM.  Reference: mp.py:374-436 and the coeff rule of
+    mps.py:1802-1808 (unequal coefficients are first multiplied into the states, in place)."""
+    assert np.all(a.qntot == b.qntot) and len(a) == len(b)
+    if not np.allclose(a.coeff, b.coeff):
+        mps_scale(a, a.coeff, inplace=True)
+        mps_scale(b, b.coeff, inplace=True)
+        a.coeff = 1
+        b.coeff = 1
     cplx = any(np.iscomplexobj(s) for s in a.sites + b.sites)
     dt = np.complex128 if cplx else np.float64
     n = len(a)
@@ -683,9 +689,9 @@ def mps_add(a, b):
     return new
 
 
-def compress(mps, spec):
+def compress(mps, spec, temp_m_trunc=None):
     """SVD truncation sweep of a canonicalised MPS, in place.  Reference: mp.py:437-511 with
-    _update_ms (mp.py:245-295)."""
+    _update_ms (mp.py:245-295).  `temp_m_trunc` (int or one entry per bond) overrides `spec`."""
     assert mps.qnidx == (0 if mps.to_right else len(mps) - 1)
     system = "L" if mps.to_right else "R"
     for idx in mps.iter_idx_list(full=False):
@@ -694,7 +700,12 @@ def compress(mps, spec):
         u, sigma, qnlset, v, sigma, qnrset = svd_qn(mps.sites[idx], qnbigl, qnbigr, mps.qntot,
                                                     system=system, full_matrices=False)
         vt = v.T
-        m = min(spec.m_trunc(sigma), len(sigma))
+        if temp_m_trunc is None:
+            m = min(spec.m_trunc(sigma), len(sigma))
+        elif np.ndim(temp_m_trunc) > 0:
+            m = min(int(temp_m_trunc[idx + 1 if mps.to_right else idx]), len(sigma))
+        else:
+            m = min(int(temp_m_trunc), len(sigma))
         u, vt, sigma = u[:, :m], vt[:m, :], sigma[:m]
         if mps.to_right:
             vt = sigma[:, None] * vt
@@ -712,17 +723,17 @@ def compress(mps, spec):
     return mps
 
 
-def compressed_sum(terms, spec, batchsize=5):
-    """lib.py:417-439."""
+def compressed_sum(terms, spec, batchsize=5, temp_m_trunc=None):
+    """lib.py:417-439.  A single term is canonicalised and compressed IN PLACE (and returned)."""
     queue = list(terms)
     if len(queue) == 1:
-        return compress(queue[0].canonicalise(), spec)
+        return compress(queue[0].canonicalise(), spec, temp_m_trunc)
     while len(queue) != 1:
         batch, queue = queue[:batchsize], queue[batchsize:]
         s = batch[0]
         for t in batch[1:]:
             s = mps_add(s, t)
-        queue.append(compress(s.canonicalise(), spec))
+        queue.append(compress(s.canonicalise(), spec, temp_m_trunc))
     return queue[0]
 
 
@@ -740,3 +751,58 @@ def evolve_prop_and_compress(mps, mpo, dt, spec, order=4, normalize=True):
     if normalize:
         new.normalize_mps_only()
     return new
+
+
+def normalize(mps, kind):
+    """mps.py:619-642 / 2025-2058, in place."""
+    nrm = mps.mp_norm
+    if kind == "mps_only":
+        new_coeff = mps.coeff
+    elif kind == "mps_and_coeff":
+        new_coeff = mps.coeff / np.linalg.norm(mps.coeff)
+    elif kind == "mps_norm_to_coeff":
+        new_coeff = mps.coeff * nrm
+    else:
+        raise ValueError(f"kind={kind} is not valid.")
+    mps_scale(mps, 1.0 / nrm, inplace=True)
+    mps.coeff = new_coeff
+    return mps
+
+
+def bond_dims_exact(mps):
+    """mp.py:130-142: bond dimensions of an exact factorisation."""
+    p = np.array([float(np.prod(s.shape[1:-1])) for s in mps.sites])
+    with np.errstate(over="ignore"):
+        d1 = [1] + list(np.cumprod(p))
+        d2 = ([1] + list(np.cumprod(p[::-1])))[::-1]
+    return np.minimum(d1, d2)
+
+
+def expand_bond_dimension(mps, hint_mpo, max_bonddim, coef=1e-10):
+    """Fill the bond dimension up to `max_bonddim` with states reached through `hint_mpo`.
+    Reference: mps.py:1934-2023 with include_ex=False (expand_bond_dimension_general, ex_mps=None).
+    The aliasing of the reference is kept: the first `expander` IS `lastone`, compressed in place."""
+    spec = CompressSpec("fixed", max_bonddim=max_bonddim)          # unused: every compress is explicit
+    max_dims = np.full(len(mps.bond_dims), max_bonddim, dtype=int)
+    m_target = np.minimum(max_dims - np.array(mps.bond_dims), bond_dims_exact(mps)).astype(int)
+    lastone = mps
+    expander_list = []
+    expander_dims = np.zeros_like(m_target)
+    hint_max = max(hint_mpo.sites[0].shape[0], *(w.shape[-1] for w in hint_mpo.sites))
+    while True:
+        lastone = normalize(mpo_apply(hint_mpo, lastone), "mps_and_coeff")
+        lastone = compress(lastone.canonicalise(), spec, int(np.max(m_target)))
+        expander_list.append(lastone)
+        expander = compressed_sum(expander_list, spec, temp_m_trunc=m_target)
+        if np.all(np.array(expander.bond_dims) >= m_target):
+            break
+        if np.all(np.array(expander.bond_dims) == expander_dims):
+            m_target2 = np.max(m_target - np.array(expander_dims))
+            expander2 = compress(mpo_apply(hint_mpo, lastone).canonicalise(), spec, int(np.maximum(m_target2, 1)))
+            expander = mps_add(expander, expander2)
+            break
+        expander_dims = np.array(expander.bond_dims)
+        lastone = compress(lastone.canonicalise(), spec, int(np.max(m_target) / hint_max) + 1)
+    norm = abs(mps.coeff) * mps.mp_norm
+    new = mps_add(mps, mps_scale(expander, coef * norm, inplace=True))
+    return normalize(compress(new.canonicalise(), spec, max_dims), "mps_norm_to_coeff")

@@ -115,6 +115,13 @@ class Mpo:
             new.canonicalise()
         return new
 
+    def __matmul__(self, other):
+        return self.apply(other)
+
+    @property
+    def bond_dims_mean(self):
+        return int(round(np.mean(self.bond_dims)))
+
     def contract(self, mps, algo="svd"):
         """An approximation of mpo @ mps: apply -> canonicalise -> compress (mpo.py:391-425)."""
         if algo != "svd":

@@ -123,6 +123,16 @@ class Mps:
         return [s.shape[1] for s in self._mp]
 
     @property
+    def bond_dims_exact(self):
+        """mp.py:130-142: bond dimensions of an exact factorisation (physical x ancilla dimension
+        per site for a density operator)."""
+        p = np.array([float(np.prod(s.shape[1:-1])) for s in self._mp])
+        with np.errstate(over="ignore"):
+            d1 = [1] + list(np.cumprod(p))
+            d2 = ([1] + list(np.cumprod(p[::-1])))[::-1]
+        return np.minimum(d1, d2)
+
+    @property
     def total_bytes(self):
         return sum(s.numel() * s.element_size() for s in self._mp)
 
@@ -499,6 +509,55 @@ class Mps:
         new.qn[0] = np.zeros((1, new.qn[0].shape[1]), dtype=int)
         new.qn[-1] = np.zeros((1, new.qn[0].shape[1]), dtype=int)
         return new
+
+    def __add__(self, other):
+        return self.add(other)
+
+    def expand_bond_dimension(self, hint_mpo=None, coef=1e-10, include_ex=True, ex_mps=None):
+        """Fill the bond dimensions up to compress_config's limit with states reached through
+        `hint_mpo` (mps.py:636-640, 1934-2023), the preparation step of a TDVP-PS run.  The
+        reference's `include_ex=True` admixes a model-specific excited state (ground state +
+        creation operators, or the maximally entangled state): pass it as `ex_mps`; a random expander
+        (`hint_mpo=None`) needs the model classes as well.  Both are outside the sweep path."""
+        from .lib import compressed_sum
+        if hint_mpo is None:
+            raise NotImplementedError("a random expander needs the reference's Model (mps.py:1983-1984); "
+                                      "pass a hint MPO")
+        if include_ex and ex_mps is None:
+            raise NotImplementedError("include_ex=True builds a model-specific state (mps.py:1944-1957): "
+                                      "pass it as ex_mps, or use include_ex=False")
+        mps = self
+        mps.compress_config.set_bonddim(len(mps.bond_dims))
+        m_target = np.minimum(np.array(mps.compress_config.max_dims) - np.array(mps.bond_dims),
+                              mps.bond_dims_exact).astype(int)
+        if ex_mps is not None:
+            ex_mps.compress_config = mps.compress_config
+            ex_mps.move_qnidx(mps.qnidx)
+            ex_mps.to_right = mps.to_right
+            lastone = mps + ex_mps
+        else:
+            lastone = mps
+        expander_list = []
+        expander_dims = np.zeros_like(m_target)
+        while True:
+            lastone = (hint_mpo @ lastone).normalize("mps_and_coeff")
+            # more bond dimension for `lastone` for quick increase
+            lastone = lastone.canonicalise().compress(int(np.max(m_target)))
+            expander_list.append(lastone)
+            expander = compressed_sum(expander_list, temp_m_trunc=m_target)
+            if np.all(np.array(expander.bond_dims) >= m_target):
+                break
+            if np.all(np.array(expander.bond_dims) == expander_dims):
+                # the expander does not grow any more: the target is too high
+                m_target2 = np.max(m_target - np.array(expander_dims))
+                expander2 = (hint_mpo @ lastone).canonicalise().compress(int(np.maximum(m_target2, 1)))
+                expander = expander + expander2
+                break
+            expander_dims = np.array(expander.bond_dims)
+            temp_m_trunc = int(np.max(m_target) / np.max(hint_mpo.bond_dims)) + 1
+            lastone = lastone.canonicalise().compress(temp_m_trunc)
+        return ((mps + expander.scale(coef * mps.norm, inplace=True)).canonicalise()
+                .compress(mps.compress_config.max_dims).normalize("mps_norm_to_coeff"))
 
     def _evolve_prop_and_compress(self, mpo, evolve_dt):
         """Propagate and compress with a fixed step, mps.py:796-884: the 4th-order Taylor expansion

@@ -596,6 +596,49 @@ def gen_pc():
     np.savez_compressed(os.path.join(HERE, "pc.npz"), **out)
 
 
+def gen_expand():
+    """expand_bond_dimension with a hint MPO and include_ex=False (mps.py:1934-2023), the preparation
+    step of every TDVP-PS run in the reference's examples: a spin-boson product state (no conserved
+    quantum number, coef 1e-6), the one-exciton state of the exciton model and its density operator."""
+    from renormalizer.model import Phonon, SpinBosonModel
+    from renormalizer.mps import Mps, Mpo, MpDm
+    from renormalizer.utils import Quantity, CompressConfig, CompressCriteria
+    out = {}
+
+    def record(tag, mps, mpo, coef):
+        dump_mp(f"{tag}_mpo", mpo, out)
+        dump_mpo_meta(f"{tag}_mpo", mpo, out)
+        dump_mp(f"{tag}_pre", mps, out)
+        dump_mps_meta(f"{tag}_pre", mps, out)
+        out[f"{tag}_pre_coeff"] = np.array(mps.coeff)
+        out[f"{tag}_coef"] = np.array(coef)
+        out[f"{tag}_max_bonddim"] = np.array(mps.compress_config.bond_dim_max_value)
+        new = mps.expand_bond_dimension(mpo, coef=coef, include_ex=False)
+        dump_mp(f"{tag}_post", new, out)
+        dump_mps_meta(f"{tag}_post", new, out)
+        out[f"{tag}_post_coeff"] = np.array(new.coeff)
+        out[f"{tag}_post_bond_dims"] = np.array(new.bond_dims)
+        out[f"{tag}_post_energy"] = np.array(new.expectation(mpo))
+
+    ph_list = [Phonon.simple_phonon(Quantity(o), Quantity(d), 4)
+               for o, d in zip([0.5, 0.8, 1.0, 1.3, 1.7, 2.2], [1.0, 0.8, 0.6, 0.5, 0.4, 0.3])]
+    model = SpinBosonModel(Quantity(0.3), Quantity(1.0), ph_list)
+    mps = Mps.ground_state(model, False)
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=12)
+    record("sbm", mps, Mpo(model), 1e-6)
+
+    model, nmol = _exciton_model()
+    mpo = Mpo(model)
+    mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ Mps.ground_state(model, False)
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    record("ex", mps, mpo, 1e-10)
+
+    dm = MpDm.max_entangled_ex(model)
+    dm.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=8)
+    record("dm", dm, mpo, 1e-10)
+    np.savez_compressed(os.path.join(HERE, "expand.npz"), **out)
+
+
 def gen_two_spin():
     """The README quickstart (README.md:36-58): two half spins, sigma+ sigma- exchange, 10 steps
     of Mps.evolve with dt = 0.05, <Z_0> after every step -- with the default propagate-and-
@@ -630,7 +673,7 @@ def gen_two_spin():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm", "stacked", "qc", "exciton",
-                             "two_spin", "thermal", "pc"]
+                             "two_spin", "thermal", "pc", "expand"]
     for name in which:
         print("generating", name, flush=True)
         globals()["gen_" + name]()

@@ -669,3 +669,42 @@ def test_two_spin_quickstart_default_integrator_golden(golden):
         zs.append(mps.expectation(z))
     assert np.abs(np.array(zs) - g["pc_z_t"]).max() < E_TOL
     assert mps.bond_dims == list(g["pc_bond_dims"])
+
+
+@pytest.mark.parametrize("tag", ["sbm", "ex", "dm"])
+def test_expand_bond_dimension_golden(golden, tag):
+    """Mps.expand_bond_dimension(hint_mpo, include_ex=False) (mps.py:1934-2023), the preparation of
+    every TDVP-PS run: Mpo.apply, canonicalise, the SVD compressions and compressed_sum on the device.
+    Bond dimensions, the norm carried to coeff, the state and its energy equal the reference's; the
+    admixed expander (weight coef) is compared where the truncated spectra are non-degenerate (the
+    spin-boson chain) -- with degenerate modes the kept multiplet members are arbitrary in LAPACK too.
+    The expanded state then takes TDVP-PS steps at the full bond dimension, conserving the energy."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria
+    from renormalizer_b200.mps import Mps
+    g = golden("expand")
+    mpo = _device_mpo_with_qn(g, f"{tag}_mpo")
+    om = load_oracle_mps(g, f"{tag}_pre", meta=f"{tag}_pre")
+    pre = Mps(om.sites, om.qn, om.sigmaqn, om.qntot, om.qnidx, om.to_right, coeff=complex(g[f"{tag}_pre_coeff"]))
+    pre.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=int(g[f"{tag}_max_bonddim"]))
+    new = pre.copy().expand_bond_dimension(mpo, coef=float(g[f"{tag}_coef"]), include_ex=False)
+    ref = to_device_mps(load_oracle_mps(g, f"{tag}_post", meta=f"{tag}_post"))
+    assert new.bond_dims == list(g[f"{tag}_post_bond_dims"])
+    assert abs(new.coeff - complex(g[f"{tag}_post_coeff"])) < E_TOL
+    assert abs(new.mp_norm - 1) < 1e-12
+    assert abs(ref.conj().dot(new) - 1) < E_TOL
+    assert abs(new.expectation(mpo) - float(g[f"{tag}_post_energy"])) < 1e-9
+    if tag == "sbm":
+        def admixture(post):
+            a, b = pre.copy(), post.copy()
+            a.coeff = b.coeff = 1
+            return b.add(a.scale(-a.conj().dot(b) / a.conj().dot(a)))
+        x, y = admixture(new), admixture(ref)
+        assert abs(abs(x.conj().dot(y)) / (x.mp_norm * y.mp_norm) - 1) < 1e-4
+    with pytest.raises(NotImplementedError):
+        pre.copy().expand_bond_dimension(mpo)               # include_ex=True needs a model-specific state
+    new.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps)
+    e0 = new.expectation(mpo)
+    stepped = new.evolve(mpo, 0.05).evolve(mpo, 0.05)
+    assert stepped.bond_dims == new.bond_dims
+    assert abs(stepped.expectation(mpo) - e0) < 1e-8
+    assert abs(stepped.mp_norm - 1) < 1e-12

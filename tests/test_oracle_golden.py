@@ -371,3 +371,33 @@ def test_two_spin_quickstart_default_integrator(golden):
         zs.append(mps.expectation(z))
     assert np.abs(np.array(zs) - g["pc_z_t"]).max() < 1e-12
     assert mps.bond_dims == list(g["pc_bond_dims"])
+
+
+@pytest.mark.parametrize("tag", ["sbm", "ex", "dm"])
+def test_expand_bond_dimension(golden, tag):
+    """expand_bond_dimension with a hint MPO (mps.py:1934-2023), the preparation step of every
+    TDVP-PS run: bond dimensions, norm carried to coeff, the whole state, and -- separately, because
+    it enters with weight coef -- the admixed expander."""
+    from helpers import load_oracle_mpo
+    from oracle.sweep import expand_bond_dimension, mps_add, mps_scale
+    g = golden("expand")
+    mpo = load_oracle_mpo(g, f"{tag}_mpo")
+    pre = load_oracle_mps(g, f"{tag}_pre", meta=f"{tag}_pre")
+    pre.coeff = complex(g[f"{tag}_pre_coeff"])
+    coef = float(g[f"{tag}_coef"])
+    new = expand_bond_dimension(pre.copy(), mpo, int(g[f"{tag}_max_bonddim"]), coef)
+    ref = load_oracle_mps(g, f"{tag}_post", meta=f"{tag}_post")
+    assert new.bond_dims == list(g[f"{tag}_post_bond_dims"])
+    assert abs(new.coeff - complex(g[f"{tag}_post_coeff"])) < 1e-12
+    assert abs(new.mp_norm - 1) < 1e-12
+    assert abs(ref.dot_conj(new) - 1) < 1e-12
+    assert abs(new.expectation(mpo.sites) - float(g[f"{tag}_post_energy"])) < 1e-10
+    # the expander: (post - <pre|post> pre) / coef has the same direction in both
+    def admixture(post):
+        a = pre.copy(); a.coeff = 1
+        b = post.copy(); b.coeff = 1
+        ov = a.dot_conj(b) / a.dot_conj(a)
+        return mps_add(b, mps_scale(a, -ov))
+    x, y = admixture(new), admixture(ref)
+    assert abs(abs(x.dot_conj(y)) / (x.mp_norm * y.mp_norm) - 1) < 1e-6
+    assert abs(x.mp_norm / y.mp_norm - 1) < 1e-6
