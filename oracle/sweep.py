@@ -806,3 +806,45 @@ def expand_bond_dimension(mps, hint_mpo, max_bonddim, coef=1e-10):
     norm = abs(mps.coeff) * mps.mp_norm
     new = mps_add(mps, mps_scale(expander, coef * norm, inplace=True))
     return normalize(compress(new.canonicalise(), spec, max_dims), "mps_norm_to_coeff")
+
+
+def mps_distance(a, b):
+    """mp.py:1009-1023 (equal coefficients)."""
+    l1, l2, l12 = a.dot_conj(a), b.dot_conj(b), a.dot_conj(b)
+    return float(np.sqrt(max((l1 + l2 - l12 - np.conj(l12)).real, 0.0)))
+
+
+def evolve_prop_and_compress_adaptive(mps, mpo, dt, spec, guess_dt, rtol=5e-4, order=5, normalize=True):
+    """Propagate-and-compress with adaptive step control.  Reference: mps.py:796-880 (adaptive
+    branch: error = distance between the sums to order-1 and to order, p = (rtol / error)^(1/order),
+    recursion over the remaining time) and mps.py:657-661.  Returns (new Mps, new guess_dt)."""
+    from math import factorial
+    p_restart, p_min, p_max = 0.5, 0.1, 2.0
+
+    def step(psi, evolve_dt, guess):
+        terms = [psi.copy()]
+        while len(terms) < order + 1:
+            terms.append(compress(mpo_apply(mpo, terms[-1]).canonicalise(), spec.both()))
+        while True:
+            h = guess if abs(guess) < abs(evolve_dt) else evolve_dt
+            scaled = [mps_scale(t, (-1.0j * h) ** k / factorial(k)) for k, t in enumerate(terms)]
+            new1 = compressed_sum(scaled[:-1], spec)
+            new2 = compressed_sum([new1, scaled[-1]], spec)
+            dis = mps_distance(new1, new2)
+            p = (rtol / (dis / new2.mp_norm + 1e-30)) ** (1.0 / order)
+            if np.allclose(h, evolve_dt):
+                if p < p_restart:
+                    guess = h * max(p_min, p)
+                else:
+                    return new2, (h * p if abs(h * p) < abs(guess) else guess)
+            else:
+                if p < p_restart:
+                    guess = guess * max(p_min, p)
+                else:
+                    guess = guess * min(p, p_max)
+                    return step(new2, evolve_dt - h, guess)
+
+    new, guess = step(mps, dt, guess_dt)
+    if normalize:
+        new.normalize_mps_only()
+    return new, guess

@@ -560,15 +560,14 @@ class Mps:
                 .compress(mps.compress_config.max_dims).normalize("mps_norm_to_coeff"))
 
     def _evolve_prop_and_compress(self, mpo, evolve_dt):
-        """Propagate and compress with a fixed step, mps.py:796-884: the 4th-order Taylor expansion
-        of exp(-i H dt); every H^k psi is Mpo.contract (apply + canonicalise + compress, with a
-        threshold criterion tightened to `both` while contracting), the scaled terms are summed and
-        compressed once more.  The truncations are the SVD path of this library."""
+        """Propagate and compress, mps.py:796-884: the Taylor expansion of exp(-i H dt) (4th order
+        with a fixed step, 5th with adaptive step control); every H^k psi is Mpo.contract (apply +
+        canonicalise + compress, with a threshold criterion tightened to `both` while contracting),
+        the scaled terms are summed and compressed once more.  The truncations are the SVD path of
+        this library."""
         from math import factorial
         from .lib import compressed_sum
         config = self.evolve_config
-        if config.adaptive:
-            raise NotImplementedError("adaptive propagate-and-compress (mps.py:826-880) is not accelerated")
         order = config.taylor_order
         termlist = [self]
         orig = self.compress_config
@@ -580,9 +579,36 @@ class Mps:
             termlist.append(mpo.contract(termlist[-1]))
         for t in termlist:
             t.compress_config = orig
-        scaled = [term.scale((-1.0j * evolve_dt) ** idx / factorial(idx), inplace=idx > 0)
-                  for idx, term in enumerate(termlist)]
-        return compressed_sum(scaled)
+        if not config.adaptive:
+            scaled = [term.scale((-1.0j * evolve_dt) ** idx / factorial(idx), inplace=idx > 0)
+                      for idx, term in enumerate(termlist)]
+            return compressed_sum(scaled)
+        # adaptive step control (mps.py:826-880): the error estimate is the distance between the sums
+        # to order-1 and to order; the remaining time is evolved by recursion
+        config.check_valid_dt(evolve_dt)
+        p_restart, p_min, p_max = 0.5, 0.1, 2.0
+        while True:
+            dt = config.guess_dt if abs(config.guess_dt) < abs(evolve_dt) else evolve_dt
+            scaled = [term.scale((-1.0j * dt) ** idx / factorial(idx)) for idx, term in enumerate(termlist)]
+            new_mps1 = compressed_sum(scaled[:-1])
+            new_mps2 = compressed_sum([new_mps1, scaled[-1]])
+            dis = new_mps1.distance(new_mps2)
+            p = (config.adaptive_rtol / (dis / new_mps2.mp_norm + 1e-30)) ** (1 / order)
+            if np.allclose(dt, evolve_dt):
+                if p < p_restart:                       # not accurate in this final sub-step: restart
+                    config.guess_dt = dt * max(p_min, p)
+                else:
+                    new_mps2.evolve_config.guess_dt = dt * p if abs(dt * p) < abs(config.guess_dt) \
+                        else config.guess_dt
+                    return new_mps2
+            else:
+                if p < p_restart:
+                    config.guess_dt *= max(p_min, p)
+                else:
+                    config.guess_dt *= min(p, p_max)
+                    new_mps2.evolve_config.guess_dt = config.guess_dt
+                    del new_mps1, termlist, scaled
+                    return new_mps2._evolve_prop_and_compress(mpo, evolve_dt - dt)
 
     def evolve(self, mpo, evolve_dt, normalize=True):
         """mps.py:644-662: propagate-and-compress (the default) and the projector-splitting

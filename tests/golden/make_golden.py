@@ -593,6 +593,24 @@ def gen_pc():
         out[f"{tag}_energy"] = np.array(en)
         out[f"{tag}_bond_dims"] = np.array(dims)
         dump_mp(f"{tag}_mpsT", mps, out)
+    # adaptive step control (mps.py:826-880): 5th-order expansion, error = distance of the 4th- and
+    # 5th-order sums, recursion over the remaining time
+    from renormalizer.utils import EvolveConfig, EvolveMethod
+    np.random.seed(777)
+    gs = Mps.ground_state(model, False)
+    mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ gs
+    mps.compress_config = CompressConfig(CompressCriteria.threshold, threshold=1e-5)
+    mps.evolve_config = EvolveConfig(EvolveMethod.prop_and_compress, adaptive=True, guess_dt=0.4,
+                                     adaptive_rtol=1e-4)
+    occ, guess, dims = [], [], []
+    for i in range(3):
+        mps = mps.evolve(mpo, 2.0)
+        occ.append([mps.expectation(o) for o in occ_ops])
+        guess.append(mps.evolve_config.guess_dt)
+        dims.append(mps.bond_dims)
+    out["ada_occ"] = np.array(occ)
+    out["ada_guess_dt"] = np.array(guess)
+    out["ada_bond_dims"] = np.array(dims)
     np.savez_compressed(os.path.join(HERE, "pc.npz"), **out)
 
 

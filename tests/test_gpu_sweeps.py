@@ -708,3 +708,30 @@ def test_expand_bond_dimension_golden(golden, tag):
     assert stepped.bond_dims == new.bond_dims
     assert abs(stepped.expectation(mpo) - e0) < 1e-8
     assert abs(stepped.mp_norm - 1) < 1e-12
+
+
+def test_prop_and_compress_adaptive_golden(golden):
+    """Adaptive propagate-and-compress (mps.py:826-880) through Mps.evolve: the controller accepts
+    the same sub-steps (bond dimensions and occupations follow the reference); guess_dt is derived
+    from the distance of two nearly equal states -- a cancellation of ten digits -- so the
+    reference's own value is defined to ~1e-5 only."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria
+    from renormalizer_b200.mpo import Mpo
+    g = golden("pc")
+    mpo = _device_mpo_with_qn(g)
+    occ = [Mpo(load_mpo(g, f"occ{i}")) for i in range(int(g["nmol"]))]
+    mps = _device_mps_with_coeff(g, "mps0")
+    mps.compress_config = CompressConfig(CompressCriteria.threshold, threshold=1e-5)
+    mps.evolve_config = EvolveConfig(EvolveMethod.prop_and_compress, adaptive=True, guess_dt=0.4,
+                                     adaptive_rtol=1e-4)
+    occs, guesses, dims = [], [], []
+    for _ in range(3):
+        mps = mps.evolve(mpo, 2.0)
+        occs.append([mps.expectation(o) for o in occ])
+        guesses.append(mps.evolve_config.guess_dt)
+        dims.append(mps.bond_dims)
+    assert np.allclose(guesses, g["ada_guess_dt"], rtol=1e-3)
+    assert np.array_equal(np.array(dims), g["ada_bond_dims"])
+    assert np.abs(np.array(occs) - g["ada_occ"]).max() < 1e-9
+    with pytest.raises(ValueError):
+        mps.evolve(mpo, -1.0)                            # check_valid_dt: wrong direction

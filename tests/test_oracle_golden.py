@@ -401,3 +401,27 @@ def test_expand_bond_dimension(golden, tag):
     x, y = admixture(new), admixture(ref)
     assert abs(abs(x.dot_conj(y)) / (x.mp_norm * y.mp_norm) - 1) < 1e-6
     assert abs(x.mp_norm / y.mp_norm - 1) < 1e-6
+
+
+def test_prop_and_compress_adaptive(golden):
+    """Adaptive propagate-and-compress (mps.py:826-880): accepted sub-steps, guess_dt, bond
+    dimensions and occupations follow the reference."""
+    from helpers import load_oracle_mpo
+    from oracle.sweep import evolve_prop_and_compress_adaptive, CompressSpec
+    g = golden("pc")
+    mpo = load_oracle_mpo(g)
+    occ = [load_mpo(g, f"occ{i}") for i in range(int(g["nmol"]))]
+    mps = _load_with_coeff(g, "mps0")
+    spec = CompressSpec("threshold", threshold=1e-5)
+    guess = 0.4
+    occs, guesses, dims = [], [], []
+    for _ in range(3):
+        mps, guess = evolve_prop_and_compress_adaptive(mps, mpo, 2.0, spec, guess, rtol=1e-4)
+        occs.append([mps.expectation(o) for o in occ])
+        guesses.append(guess)
+        dims.append(mps.bond_dims)
+    # guess_dt comes from the distance of two nearly equal states, sqrt(l1 + l2 - 2 Re l12): a
+    # cancellation of ten digits, so the reference's own value is defined to ~1e-5 only
+    assert np.allclose(guesses, g["ada_guess_dt"], rtol=1e-3)
+    assert np.array_equal(np.array(dims), g["ada_bond_dims"])
+    assert np.abs(np.array(occs) - g["ada_occ"]).max() < 1e-10
