@@ -848,3 +848,42 @@ def evolve_prop_and_compress_adaptive(mps, mpo, dt, spec, guess_dt, rtol=5e-4, o
     if normalize:
         new.normalize_mps_only()
     return new, guess
+
+
+def calc_bond_singular_values(mps_in):
+    """Singular values at every bond, padded to a rectangle.  Reference: mps.py:1759-1773
+    (copy, ensure_right_canonical, compress(temp_m_trunc=inf, ret_s=True); mp.py:497-511)."""
+    mps = mps_in.copy()
+    mps.ensure_right_canonical()
+    system = "L" if mps.to_right else "R"
+    s_list = []
+    for idx in mps.iter_idx_list(full=False):
+        shape = mps.sites[idx].shape
+        qnbigl, qnbigr, _ = mps.big_qn([idx])
+        u, sigma, qnlset, v, sigma, qnrset = svd_qn(mps.sites[idx], qnbigl, qnbigr, mps.qntot,
+                                                    system=system, full_matrices=False)
+        s_list.append(sigma)
+        m = len(sigma)
+        if mps.to_right:
+            mps.sites[idx + 1] = np.tensordot(sigma[:, None] * v.T, mps.sites[idx + 1], axes=1)
+            mps.sites[idx] = u.reshape(shape[:-1] + (m,))
+            mps.qn[idx + 1] = np.array(qnlset)
+            mps.qnidx = idx + 1
+        else:
+            mps.sites[idx - 1] = np.tensordot(mps.sites[idx - 1], u * sigma[None, :], axes=1)
+            mps.sites[idx] = v.T.reshape((m,) + shape[1:])
+            mps.qn[idx] = np.array(qnrset)
+            mps.qnidx = idx - 1
+    width = max(len(x) for x in s_list)
+    return np.array([np.pad(x, (0, width - len(x))) for x in s_list])
+
+
+def calc_bond_entropy(mps):
+    """Von Neumann entropy of every bond.  Reference: mps.py:1775-1793, utils/utils.py:41-48."""
+    out = []
+    for sigma in calc_bond_singular_values(mps):
+        p = sigma ** 2
+        p = p / p.sum()
+        p = p[0 < p]
+        out.append(-(p * np.log(p)).sum())
+    return np.array(out)

@@ -471,6 +471,32 @@ class Mps:
             return float(val.real)
         return val
 
+    def calc_bond_singular_values(self) -> np.ndarray:
+        """mps.py:1759-1773: the singular values at every bond (rows padded with zeros), from a
+        compression sweep that truncates nothing on a right-canonical copy."""
+        mps = self.copy()
+        mps.ensure_right_canonical()
+        _, s_array = mps.compress(temp_m_trunc=np.inf, ret_s=True)
+        return s_array
+
+    def calc_bond_entropy(self, s_array=None) -> np.ndarray:
+        """mps.py:1775-1793: von Neumann entropy -Tr(rho ln rho) of either block at every bond."""
+        if s_array is None:
+            s_array = self.calc_bond_singular_values()
+        out = []
+        for sigma in s_array:
+            p = np.asarray(sigma) ** 2
+            p = p / p.sum()
+            p = p[0 < p]
+            out.append(-(p * np.log(p)).sum())
+        return np.array(out)
+
+    def calc_entropy(self, entropy_type):
+        """mps.py:1689-1732; the reduced-density-matrix entropies need the model's site layout."""
+        if entropy_type != "bond":
+            raise NotImplementedError(f"entropy type {entropy_type} (mps.py:1716-1727) is outside the sweep path")
+        return self.calc_bond_entropy()
+
     def distance(self, other) -> float:
         """mp.py:1009-1023."""
         l1 = self.conj().dot(self)

@@ -657,6 +657,35 @@ def gen_expand():
     np.savez_compressed(os.path.join(HERE, "expand.npz"), **out)
 
 
+def gen_entropy():
+    """Bond singular values and von Neumann bond entropies (mps.py:1759-1793) of an evolved exciton
+    state and of a thermal density operator."""
+    from renormalizer.mps import Mps, Mpo, MpDm
+    from renormalizer.utils import CompressConfig, EvolveConfig, EvolveMethod, CompressCriteria
+    out = {}
+    model, nmol = _exciton_model()
+    mpo = Mpo(model)
+    dump_mp("mpo", mpo, out)
+    mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ Mps.ground_state(model, False)
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    mps = mps.expand_bond_dimension(mpo, include_ex=False)
+    for i in range(3):
+        mps = mps.evolve(mpo, 2.0)
+    dm = MpDm.max_entangled_ex(model)
+    dm.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=8)
+    dm.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    dm = dm.expand_bond_dimension(mpo, include_ex=False)
+    for i in range(2):
+        dm = dm.evolve(mpo, -1.0j)
+    for tag, m in (("mps", mps), ("dm", dm)):
+        dump_mp(tag, m, out)
+        dump_mps_meta(tag, m, out)
+        out[f"{tag}_singular_values"] = m.calc_bond_singular_values()
+        out[f"{tag}_bond_entropy"] = m.calc_bond_entropy()
+    np.savez_compressed(os.path.join(HERE, "entropy.npz"), **out)
+
+
 def gen_two_spin():
     """The README quickstart (README.md:36-58): two half spins, sigma+ sigma- exchange, 10 steps
     of Mps.evolve with dt = 0.05, <Z_0> after every step -- with the default propagate-and-
@@ -691,7 +720,7 @@ def gen_two_spin():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm", "stacked", "qc", "exciton",
-                             "two_spin", "thermal", "pc", "expand"]
+                             "two_spin", "thermal", "pc", "expand", "entropy"]
     for name in which:
         print("generating", name, flush=True)
         globals()["gen_" + name]()

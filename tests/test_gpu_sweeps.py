@@ -735,3 +735,18 @@ def test_prop_and_compress_adaptive_golden(golden):
     assert np.abs(np.array(occs) - g["ada_occ"]).max() < 1e-9
     with pytest.raises(ValueError):
         mps.evolve(mpo, -1.0)                            # check_valid_dt: wrong direction
+
+
+@pytest.mark.parametrize("tag", ["mps", "dm"])
+def test_bond_entropy_golden(golden, tag):
+    """Mps.calc_bond_singular_values / calc_bond_entropy (mps.py:1759-1793): a compression sweep
+    that truncates nothing, on the device SVD."""
+    g = golden("entropy")
+    mps = to_device_mps(load_oracle_mps(g, tag, meta=tag))
+    s = mps.calc_bond_singular_values()
+    ref = g[f"{tag}_singular_values"]
+    assert s.shape == ref.shape
+    assert np.abs(s - ref).max() < 1e-12
+    assert np.abs(mps.calc_entropy("bond") - g[f"{tag}_bond_entropy"]).max() < E_TOL
+    with pytest.raises(NotImplementedError):
+        mps.calc_entropy("1site")

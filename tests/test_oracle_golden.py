@@ -425,3 +425,15 @@ def test_prop_and_compress_adaptive(golden):
     assert np.allclose(guesses, g["ada_guess_dt"], rtol=1e-3)
     assert np.array_equal(np.array(dims), g["ada_bond_dims"])
     assert np.abs(np.array(occs) - g["ada_occ"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("tag", ["mps", "dm"])
+def test_bond_entropy(golden, tag):
+    """Bond singular values and von Neumann entropies (mps.py:1759-1793)."""
+    from oracle.sweep import calc_bond_singular_values, calc_bond_entropy
+    g = golden("entropy")
+    mps = load_oracle_mps(g, tag, meta=tag)
+    s = calc_bond_singular_values(mps)
+    assert s.shape == g[f"{tag}_singular_values"].shape
+    assert np.abs(s - g[f"{tag}_singular_values"]).max() < 1e-12
+    assert np.abs(calc_bond_entropy(mps) - g[f"{tag}_bond_entropy"]).max() < 1e-10
