@@ -15,6 +15,17 @@ Every array below is produced by reference code paths:
   holstein.npz  Mpo(holstein_model), Mps.random, optimize_mps (mps/gs.py:54), 1site + 2site
   sbm.npz       SpinBosonModel MPO, expand_bond_dimension'd MPS, Mps.evolve with tdvp_ps
                 (mps/mps.py:1268) and tdvp_ps2 (mps/mps.py:1407), sigma_z trajectory and final MPS
+  stacked.npz   optimize_mps with StackedMpo (mps/mpo.py:483, mps/tests/test_gs.py:148)
+  qc_h6.npz     ab initio DMRG on the reference's H6 FCIDUMP, two quantum numbers (test_gs.py:103)
+  exciton.npz   FMO-like HolsteinModel with long-range J: TDVP-PS of the one-exciton state and of
+                its density operator (MpDm)
+  thermal.npz   imaginary-time TDVP-PS of a density operator (mps/thermalprop.py:96), real-time
+                steps of the thermal state, adaptive_tdvp (mps/mps.py:46)
+  two_spin.npz  the README quickstart with the default integrator, tdvp_ps and tdvp_ps2
+  pc.npz        propagate-and-compress (mps/mps.py:796): fixed step with threshold / fixed
+                truncation, adaptive step
+  expand.npz    expand_bond_dimension(hint_mpo, include_ex=False) (mps/mps.py:1934)
+  entropy.npz   calc_bond_singular_values / calc_bond_entropy (mps/mps.py:1759)
 """
 import os
 import sys
