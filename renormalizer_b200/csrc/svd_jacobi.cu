@@ -1,6 +1,8 @@
-// One-sided (Hestenes) Jacobi SVD of a bond matrix block: A = U diag(S) V^H.
+// SVD of a bond matrix block, A = U diag(S) V^H, by one-sided (Hestenes) Jacobi iteration.
+//   rn_svd        : QR-preconditioned (Drmac-Veselic) block Jacobi -- the product path (svd_qn)
+//   rn_svd_jacobi : the bare iteration on the block itself (scalar kernel below 64 columns)
 //
-// Columns are held as contiguous rows (At[c*ldt + r] = A[r][c]) so the three inner products and
+// Scalar kernel: columns are held as contiguous rows (At[c*ldt + r] = A[r][c]) so the three inner products and
 // the plane rotation of a column pair are coalesced streams reduced with warp shuffles.  A sweep
 // is n-1 rounds of a round-robin tournament; the n/2 disjoint pairs of one round run in parallel,
 // one block per pair.  Rotations are accumulated into V the same way.  High relative accuracy of
@@ -94,7 +96,7 @@ jacobi_round_kernel(typename std::conditional<CPLX, double2, double>::type* __re
 // rotation of a pair is computed from a, b, g exactly as above; G is updated by the same rotations
 // instead of being recomputed from the columns).  Demmel & Veselic's relative accuracy of Jacobi on
 // G = D A D carries over because G is formed from the current columns at every visit.  A sweep is
-// n/16 - 1 launches instead of n - 1, and every column is read twice and written once per launch.
+// 3 (n/16 - 1) launches instead of n - 1, and every column is read twice and written once per round.
 constexpr int JB = 16;            // columns per block
 constexpr int JK = 2 * JB;        // columns per CTA
 constexpr int JBT = 256;          // threads
