@@ -17,7 +17,7 @@ class Mps:
     Reference: renormalizer/mps/mp.py:34-80 (MatrixProduct state), mps/mps.py:118.
     """
 
-    def __init__(self, sites, qn, sigmaqn, qntot, qnidx, to_right, coeff=1.0):
+    def __init__(self, sites, qn, sigmaqn, qntot, qnidx, to_right, coeff=1.0, is_mpo=False):
         self.sites = [np.asarray(s) for s in sites]
         self.qn = [np.asarray(q) for q in qn]
         self.sigmaqn = [np.asarray(s) for s in sigmaqn]
@@ -25,13 +25,16 @@ class Mps:
         self.qnidx = int(qnidx)
         self.to_right = bool(to_right)
         self.coeff = coeff
+        # an operator handled as a matrix product (mpo.py:297-303): canonicalisation balances the
+        # norm between the two factors and the singular values go to the other side (mp.py:258-275)
+        self.is_mpo = bool(is_mpo)
 
     def __len__(self):
         return len(self.sites)
 
     def copy(self):
         return Mps([s.copy() for s in self.sites], [q.copy() for q in self.qn], self.sigmaqn,
-                   self.qntot.copy(), self.qnidx, self.to_right, self.coeff)
+                   self.qntot.copy(), self.qnidx, self.to_right, self.coeff, self.is_mpo)
 
     def to_complex(self):
         m = self.copy()
@@ -92,6 +95,13 @@ class Mps:
                                       system=system, full_matrices=False)
         vt = v.T
         m = u.shape[1]
+        if self.is_mpo:                               # mp.py:258-267
+            if self.to_right:
+                nrm = np.linalg.norm(vt)
+                u, vt = u * nrm, vt / nrm
+            else:
+                nrm = np.linalg.norm(u)
+                u, vt = u / nrm, vt * nrm
         if self.to_right:
             self.sites[idx + 1] = np.tensordot(vt, self.sites[idx + 1], axes=1)
             self.sites[idx] = u.reshape(shape[:-1] + (m,))
@@ -173,7 +183,8 @@ class Mps:
 class Environ:
     """Left/right environment store.  Reference: renormalizer/mps/lib.py:12-129."""
 
-    def __init__(self, mps, mpo, domain=None):
+    def __init__(self, mps, mpo, domain=None, mps_conj=None):
+        """`mps_conj` (optional): the already-conjugated bra state (lib.py:19-31)."""
         self.disk = {}
         self.sentinel = np.ones((1, 1, 1))
         self.disk[("L", -1)] = self.sentinel
@@ -183,20 +194,22 @@ class Environ:
             rng = range(0, n - 1) if dom == "L" else range(n - 1, 0, -1)
             t = self.sentinel
             for i in rng:
-                t = env_update(t, mps.sites[i], mpo[i], dom)
+                t = env_update(t, mps.sites[i], mpo[i], dom,
+                               ms_conj=None if mps_conj is None else mps_conj.sites[i])
                 self.disk[(dom, i)] = t
 
     def read(self, domain, idx):
         return self.disk[(domain, idx)]
 
-    def get_lr(self, domain, idx, mps, mpo, method):
+    def get_lr(self, domain, idx, mps, mpo, method, mps_conj=None):
         if idx < 0 or idx >= len(mps):
             return self.sentinel
         if method == "Enviro":
             return self.read(domain, idx)
         assert method == "System"
         prev = self.read(domain, idx + (-1 if domain == "L" else 1))
-        t = env_update(prev, mps.sites[idx], mpo[idx], domain)
+        t = env_update(prev, mps.sites[idx], mpo[idx], domain,
+                       ms_conj=None if mps_conj is None else mps_conj.sites[idx])
         self.disk[(domain, idx)] = t
         return t
 
@@ -707,14 +720,22 @@ def compress(mps, spec, temp_m_trunc=None):
         else:
             m = min(int(temp_m_trunc), len(sigma))
         u, vt, sigma = u[:, :m], vt[:m, :], sigma[:m]
+        # mp.py:270-275: the singular values go with the centre -- for an operator, the other way
+        sigma_right = mps.to_right != mps.is_mpo
         if mps.to_right:
-            vt = sigma[:, None] * vt
+            if sigma_right:
+                vt = sigma[:, None] * vt
+            else:
+                u = u * sigma[None, :]
             mps.sites[idx + 1] = np.tensordot(vt, mps.sites[idx + 1], axes=1)
             mps.sites[idx] = u.reshape(shape[:-1] + (m,))
             mps.qn[idx + 1] = np.array(qnlset[:m])
             mps.qnidx = idx + 1
         else:
-            u = u * sigma[None, :]
+            if sigma_right:
+                vt = sigma[:, None] * vt
+            else:
+                u = u * sigma[None, :]
             mps.sites[idx - 1] = np.tensordot(mps.sites[idx - 1], u, axes=1)
             mps.sites[idx] = vt.reshape((m,) + shape[1:])
             mps.qn[idx] = np.array(qnrset[:m])
@@ -887,3 +908,62 @@ def calc_bond_entropy(mps):
         p = p[0 < p]
         out.append(-(p * np.log(p)).sum())
     return np.array(out)
+
+
+def mps_conj(mps):
+    new = mps.copy()
+    new.sites = [s.conj() for s in new.sites]
+    return new
+
+
+def variational_compress(state, mpo, sigmaqn_mpo, mpo_to_right, max_bonddim, method="2site",
+                         vguess_m=(5, 5), vrtol=1e-5, vprocedure=None):
+    """A compressed approximation of mpo @ state by sweeps.  Reference: mp.py:513-650
+    (Mpo.contract(algo="variational"), guess=None): the guess is the product of the SVD-compressed
+    operator and state; every site update applies H_eff built from environments with the guess as bra
+    and `state` as ket to the centre tensor of `state` and decomposes the result into the guess
+    (_update_mps); convergence on the relative distance between successive sweeps."""
+    spec = CompressSpec("fixed", max_bonddim=max_bonddim)
+    op = Mps(mpo.sites, mpo.qn, sigmaqn_mpo, mpo.qntot, mpo.qnidx, mpo_to_right, is_mpo=True)
+    c_op = compress(op.copy().canonicalise(), spec, vguess_m[0])
+    c_state = compress(state.copy().canonicalise(), spec, vguess_m[1])
+    mps = mpo_apply(Mpo(c_op.sites, c_op.qn, c_op.qntot, c_op.qnidx), c_state)
+    mps.ensure_left_canonical()
+    if vprocedure is None:                                      # configs.py:159-166
+        vprocedure = ([[max_bonddim, 1.0], [max_bonddim, 0.7]] if method == "1site" else []) + \
+            [[max_bonddim, 0.5], [max_bonddim, 0.3], [max_bonddim, 0.1]] + [[max_bonddim, 0]] * 10
+    environ = Environ(state, mpo.sites, "L", mps_conj=mps_conj(mps))
+    n = len(mps)
+    mps_old = None
+    for isweep, (m_max, percent) in enumerate(vprocedure):
+        for imps in mps.iter_idx_list(full=True):
+            if method == "2site" and ((mps.to_right and imps == n - 1) or (not mps.to_right and imps == 0)):
+                break
+            lmethod, rmethod = ("System", "Enviro") if mps.to_right else ("Enviro", "System")
+            if method == "1site":
+                lidx, cidx, ridx = imps - 1, [imps], imps + 1
+            elif mps.to_right:
+                lidx, cidx, ridx = imps - 1, [imps, imps + 1], imps + 2
+            else:
+                lidx, cidx, ridx = imps - 2, [imps - 1, imps], imps + 1
+            bra = mps_conj(mps)
+            ltensor = environ.get_lr("L", lidx, state, mpo.sites, lmethod, mps_conj=bra)
+            rtensor = environ.get_lr("R", ridx, state, mpo.sites, rmethod, mps_conj=bra)
+            qnbigl, qnbigr, qnmat = mps.big_qn(cidx)
+            mask = get_qn_mask(qnmat, mps.qntot)
+            cmo = [mpo.sites[i] for i in cidx]
+            if method == "1site":
+                cms = state.sites[cidx[0]]
+            else:
+                cms = np.tensordot(state.sites[cidx[0]], state.sites[cidx[1]], axes=1)
+            cout = hop_apply(ltensor, rtensor, cmo, cms)
+            cout[~mask] = 0
+            update_mps(mps, cout, cidx, qnbigl, qnbigr, int(m_max), percent)
+        mps.switch_direction()
+        if isweep > 0 and percent == 0:
+            error = mps_distance(mps, mps_old) / np.sqrt(mps.dot_conj(mps).real)
+            if error < vrtol:
+                break
+        mps_old = mps.copy()
+    mps.canonicalise()
+    return mps

@@ -26,6 +26,7 @@ Every array below is produced by reference code paths:
                 truncation, adaptive step
   expand.npz    expand_bond_dimension(hint_mpo, include_ex=False) (mps/mps.py:1934)
   entropy.npz   calc_bond_singular_values / calc_bond_entropy (mps/mps.py:1759)
+  vcompress.npz Mpo.contract(mps, algo="variational") (mps/mp.py:513)
 """
 import os
 import sys
@@ -697,6 +698,42 @@ def gen_entropy():
     np.savez_compressed(os.path.join(HERE, "entropy.npz"), **out)
 
 
+def gen_vcompress():
+    """Variational compression of mpo @ mps (mp.py:513-650, Mpo.contract(algo="variational")): the
+    sweep over environments with bra = compressed guess and ket = the state, H_eff applied to the
+    ket centre, SVD update of the guess -- for the next round's device implementation."""
+    from renormalizer.mps import Mps, Mpo
+    from renormalizer.utils import CompressConfig, EvolveConfig, EvolveMethod, CompressCriteria
+    out = {}
+    model, nmol = _exciton_model()
+    mpo = Mpo(model)
+    dump_mp("mpo", mpo, out)
+    dump_mpo_meta("mpo", mpo, out)
+    out["mpo_to_right"] = np.array(bool(mpo.to_right))
+    for i in range(len(mpo)):
+        out[f"mpo_sigmaqn_{i}"] = np.array(mpo._get_sigmaqn(i))
+    mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ Mps.ground_state(model, False)
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    mps.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps, adaptive=False)
+    mps = mps.expand_bond_dimension(mpo, include_ex=False)
+    for i in range(2):
+        mps = mps.evolve(mpo, 2.0)
+    dump_mp("mps", mps, out)
+    dump_mps_meta("mps", mps, out)
+    for method in ("1site", "2site"):
+        m = mps.copy()
+        m.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=8, vmethod=method)
+        new = mpo.contract(m, algo="variational")
+        exact = mpo.apply(mps)
+        out[f"{method}_bond_dims"] = np.array(new.bond_dims)
+        out[f"{method}_norm"] = np.array(new.mp_norm)
+        out[f"{method}_overlap_exact"] = np.array(new.conj().dot(exact))
+        out[f"{method}_exact_norm"] = np.array(exact.mp_norm)
+        dump_mp(f"{method}_new", new, out)
+        dump_mps_meta(f"{method}_new", new, out)
+    np.savez_compressed(os.path.join(HERE, "vcompress.npz"), **out)
+
+
 def gen_two_spin():
     """The README quickstart (README.md:36-58): two half spins, sigma+ sigma- exchange, 10 steps
     of Mps.evolve with dt = 0.05, <Z_0> after every step -- with the default propagate-and-
@@ -731,7 +768,7 @@ def gen_two_spin():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["kernels", "svdqn", "krylov", "davidson", "holstein", "sbm", "stacked", "qc", "exciton",
-                             "two_spin", "thermal", "pc", "expand", "entropy"]
+                             "two_spin", "thermal", "pc", "expand", "entropy", "vcompress"]
     for name in which:
         print("generating", name, flush=True)
         globals()["gen_" + name]()

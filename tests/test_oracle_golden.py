@@ -437,3 +437,27 @@ def test_bond_entropy(golden, tag):
     assert s.shape == g[f"{tag}_singular_values"].shape
     assert np.abs(s - g[f"{tag}_singular_values"]).max() < 1e-12
     assert np.abs(calc_bond_entropy(mps) - g[f"{tag}_bond_entropy"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_variational_compress(golden, method):
+    """Mpo.contract(mps, algo="variational") (mp.py:513-650): the oracle restatement follows the
+    reference (bond dimensions, norm, overlap with the exact product, the state itself).  The
+    device implementation is next round's work; this pins what it will be checked against."""
+    from helpers import load_oracle_mpo
+    from oracle.sweep import variational_compress, mpo_apply
+    g = golden("vcompress")
+    mpo = load_oracle_mpo(g)
+    n = len(mpo)
+    state = load_oracle_mps(g, "mps", meta="mps")
+    np.random.seed(0)
+    new = variational_compress(state, mpo, [g[f"mpo_sigmaqn_{i}"] for i in range(n)], bool(g["mpo_to_right"]),
+                               max_bonddim=8, method=method)
+    assert new.bond_dims == list(g[f"{method}_bond_dims"])
+    assert abs(new.mp_norm - float(g[f"{method}_norm"])) < 1e-9
+    exact = mpo_apply(mpo, state)
+    assert abs(new.dot_conj(exact) - complex(g[f"{method}_overlap_exact"])) < 1e-9
+    ref = load_oracle_mps(g, f"{method}_new", meta=f"{method}_new")
+    assert abs(abs(ref.dot_conj(new)) / (ref.mp_norm * new.mp_norm) - 1) < 1e-8
+    # a compression: close to the exact product
+    assert abs(new.dot_conj(exact)) / (new.mp_norm * exact.mp_norm) > 1 - 1e-6
