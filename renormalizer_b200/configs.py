@@ -23,7 +23,8 @@ class EvolveMethod(Enum):
 
 
 class CompressConfig:
-    def __init__(self, criteria=CompressCriteria.threshold, threshold=1e-3, max_bonddim=32):
+    def __init__(self, criteria=CompressCriteria.threshold, threshold=1e-3, max_bonddim=32,
+                 vmethod="2site", vprocedure=None, vrtol=1e-5, vguess_m=(5, 5)):
         if isinstance(criteria, str):
             criteria = CompressCriteria[criteria]
         self.criteria = criteria
@@ -31,6 +32,15 @@ class CompressConfig:
         self.bond_dim_max_value = max_bonddim
         self.max_dims = None
         self.ofs = None
+        # variational compression (configs.py:156-170)
+        self.vmethod = vmethod
+        if vprocedure is None:
+            head = [[max_bonddim, 1.0], [max_bonddim, 0.7]] if vmethod == "1site" else []
+            vprocedure = head + [[max_bonddim, 0.5], [max_bonddim, 0.3], [max_bonddim, 0.1]] \
+                + [[max_bonddim, 0]] * 10
+        self.vprocedure = vprocedure
+        self.vrtol = vrtol
+        self.vguess_m = vguess_m
 
     @property
     def threshold(self):

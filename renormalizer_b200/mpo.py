@@ -8,15 +8,32 @@ from .ops import MpoSite
 
 
 class Mpo:
-    def __init__(self, site_tensors, offset=0.0, qn=None, qntot=None, qnidx=None):
+    def __init__(self, site_tensors, offset=0.0, qn=None, qntot=None, qnidx=None, sigmaqn=None,
+                 to_right=False):
         """`qn` (one array per bond), `qntot` and `qnidx` are the operator's quantum numbers
         (mp.py:34-80); only `apply` / `contract` read them, and an operator that conserves every
-        quantum number (all zero, the default) needs none."""
+        quantum number (all zero, the default) needs none.  `sigmaqn` (per site, shape (d, d, nq):
+        Mpo._get_sigmaqn, mpo.py:293-295) and `to_right` are needed only to compress the operator
+        itself (the default guess of the variational compression)."""
         self._sites = [w if isinstance(w, MpoSite) else MpoSite(w) for w in site_tensors]
         self.offset = offset
         self.qn = None if qn is None else [np.asarray(q) for q in qn]
         self.qntot = None if qntot is None else np.asarray(qntot)
         self.qnidx = len(self._sites) - 1 if qnidx is None else int(qnidx)
+        self.sigmaqn = None if sigmaqn is None else [np.asarray(q) for q in sigmaqn]
+        self.to_right = bool(to_right)
+
+    def as_matrix_product(self, nq=1):
+        """The operator as a matrix product with two physical indices per site (an `Mps` object
+        with is_mpo set): what MatrixProduct.canonicalise / compress act on for an Mpo."""
+        from .mps import Mps
+        qn = self.qn if self.qn is not None else [np.zeros((d, nq), dtype=int) for d in self.bond_dims]
+        qntot = self.qntot if self.qntot is not None else np.zeros(nq, dtype=int)
+        sq = self.sigmaqn if self.sigmaqn is not None else \
+            [np.zeros((d, d, nq), dtype=int) for d in self.pbond_list]
+        mp = Mps([s.dense for s in self._sites], qn, sq, qntot, self.qnidx, self.to_right)
+        mp.is_mpo = True
+        return mp
 
     def __len__(self):
         return len(self._sites)
@@ -124,8 +141,10 @@ class Mpo:
 
     def contract(self, mps, algo="svd"):
         """An approximation of mpo @ mps: apply -> canonicalise -> compress (mpo.py:391-425)."""
+        if algo == "variational":
+            return mps.variational_compress(self)
         if algo != "svd":
-            raise NotImplementedError("variational compression is outside the accelerated path (mp.py:513)")
+            raise AssertionError(f"unknown compression algorithm {algo}")
         new = self.apply(mps)
         new.canonicalise()
         new.compress()

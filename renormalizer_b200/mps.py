@@ -17,7 +17,7 @@ from .configs import CompressConfig, CompressCriteria, EvolveConfig, OptimizeCon
 from .hop_expr import hop_expr_dtype
 from .krylov import expm_krylov
 from .lib import Environ, contract_one_site
-from .svd_qn import add_outer, svd_qn, select_basis, eigh_qn, economic_rank
+from .svd_qn import add_outer, svd_qn, select_basis, eigh_qn, economic_rank, qn_mask_outer
 
 
 class Mps:
@@ -32,6 +32,9 @@ class Mps:
         self.compress_config = CompressConfig()
         self.optimize_config = OptimizeConfig()
         self.evolve_config = EvolveConfig()
+        # True for an operator handled as a matrix product (Mpo.as_matrix_product): canonicalisation
+        # balances the norm between the factors and the singular values go the other way
+        self.is_mpo = False
 
     # ------------------------------------------------------------------ construction / transfer
     @classmethod
@@ -68,6 +71,7 @@ class Mps:
         new.qnidx = self.qnidx
         new.to_right = self.to_right
         new.coeff = self.coeff
+        new.is_mpo = getattr(self, "is_mpo", False)
         new.compress_config = self.compress_config.copy()
         new.optimize_config = self.optimize_config.copy()
         new.evolve_config = self.evolve_config.copy()
@@ -235,14 +239,23 @@ class Mps:
         return self
 
     def _update_ms(self, idx, u, vt, sigma=None, qnlset=None, qnrset=None, m_trunc=None):
-        """mp.py:245-295 for an MPS (no MPO norm balancing)."""
+        """mp.py:245-295."""
         if m_trunc is None:
             m_trunc = u.shape[1]
         u = u[:, :m_trunc]
         vt = vt[:m_trunc, :]
-        if sigma is not None:
+        is_mpo = getattr(self, "is_mpo", False)
+        if sigma is None:
+            if is_mpo:                              # canonicalise an operator: balance the norm
+                if self.to_right:
+                    nrm = torch.linalg.vector_norm(vt)
+                    u, vt = u * nrm, vt / nrm
+                else:
+                    nrm = torch.linalg.vector_norm(u)
+                    u, vt = u / nrm, vt * nrm
+        else:
             sig = torch.from_numpy(np.ascontiguousarray(sigma[:m_trunc])).to(u.device).to(u.dtype)
-            if self.to_right:
+            if self.to_right != is_mpo:             # (mps, to_right) or (mpo, to_left)
                 vt = vt * sig[:, None]
             else:
                 u = u * sig[None, :]
@@ -538,6 +551,90 @@ class Mps:
 
     def __add__(self, other):
         return self.add(other)
+
+    def variational_compress(self, mpo=None, guess=None):
+        """A compressed approximation of mpo @ self by sweeps, mp.py:513-650: environments with the
+        guess as bra and `self` as ket, H_eff applied to the centre tensor of `self`, the result
+        decomposed into the guess (_update_mps); converged when successive sweeps agree to vrtol.
+        `self` is not overwritten, `guess` is.  The bra and ket bonds differ; every tensor is
+        zero-padded to one common bond dimension per bond, so the sweeps run on the same (square)
+        environment and H_eff kernels as DMRG and the results are sliced back."""
+        if mpo is None:
+            raise NotImplementedError("Recommend to use svd to compress a single mps/mpo/mpdm.")
+        if guess is None:
+            nq = len(self.qntot)
+            op = mpo.as_matrix_product(nq)
+            op.compress_config = self.compress_config.copy()
+            compressed_op = op.canonicalise().compress(temp_m_trunc=self.compress_config.vguess_m[0])
+            compressed_mps = self.copy().canonicalise().compress(temp_m_trunc=self.compress_config.vguess_m[1])
+            from .mpo import Mpo
+            guess = Mpo([asnumpy(t) for t in compressed_op], qn=compressed_op.qn, qntot=compressed_op.qntot,
+                        qnidx=compressed_op.qnidx).apply(compressed_mps)
+        mps = guess
+        mps.ensure_left_canonical()
+        procedure = mps.compress_config.vprocedure
+        method = mps.compress_config.vmethod
+        n = self.site_num
+        cplx = self.is_complex or mps.is_complex
+        dtype = torch.complex128 if cplx else torch.float64
+        limit = max(int(c.bond_dim_max_value) if isinstance(c, CompressConfig) else int(c) for c, _ in procedure)
+        big = [max(a, b, limit) if 0 < i < n else 1
+               for i, (a, b) in enumerate(zip(self.bond_dims, mps.bond_dims))]
+
+        def pad(t, i):
+            out = torch.zeros((big[i],) + tuple(t.shape[1:-1]) + (big[i + 1],), dtype=dtype, device=t.device)
+            out[:t.shape[0], ..., :t.shape[-1]] = t
+            return out
+
+        ket = [pad(t, i) for i, t in enumerate(self._mp)]
+
+        def bra():                                  # the conjugated guess, padded (mp.py:600-607)
+            return [pad(t.conj(), i) for i, t in enumerate(mps._mp)]
+
+        environ = Environ(ket, mpo, "L", mps_conj=bra())
+        mps_old = None
+        for isweep, (compress_config, percent) in enumerate(procedure):
+            if isinstance(compress_config, CompressConfig):
+                mps.compress_config = compress_config
+            elif isinstance(compress_config, (int, np.integer)):
+                mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=int(compress_config))
+            else:
+                assert False
+            for imps in mps.iter_idx_list(full=True):
+                if method == "2site" and ((mps.to_right and imps == n - 1) or ((not mps.to_right) and imps == 0)):
+                    break
+                lmethod, rmethod = ("System", "Enviro") if mps.to_right else ("Enviro", "System")
+                if method == "1site":
+                    lidx, cidx, ridx = imps - 1, [imps], imps + 1
+                elif method == "2site":
+                    if mps.to_right:
+                        lidx, cidx, ridx = imps - 1, [imps, imps + 1], imps + 2
+                    else:
+                        lidx, cidx, ridx = imps - 2, [imps - 1, imps], imps + 1
+                else:
+                    assert False
+                conj = bra()
+                ltensor = environ.GetLR("L", lidx, ket, mpo, itensor=None, method=lmethod, mps_conj=conj)
+                rtensor = environ.GetLR("R", ridx, ket, mpo, itensor=None, method=rmethod, mps_conj=conj)
+                qnbigl, qnbigr, _ = mps._get_big_qn(cidx, need_mat=False)
+                qn_mask = qn_mask_outer(qnbigl, qnbigr, mps.qntot)
+                cmo = [mpo[idx] for idx in cidx]
+                cms = ket[cidx[0]] if method == "1site" else ops.tensordot1(ket[cidx[0]], ket[cidx[1]])
+                hop = hop_expr_dtype(ltensor, rtensor, cmo, list(cms.shape), dtype)
+                cout = hop(cms)
+                hop.close()
+                # back to the guess's own bond dimensions; drop what violates the quantum numbers
+                cout = cout[:mps.bond_dims[cidx[0]], ..., :mps.bond_dims[cidx[-1] + 1]].contiguous()
+                cout = cout * torch.from_numpy(qn_mask).to(cout.device).to(cout.dtype)
+                mps._update_mps(cout, cidx, qnbigl, qnbigr, percent)
+            mps._switch_direction()
+            if isweep > 0 and percent == 0:
+                error = mps.distance(mps_old) / np.sqrt(mps.dot(mps.conj()).real)
+                if error < mps.compress_config.vrtol:
+                    break
+            mps_old = mps.copy()
+        mps.canonicalise()
+        return mps
 
     def expand_bond_dimension(self, hint_mpo=None, coef=1e-10, include_ex=True, ex_mps=None):
         """Fill the bond dimensions up to compress_config's limit with states reached through

@@ -750,3 +750,31 @@ def test_bond_entropy_golden(golden, tag):
     assert np.abs(mps.calc_entropy("bond") - g[f"{tag}_bond_entropy"]).max() < E_TOL
     with pytest.raises(NotImplementedError):
         mps.calc_entropy("1site")
+
+
+@pytest.mark.parametrize("method", ["1site", "2site"])
+def test_variational_compress_golden(golden, method):
+    """Mpo.contract(mps, algo="variational") (mp.py:513-650): the default guess (SVD-compressed
+    operator times SVD-compressed state), the sweeps with the guess as bra and the state as ket on
+    the device environment / H_eff / SVD kernels; bond dimensions, norm, overlap with the exact
+    product and the state itself follow the reference."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria
+    from renormalizer_b200.mpo import Mpo
+    g = golden("vcompress")
+    n = int(g["mpo_n"])
+    mpo = Mpo(load_mpo(g), qn=[g[f"mpo_qn_{i}"] for i in range(n + 1)], qntot=g["mpo_qntot"],
+              qnidx=int(g["mpo_qnidx"]), sigmaqn=[g[f"mpo_sigmaqn_{i}"] for i in range(n)],
+              to_right=bool(g["mpo_to_right"]))
+    state = to_device_mps(load_oracle_mps(g, "mps", meta="mps"))
+    state.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=8, vmethod=method)
+    before = [t.clone() for t in state]
+    np.random.seed(0)
+    new = mpo.contract(state, algo="variational")
+    assert all(torch.equal(a, b) for a, b in zip(before, state))          # `self` is not overwritten
+    assert new.bond_dims == list(g[f"{method}_bond_dims"])
+    assert abs(new.mp_norm - float(g[f"{method}_norm"])) < 1e-8
+    exact = mpo.apply(state)
+    assert abs(new.conj().dot(exact) - complex(g[f"{method}_overlap_exact"])) < 1e-8
+    ref = to_device_mps(load_oracle_mps(g, f"{method}_new", meta=f"{method}_new"))
+    assert abs(abs(ref.conj().dot(new)) / (ref.mp_norm * new.mp_norm) - 1) < T_TOL
+    assert abs(new.conj().dot(exact)) / (new.mp_norm * exact.mp_norm) > 1 - 1e-6
