@@ -166,3 +166,20 @@ def test_mpo_algebra_for_omega_targeting():
     sq = shifted.squared()
     assert sq.bond_dims == [b * b for b in shifted.bond_dims]
     assert np.allclose(_dense_from_mpo(sq.to_numpy()), Hs @ Hs, atol=1e-11)
+
+
+def test_sweep_host_logic_with_stubbed_kernels():
+    """The host side of the sweeps (bookkeeping, truncation, drivers) against the reference's goldens
+    with the C-ABI kernels replaced by the NumPy/torch test double `tests/_host_logic_stub.py`, in a
+    subprocess so that the patched modules do not leak into this session."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, PYTHONPATH=here + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    select = ("expand or adaptive_golden or entropy or prop_and_compress or quickstart or thermal or exciton "
+              "or density or variational or stacked or dmrg_qc_h6_golden or dmrg_holstein_golden")
+    cmd = [sys.executable, "-m", "pytest", "-p", "_host_logic_stub", os.path.join(here, "test_gpu_sweeps.py"),
+           "-q", "-x", "-p", "no:cacheprovider", "-k", f"({select}) and not tensor_path"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(here))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout
