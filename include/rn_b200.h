@@ -102,7 +102,8 @@ int rn_env_update(void* stream, int cplx, int domain, const void* env, int Ea, i
  *   rn_qr : A = Q R,  Q (m x k) orthonormal columns, R (k x n) upper trapezoidal (LAPACK signs)
  *   rn_lq : A = L Q,  L (m x k) lower trapezoidal,   Q (k x n) orthonormal rows
  *   rn_svd_jacobi : A = U diag(S) Vh, U (m x k), Vh (k x n); S is NOT sorted; *sweeps_out (host
- *                   int, may be NULL) receives the number of Jacobi sweeps.  The bare iteration.
+ *                   int, may be NULL) receives the number of Jacobi sweeps, NEGATED when the last
+ *                   sweep still rotated (no convergence within max_sweeps).  The bare iteration.
  *   rn_svd        : the same decomposition, QR-preconditioned (norm-ordered QR, QR of R^H, Jacobi
  *                   on the k x k factor): what scipy.linalg.svd(..., lapack_driver="gesdd") is
  *                   replaced by in optimized_svd (svd_qn.py:13-49) for every block that is not

@@ -85,9 +85,9 @@ _fast = {"lib": None, "dev": -1, "raw_stream": None}
 
 def get(device_index=None):
     """Library handle, initialised for the given (default: current) CUDA device."""
-    if device_index is None and _fast["lib"] is not None:
-        return _fast["lib"]
     import torch
+    if device_index is None and _fast["lib"] is not None and _fast["dev"] == torch.cuda.current_device():
+        return _fast["lib"]
     if not torch.cuda.is_available():
         raise RnError("renormalizer_b200 needs a CUDA device (B200, sm_100a); none is available "
                       "and there is no CPU fallback")
@@ -113,20 +113,19 @@ def check(err, what):
 def stream_ptr():
     """cudaStream_t of torch's current stream on the initialised device (fast path: no Python-side
     device bookkeeping)."""
+    import torch
+    dev = torch.cuda.current_device()
+    if dev != _fast["dev"]:
+        get(dev)                    # a torch.cuda.set_device since the last call: re-key on it
     raw = _fast["raw_stream"]
     if raw is not None:
-        return raw(_fast["dev"])
-    import torch
+        return raw(dev)
     return torch.cuda.current_stream().cuda_stream
 
 
 class LaunchCounter:
     """Kernels launched by librn_b200.so (counted inside the library at every launch site);
     bench.py reports the difference over the timed region as gpu_launches."""
-
-    @classmethod
-    def add(cls, n):          # kept for call-site compatibility; the library counts for itself
-        pass
 
     @classmethod
     def total(cls):

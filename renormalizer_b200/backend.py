@@ -77,6 +77,8 @@ def asxp(array, dtype=None):
         t = t.to(dtype)
     elif t.dtype not in (torch.float64, torch.complex128):
         t = t.to(torch.complex128 if t.is_complex() else torch.float64)
+    if t.is_conj():          # a lazy conj view shares storage with its source: kernels read raw memory
+        t = t.resolve_conj()
     return t.contiguous()
 
 

@@ -400,6 +400,7 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
   const int N = (nt + 1) & ~1;  // even number of players
   const double tol = sqrt((double)mt) * 2.220446049250313e-16;
   int sweeps = 0;
+  bool converged = nt <= 1;
   static int block_on = -1;                 // RN_SVD_BLOCK=0 keeps the scalar kernel (diagnostics)
   if (block_on < 0) {
     const char* e = getenv("RN_SVD_BLOCK");
@@ -444,10 +445,11 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
       int h = 0;
       RN_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
       RN_CHECK(cudaStreamSynchronize(st));
-      if (!h) { ++sweeps; break; }
+      if (!h) { ++sweeps; converged = true; break; }
     }
   }
-  if (sweeps_out) *sweeps_out = sweeps;
+  // a negative count reports that the last sweep still rotated (not converged in max_sweeps)
+  if (sweeps_out) *sweeps_out = converged ? sweeps : -sweeps;
   { RN_LAUNCH(jacobi_finalize_kernel<CPLX>, nt, J_THREADS, 0, st, At, mt, ldt, S); rn::g_launches++; }
   RN_LAUNCH_CHECK();
   RN_CHECK(cudaFreeAsync(flag, st));

@@ -211,3 +211,189 @@ def random_mps_qn(sigmaqn, qntot, m_max, rng):
     last /= np.linalg.norm(last)
     sites.append(last)
     return sites, qn
+
+
+# ---------------------------------------------------------------------------------------------
+# Ab initio (quantum chemistry) Hamiltonians in spin orbitals, renormalizer/model/h_qc.py:146-221:
+#     H = sum_pq h1e[p,q] a+_p a_q + sum_pqrs h2e[p,q,r,s] a+_p a+_q a_r a_s
+# after the Jordan-Wigner transformation of h_qc.py:150-159 (a+_j = Z_0 .. Z_{j-1} sigma-_j with
+# index 1 = occupied), one half-spin site per spin orbital, quantum numbers (N_alpha, N_beta).
+# The reference builds the MPO symbolically (bipartite-graph algorithm, mpo.py); here the operator
+# sum is turned into an MPO numerically: site by site, the coefficient matrix between the left
+# bond states extended by the local operator and the distinct remaining operator strings is
+# rank-factorised (quantum-number block by block), which yields the same minimal bond dimensions.
+# ---------------------------------------------------------------------------------------------
+_JW_MATS = [np.eye(2), np.diag([1.0, -1.0]), np.diag([1.0], k=1), np.diag([1.0], k=-1),
+            np.diag([1.0, 0.0]), np.diag([0.0, 1.0])]          # I, Z, sigma+ (a), sigma- (a+), 1-n, n
+_JW_I, _JW_Z, _JW_P, _JW_M = 0, 1, 2, 3
+
+
+def _jw_table():
+    """Multiplication table of the local alphabet: mats[i] @ mats[j] = sign * mats[k] (sign 0: zero)."""
+    nsym = len(_JW_MATS)
+    idx = np.zeros((nsym, nsym), dtype=np.int8)
+    sgn = np.zeros((nsym, nsym), dtype=np.int8)
+    for i in range(nsym):
+        for j in range(nsym):
+            prod = _JW_MATS[i] @ _JW_MATS[j]
+            for k in range(nsym):
+                for s in (1, -1):
+                    if np.array_equal(prod, s * _JW_MATS[k]):
+                        idx[i, j], sgn[i, j] = k, s
+    return idx, sgn
+
+
+def qc_operator_strings(h1e, h2e):
+    """Operator strings of the Jordan-Wigner transformed Hamiltonian: (strings, coefs) with
+    strings[t, l] the index into the local alphabet (I, Z, sigma+, sigma-, 1-n, n) of term t on
+    spin orbital l; equal strings are merged."""
+    n = h1e.shape[0]
+    tidx, tsgn = _jw_table()
+    sites = np.arange(n)[None, :]
+    all_str, all_c = [], []
+    for ints, kinds in ((h1e, (_JW_M, _JW_P)), (h2e, (_JW_M, _JW_M, _JW_P, _JW_P))):
+        orb = np.argwhere(ints != 0)
+        if len(orb) == 0:
+            continue
+        coef = ints[tuple(orb.T)].astype(float)
+        cur = np.zeros((len(orb), n), dtype=np.int8)
+        sign = np.ones(len(orb), dtype=np.int64)
+        for f, kind in enumerate(kinds):
+            j = orb[:, f:f + 1]
+            fac = np.where(sites < j, _JW_Z, np.where(sites == j, kind, _JW_I)).astype(np.int8)
+            sign = sign * np.prod(tsgn[cur, fac].astype(np.int64), axis=1)
+            cur = tidx[cur, fac]
+        keep = sign != 0
+        all_str.append(cur[keep])
+        all_c.append(coef[keep] * sign[keep])
+    strings = np.concatenate(all_str)
+    coefs = np.concatenate(all_c)
+    uniq, inv = np.unique(strings, axis=0, return_inverse=True)
+    summed = np.zeros(len(uniq))
+    np.add.at(summed, inv.reshape(-1), coefs)
+    keep = np.abs(summed) > 1e-15 * np.abs(summed).max()
+    return uniq[keep], summed[keep]
+
+
+def qc_sigmaqn(norbs):
+    """h_qc.py:209-216: even spin orbitals carry (1, 0) when occupied, odd ones (0, 1)."""
+    return [np.array([[0, 0], [1, 0]]) if i % 2 == 0 else np.array([[0, 0], [0, 1]]) for i in range(norbs)]
+
+
+def operator_sum_mpo(strings, coefs, mats, sym_qn, tol=1e-13):
+    """MPO site tensors W[b, up, down, f] of sum_t coefs[t] prod_l mats[strings[t, l]] (site l).
+
+    sym_qn[s, :] is the change of the conserved quantum numbers produced by symbol s; every term
+    must conserve them.  Returns (sites, bond quantum numbers)."""
+    strings = np.asarray(strings)
+    nterm, n = strings.shape
+    nsym = len(mats)
+    sym_qn = np.asarray(sym_qn)
+    mats = np.stack(mats)
+    suf, A = strings, np.asarray(coefs, dtype=float)[None, :].copy()
+    state_qn = np.zeros((1, sym_qn.shape[1]), dtype=int)
+    sites, bond_qn = [], [state_qn]
+    smax = 0.0
+    for i in range(n):
+        ops = suf[:, 0].astype(int)
+        ns = A.shape[0]
+        if i == n - 1:
+            w = np.zeros((ns, mats.shape[1], mats.shape[2], 1))
+            for u, o in enumerate(ops):
+                w[:, :, :, 0] += A[:, u, None, None] * mats[o][None]
+            sites.append(w)
+            bond_qn.append(np.zeros((1, sym_qn.shape[1]), dtype=int))
+            break
+        urest, inv = np.unique(suf[:, 1:], axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        # rows (state, op) grouped by their quantum number; each group only meets the columns its
+        # (state, op) pairs point to
+        groups = {}
+        for o in np.unique(ops):
+            cols_o = np.nonzero(ops == o)[0]
+            sub = A[:, cols_o]
+            live = np.nonzero(np.abs(sub).max(axis=1) > 0)[0]
+            for s in live:
+                groups.setdefault(tuple(state_qn[s] + sym_qn[o]), []).append((s, o, cols_o))
+        q_cols, q_rows, r_blocks, new_qn = [], [], [], []
+        for g in sorted(groups):
+            members = groups[g]
+            cols = np.unique(np.concatenate([inv[c] for _, _, c in members]))
+            pos = {c: k for k, c in enumerate(cols)}
+            sub = np.zeros((len(members), len(cols)))
+            for r, (s, o, cols_o) in enumerate(members):
+                sub[r, [pos[c] for c in inv[cols_o]]] = A[s, cols_o]
+            # rank factorisation sub = Q R through the LQ factorisation of the (short, wide) block
+            qt, lt = np.linalg.qr(sub.T)                  # sub = lt.T @ qt.T
+            u, sv, vh = np.linalg.svd(lt.T, full_matrices=False)
+            smax = max(smax, sv[0] if len(sv) else 0.0)
+            k = int(np.count_nonzero(sv > tol * smax))
+            if k == 0:
+                continue
+            q_rows.append(members)
+            q_cols.append(u[:, :k])
+            r_blocks.append((cols, (sv[:k, None] * vh[:k]) @ qt.T))
+            new_qn += [g] * k
+        ktot = len(new_qn)
+        w = np.zeros((ns, mats.shape[1], mats.shape[2], ktot))
+        a_new = np.zeros((ktot, len(urest)))
+        k0 = 0
+        for members, q, (cols, r) in zip(q_rows, q_cols, r_blocks):
+            k = q.shape[1]
+            for row, (s, o, _) in enumerate(members):
+                w[s, :, :, k0:k0 + k] += mats[o][:, :, None] * q[row][None, None, :]
+            a_new[k0:k0 + k, cols] = r
+            k0 += k
+        sites.append(w)
+        state_qn = np.array(new_qn, dtype=int).reshape(ktot, -1)
+        bond_qn.append(state_qn)
+        suf, A = urest, a_new
+    return sites, bond_qn
+
+
+def qc_mpo(h1e, h2e, tol=1e-13):
+    """MPO of the ab initio Hamiltonian (spin orbitals, Jordan-Wigner) with (N_alpha, N_beta) bond
+    quantum numbers; the nuclear repulsion is not included (as in the reference's model)."""
+    n = h1e.shape[0]
+    strings, coefs = qc_operator_strings(np.asarray(h1e), np.asarray(h2e))
+    # quantum-number change per symbol depends on the spin of the orbital: build per-site tables
+    # by giving sigma- (creation) +1 and sigma+ (annihilation) -1 in the orbital's spin component
+    sites, bond_qn = _qc_operator_sum(strings, coefs, n, tol)
+    return sites, bond_qn
+
+
+def _qc_operator_sum(strings, coefs, n, tol):
+    # operator_sum_mpo takes one symbol table for all sites; spin alternates between sites, so the
+    # alphabet is doubled: symbols 0-5 on alpha (even) orbitals, 6-11 on beta (odd) orbitals
+    strings = strings.astype(np.int16).copy()
+    strings[:, 1::2] += len(_JW_MATS)
+    mats = _JW_MATS + _JW_MATS
+    qn = np.zeros((2 * len(_JW_MATS), 2), dtype=int)
+    qn[_JW_M] = (1, 0)
+    qn[_JW_P] = (-1, 0)
+    qn[len(_JW_MATS) + _JW_M] = (0, 1)
+    qn[len(_JW_MATS) + _JW_P] = (0, -1)
+    return operator_sum_mpo(strings, coefs, mats, qn, tol)
+
+
+def random_qc_integrals(nspatial, rng, decay=0.35):
+    """Synthetic integrals of the shape read_fcidump returns (h_qc.py:15-72): symmetric one-electron
+    matrix, two-electron integrals with the 8-fold symmetry of real orbitals, spin-orbital form and
+    antisymmetrised as int_to_h does.  Off-diagonal elements decay with the orbital distance so the
+    ground state has the area-law structure of a localised-orbital calculation."""
+    n = nspatial
+    dist = np.abs(np.arange(n)[:, None] - np.arange(n)[None, :])
+    h = rng.standard_normal((n, n)) * np.exp(-decay * dist)
+    h = 0.5 * (h + h.T) - np.diag(np.linspace(1.0, 0.0, n))
+    # (pq|rs) = sum_k L[k,p,q] L[k,r,s] with symmetric L: positive, 8-fold symmetric
+    nk = 2 * n
+    lvec = rng.standard_normal((nk, n, n)) * np.exp(-decay * dist)[None] / np.sqrt(nk)
+    lvec = 0.5 * (lvec + lvec.transpose(0, 2, 1))
+    eri = np.einsum("kpq,krs->pqrs", lvec, lvec)
+    ns = 2 * n
+    p = np.arange(ns)
+    sh = np.where((p[:, None] % 2) == (p[None, :] % 2), h[p[:, None] // 2, p[None, :] // 2], 0.0)
+    P, Q, R, S = np.meshgrid(p, p, p, p, indexing="ij")
+    seri = np.where((P % 2 == S % 2) & (Q % 2 == R % 2), eri[P // 2, S // 2, Q // 2, R // 2], 0.0)
+    aseri = np.where((P < Q) & (R < S), seri - seri.transpose(0, 1, 3, 2), 0.0)
+    return sh, aseri

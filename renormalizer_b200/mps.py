@@ -511,7 +511,12 @@ class Mps:
         return self.calc_bond_entropy()
 
     def distance(self, other) -> float:
-        """mp.py:1009-1023."""
+        """mp.py:1009-1023 with the coeff rule of mps.py:1810-1816."""
+        if not np.allclose(self.coeff, other.coeff):
+            self.scale(self.coeff, inplace=True)
+            other.scale(other.coeff, inplace=True)
+            self.coeff = 1
+            other.coeff = 1
         l1 = self.conj().dot(self)
         l2 = other.conj().dot(other)
         l12 = self.conj().dot(other)
@@ -794,7 +799,10 @@ class Mps:
         """One-site projector-splitting TDVP step (mps.py:1268-1404, Krylov local solver):
         forward half sweep and backward half sweep, each site evolved by dt/2 with H_eff and each
         bond matrix evolved backwards with the zero-site H_eff."""
-        if np.iscomplex(evolve_dt):
+        # mps.py:1272-1279: imaginary time keeps the state's dtype.  A step with both a real and an
+        # imaginary part makes exp(-i dt H_eff) complex, so a real state is promoted (the reference's
+        # NumPy arithmetic promotes implicitly).
+        if np.iscomplex(evolve_dt) and complex(evolve_dt).real == 0:
             mps = self.copy()
         else:
             mps = self.to_complex()
@@ -855,7 +863,10 @@ class Mps:
         pair of neighbouring sites is evolved forward by dt/2 with the two-site H_eff and split by
         the truncating SVD of `_update_mps`; the site that moves on with the sweep is evolved
         backwards with the one-site H_eff and re-canonicalised."""
-        if np.iscomplex(evolve_dt):
+        # mps.py:1272-1279: imaginary time keeps the state's dtype.  A step with both a real and an
+        # imaginary part makes exp(-i dt H_eff) complex, so a real state is promoted (the reference's
+        # NumPy arithmetic promotes implicitly).
+        if np.iscomplex(evolve_dt) and complex(evolve_dt).real == 0:
             mps = self.copy()
         else:
             mps = self.to_complex()

@@ -24,12 +24,22 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _dense(t):
+    """What the C ABI reads is t.data_ptr(): a lazily conjugated view (torch's conj bit, which
+    `.contiguous()` keeps on an already contiguous tensor) must be materialised first."""
+    if t.is_conj():
+        t = t.resolve_conj()
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def _check_dev(*ts):
     for t in ts:
         if t is None:
             continue
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
             raise ValueError("expected contiguous CUDA tensors")
+        if t.is_conj() or t.is_neg():
+            raise ValueError("lazily conjugated / negated view passed to a kernel (use _dense)")
         if t.dtype not in (torch.float64, torch.complex128):
             raise ValueError(f"unsupported dtype {t.dtype}")
 
@@ -49,7 +59,6 @@ def gemm_tn(a, b, m, n, k, lda, ldb, out=None, ldc=None, accumulate=False):
         ldc = n
     check(lib.rn_dgemm_tn(stream_ptr(), m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldc,
                           1 if accumulate else 0, 1, 0, 0, 0), "rn_dgemm_tn")
-    LaunchCounter.add(1)
     return out
 
 
@@ -61,7 +70,6 @@ def ozaki_gemm_tn(a, b, m, n, k, lda, ldb, nslices=7, out=None, ldc=None):
         ldc = n
     check(lib.rn_ozaki_gemm_tn(stream_ptr(), m, n, k, _ptr(a), lda, _ptr(b), ldb, _ptr(out), ldc,
                                nslices), "rn_ozaki_gemm_tn")
-    LaunchCounter.add(3)
     return out
 
 
@@ -74,14 +82,13 @@ def pack(src, rows, cols, s_row, s_col, mode=0, conj=False):
     dst = torch.empty((out_rows, cols * es), dtype=torch.float64, device=src.device)
     check(lib.rn_pack(stream_ptr(), cplx, mode, 1 if conj else 0, rows, cols, _ptr(src),
                       s_row, s_col, _ptr(dst), cols * es), "rn_pack")
-    LaunchCounter.add(1)
     return dst
 
 
 def matmul(a, b):
     """a (M,K) @ b (K,N) for real / complex tensors through pack + the K-major GEMM
     (xp.tensordot with one contracted axis, matrix.py:210)."""
-    a, b = promote(a.contiguous(), b.contiguous())
+    a, b = promote(_dense(a), _dense(b))
     _check_dev(a, b)
     M, K = a.shape
     K2, N = b.shape
@@ -188,8 +195,8 @@ class HopPlan:
         if not ancilla and nsite + 2 != len(cshape):
             raise ValueError(f"cshape {cshape} does not match {nsite} centre sites")
         self.dtype = dtype
-        self.L = ltensor if ltensor.dtype == dtype else ltensor.to(dtype)
-        self.R = rtensor if rtensor.dtype == dtype else rtensor.to(dtype)
+        self.L = _dense(ltensor if ltensor.dtype == dtype else ltensor.to(dtype))
+        self.R = _dense(rtensor if rtensor.dtype == dtype else rtensor.to(dtype))
         _check_dev(self.L, self.R)
         La, Lb, Lc = self.L.shape
         Rl, Rf, Rk = self.R.shape
@@ -221,19 +228,19 @@ class HopPlan:
                                      c1[0], _ptr(c1[1]), _ptr(c1[2]), _ptr(c1[3]),
                                      c2[0], _ptr(c2[1]), _ptr(c2[2]), _ptr(c2[3]), path),
               "rn_hop_plan_create")
-        if dtype == torch.complex128:
-            LaunchCounter.add(1)
         self.handle = handle
         self.nlaunch = 2 + nsite + 1
 
     def apply(self, c, out=None):
         if c.dtype != self.dtype:
+            if c.is_complex():
+                raise ValueError("complex centre tensor on a real H_eff plan (the imaginary part would be dropped)")
             c = c.to(self.dtype)
-        c = c.contiguous()
+        c = _dense(c)
+        _check_dev(c)
         if out is None:
             out = torch.empty(self.out_shape, dtype=self.dtype, device=c.device)
         check(self.lib.rn_hop_apply(self.handle, stream_ptr(), _ptr(c), _ptr(out)), "rn_hop_apply")
-        LaunchCounter.add(self.nlaunch)
         return out
 
     def close(self):
@@ -253,7 +260,7 @@ def env_update(environ, bra, ket, site, domain, path=None):
     `bra` is the un-conjugated bra-side site tensor."""
     lib = _lib.get()
     environ, bra, ket = promote(environ, bra, ket)
-    environ, bra, ket = environ.contiguous(), bra.contiguous(), ket.contiguous()
+    environ, bra, ket = _dense(environ), _dense(bra), _dense(ket)
     _check_dev(environ, bra, ket)
     cplx = _is_cplx(ket)
     Ea, Eb, Ec = environ.shape
@@ -279,14 +286,13 @@ def env_update(environ, bra, ket, site, domain, path=None):
     check(lib.rn_env_update(stream_ptr(), cplx, dom, _ptr(environ), Ea, Eb, Ec, _ptr(bra), _ptr(ket),
                             d, g, Mf, Mh, F, _ptr(rowptr), _ptr(pq), _ptr(val), _ptr(out), path),
           "rn_env_update")
-    LaunchCounter.add(6 if cplx else (5 if dom == 0 else 3))
     return out
 
 
 def qr(a, lq=False):
     """Householder QR (or LQ) of a 2-D device tensor; returns (Q, R) or (L, Q)."""
     lib = _lib.get()
-    a = a.contiguous()
+    a = _dense(a)
     _check_dev(a)
     m, n = a.shape
     k = min(m, n)
@@ -295,12 +301,10 @@ def qr(a, lq=False):
         q = torch.empty((m, k), dtype=a.dtype, device=a.device)
         r = torch.empty((k, n), dtype=a.dtype, device=a.device)
         check(lib.rn_qr(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(q), k, _ptr(r), n), "rn_qr")
-        LaunchCounter.add(2 * k + 4)
         return q, r
     l = torch.empty((m, k), dtype=a.dtype, device=a.device)
     q = torch.empty((k, n), dtype=a.dtype, device=a.device)
     check(lib.rn_lq(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(l), k, _ptr(q), n), "rn_lq")
-    LaunchCounter.add(2 * k + 4)
     return l, q
 
 
@@ -318,7 +322,7 @@ def svd(a, max_sweeps=40, sort=True, precondition=None):
     those the bare iteration (rn_svd_jacobi, `precondition=False`) needs > 40 sweeps over the long
     columns of T while X needs 6-9 sweeps over columns of length k."""
     lib = _lib.get()
-    a = a.contiguous()
+    a = _dense(a)
     _check_dev(a)
     m, n = a.shape
     k = min(m, n)
@@ -335,7 +339,14 @@ def svd(a, max_sweeps=40, sort=True, precondition=None):
     else:
         check(lib.rn_svd_jacobi(stream_ptr(), cplx, m, n, _ptr(a), n, _ptr(u), k, _ptr(s), _ptr(vh), n,
                                 max_sweeps, ctypes.byref(sweeps)), "rn_svd_jacobi")
-    svd.last_sweeps = sweeps.value
+    svd.last_sweeps = abs(sweeps.value)
+    if sweeps.value < 0:
+        # the last sweep still rotated: the factors are not orthogonal to working precision
+        if not precondition:
+            return svd(a, max_sweeps=max_sweeps, sort=sort, precondition=True)
+        if max_sweeps < 120:
+            return svd(a, max_sweeps=120, sort=sort, precondition=True)
+        raise _lib.RnError(f"rn_svd: Jacobi iteration on a {m} x {n} block did not converge in {max_sweeps} sweeps")
     if sort:
         order = torch.argsort(s, descending=True)
         u, s, vh = u.index_select(1, order), s.index_select(0, order), vh.index_select(0, order)
@@ -360,7 +371,6 @@ def multi_dot(V, x, nvec, n, cplx, ws, out=None):
     ld = V.stride(0) * es if V.ndim == 2 else n * es
     check(lib.rn_multi_dot(stream_ptr(), 1 if cplx else 0, n, nvec, _ptr(V), ld, _ptr(x), _ptr(ws.ws),
                            _ptr(out)), "rn_multi_dot")
-    LaunchCounter.add(2)
     return out
 
 
@@ -371,7 +381,6 @@ def lincomb(V, coef, nvec, n, cplx, out):
     ld = V.stride(0) * es
     check(lib.rn_lincomb(stream_ptr(), 1 if cplx else 0, n, nvec, _ptr(V), ld, _ptr(coef), _ptr(out)),
           "rn_lincomb")
-    LaunchCounter.add(1)
     return out
 
 
@@ -380,21 +389,18 @@ def lanczos_update(w, vj, vjm1, alpha, beta_prev, ws, beta_out):
     nd = w.numel() * _es(w)
     check(lib.rn_lanczos_update(stream_ptr(), nd, _ptr(w), _ptr(vj), _ptr(vjm1), _ptr(alpha),
                                 _ptr(beta_prev), _ptr(ws.ws), _ptr(beta_out)), "rn_lanczos_update")
-    LaunchCounter.add(2)
 
 
 def scale_inv(x, s, out):
     lib = _lib.get()
     nd = x.numel() * _es(x)
     check(lib.rn_scale_inv(stream_ptr(), nd, _ptr(x), _ptr(s), _ptr(out)), "rn_scale_inv")
-    LaunchCounter.add(1)
 
 
 def lanczos_step(plan, n, V, j, alpha, beta, w, ws):
     """One fused Lanczos iteration on the Krylov stack V through rn_lanczos_step."""
     check(plan.lib.rn_lanczos_step(plan.handle, stream_ptr(), n, _ptr(V), j, _ptr(alpha), _ptr(beta),
                                    _ptr(w), _ptr(ws.ws)), "rn_lanczos_step")
-    LaunchCounter.add(plan.nlaunch + 5)
 
 
 _CUDA_ERROR_NOT_SUPPORTED = 801

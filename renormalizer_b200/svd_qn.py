@@ -87,7 +87,9 @@ def _orthonormal_null_vectors(u, s, vh):
     if k == 0:
         return u, vh
     sh = s.cpu().numpy()
-    tol = sh.max() * max(u.shape[0], vh.shape[1]) * np.finfo(float).eps
+    # numerical rank as numpy.linalg.matrix_rank, with a margin for the round-off of the two QR
+    # factorisations in front of the Jacobi iteration
+    tol = sh.max() * max(u.shape[0], vh.shape[1]) * np.finfo(float).eps * 8
     ngood = int(np.count_nonzero(sh > tol))          # s is sorted: the null vectors come last
     if ngood == k:
         return u, vh

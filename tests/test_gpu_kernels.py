@@ -535,3 +535,78 @@ def test_ozaki_gemm_cta_pair_subprocess():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "pair ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("shape", [((1, 16), (16, 1)), ((9, 16), (16, 7)), ((40, 40), (40, 40))])
+def test_ops_take_lazy_conj_views(shape):
+    """Regression (round 1, variational compression): torch's `.conj()` is a lazy view (conj bit) and
+    `.contiguous()` keeps it on an already contiguous tensor, so a kernel reading data_ptr() saw the
+    UN-conjugated data.  Every op must materialise such views."""
+    from renormalizer_b200 import ops
+    rng = np.random.default_rng(5)
+    a, b = rnd(rng, shape[0], True), rnd(rng, shape[1], True)
+    ta, tb = dev(a), dev(b)
+    assert relerr(host(ops.matmul(ta.conj(), tb)), a.conj() @ b) < TOL
+    assert relerr(host(ops.matmul(ta, tb.conj())), a @ b.conj()) < TOL
+    # conj().transpose().contiguous() of a single-row / single-column tensor is still a lazy view
+    at = ta.conj().transpose(0, 1).contiguous()
+    assert relerr(host(ops.matmul(at, dev(a))), a.conj().T @ a) < TOL
+    q, r = ops.qr(dev(a.T.copy()).conj())
+    assert relerr(host(q) @ host(r), a.T.conj()) < 1e-12
+    u, s, vh = ops.svd(ta.conj())
+    assert relerr((host(u) * host(s)) @ host(vh), a.conj()) < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("m,n,r", [(16, 2, 1), (24, 24, 9), (40, 64, 13), (200, 96, 30), (96, 300, 50), (130, 130, 0)])
+def test_block_svd_rank_deficient_orthonormal(cplx, m, n, r):
+    """Rank-deficient blocks (zero-padded bonds, bond dimension above the rank): the vectors one-sided
+    Jacobi returns for (numerically) zero singular values are replaced by an orthonormal completion;
+    U and V must be orthonormal and reproduce the block (svd_qn.py:13-66 semantics)."""
+    from renormalizer_b200.svd_qn import _block_svd
+    rng = np.random.default_rng(m * 7 + n)
+    a = rnd(rng, (m, r), cplx) @ rnd(rng, (r, n), cplx) if r else np.zeros((m, n), dtype=complex if cplx else float)
+    for full in (False, True):
+        np.random.seed(3)
+        u, s, vh = _block_svd(dev(a), full, True)
+        u, s, vh = host(u), host(s), host(vh)
+        k = min(m, n)
+        assert np.abs(u.conj().T @ u - np.eye(u.shape[1])).max() < 1e-12
+        assert np.abs(vh @ vh.conj().T - np.eye(vh.shape[0])).max() < 1e-12
+        assert np.abs((u[:, :k] * s) @ vh[:k] - a).max() < 1e-12 * max(1.0, np.abs(a).max())
+        if r:
+            assert np.abs(s[:r] - np.linalg.svd(a, compute_uv=False)[:r]).max() < 1e-12 * s[0]
+        assert np.all(s[r:] < 1e-12 * max(s[0], 1e-300)) or r == 0
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("domain", ["L", "R"])
+@pytest.mark.parametrize("pad", [0, 5])
+def test_env_update_bra_differs_from_ket_zero_padded(cplx, domain, pad):
+    """contract_one_site with ms_conj != conj(ms) (variational compression, mp.py:600-607): bra and
+    ket of different bond dimensions, embedded in zero-padded square tensors as
+    Mps.variational_compress does; rectangular operands without padding as well."""
+    from renormalizer_b200.lib import contract_one_site
+    rng = np.random.default_rng(17)
+    w, d = 3, 4
+    ea, ec, mf, mh = 6, 9, 7, 11                     # bra / ket bonds before and after the site
+    big_in, big_out = (max(ea, ec) + pad, max(mf, mh) + pad) if pad else (None, None)
+    env = rnd(rng, (ea, w, ec), cplx)
+    mo = rng.standard_normal((w, d, d, w)) * (rng.random((w, d, d, w)) < 0.6)
+    if domain == "L":
+        ket, bra = rnd(rng, (ec, d, mh), cplx), rnd(rng, (ea, d, mf), cplx)
+    else:
+        ket, bra = rnd(rng, (mh, d, ec), cplx), rnd(rng, (mf, d, ea), cplx)
+
+    def padded(t, shape):
+        out = np.zeros(shape, dtype=t.dtype)
+        out[tuple(slice(0, s) for s in t.shape)] = t
+        return out
+    if pad:
+        env = padded(env, (big_in, w, big_in))
+        shp = (big_in, d, big_out) if domain == "L" else (big_out, d, big_in)
+        ket, bra = padded(ket, shp), padded(bra, shp)
+    ref = oc.env_update(env, ket, mo, domain, ms_conj=bra.conj())
+    got = host(contract_one_site(dev(env), dev(ket), mo, domain, ms_conj=dev(bra).conj()))
+    assert got.shape == ref.shape
+    assert relerr(got, ref) < TOL
