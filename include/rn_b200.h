@@ -154,6 +154,20 @@ int rn_expm_krylov(rn_hop_plan* plan, void* stream, int cplx, long n, const void
                    double dt_re, double dt_im, void* out, int* nsteps_out);
 int rn_krylov_max_dim(void);
 
+/* ---- Davidson eigensolver (DMRG local solver) -----------------------------------------------
+ * Replaces renormalizer/lib/davidson/davidson.py:73 davidson(aop, x0, precond, ...) as called by
+ * renormalizer/mps/gs.py:538-576 for nroots == 1: lowest eigenpair of  inverse * sum_p H_eff[p]
+ * restricted to the entries with mask[k] != 0 (mask NULL: all), preconditioner 1/(hdiag - e + 1e-4)
+ * (gs.py:512-514).  plans: nplans H_eff plans over the same centre tensor (the members of a stacked
+ * MPO); x0: start vector (n elements, zero outside the mask); hdiag: n doubles.  c_out receives the
+ * Ritz vector (not sign-fixed), *e_out the eigenvalue, *nhop_out the number of H_eff applications,
+ * *converged_out 1 when |de| < tol and |r| < sqrt(tol) was reached within max_cycle.  The schedule
+ * (subspace max_space, restart, lindep) is the reference's. */
+int rn_davidson(rn_hop_plan** plans, int nplans, void* stream, int cplx, long n, const void* x0,
+                const unsigned char* mask, const double* hdiag, double inverse, double tol,
+                int max_cycle, int max_space, double lindep, void* c_out, double* e_out,
+                int* nhop_out, int* converged_out);
+
 /* ---- host-buffer entry points (what a NumPy-side caller binds) -------------------------------
  * Same contractions with HOST pointers: inputs are copied to the device, the kernels above run,
  * the result is copied back and the stream is synchronised.  W is the dense MPO site(s)
@@ -177,6 +191,10 @@ int rn_svd_host(int cplx, int m, int n, const void* A, void* U, double* S, void*
 long rn_launch_count(void);
 int rn_profile_begin(void);
 int rn_profile_end(double* total_ms, double* total_flops, long* launches);
+/* Dense int8 tensor-core rate of the device (the digit GEMM's roofline denominator): one CTA per SM
+ * issues `iters` resident-operand 128x128x128 tcgen05.mma kind::i8 products; *tops_out in 1e12 op/s,
+ * timed with CUDA events on `stream`. */
+int rn_int8_peak(void* stream, int iters, double* tops_out);
 
 #ifdef __cplusplus
 }

@@ -324,7 +324,8 @@ class StackedMpo:
         self.mpos = list(mpos)
 
 
-def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, stats=None, nroots=1):
+def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, stats=None, nroots=1,
+                      site_filter=None, site_done=None):
     """One DMRG sweep over all sites.  Reference: renormalizer/mps/gs.py:174-304 (omega=None,
     algo="davidson"; nroots > 1 is the state-averaged algorithm).  Returns (micro results
     [(e, cidx)], res_mps) with res_mps a list of Mps when nroots > 1."""
@@ -348,6 +349,12 @@ def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, s
         lts = [env_i.get_lr("L", lidx, mps, op_i, lmethod) for env_i, op_i in zip(environs, members)]
         rts = [env_i.get_lr("R", ridx, mps, op_i, rmethod) for env_i, op_i in zip(environs, members)]
         cmos = [[op_i[i] for i in cidx] for op_i in members]
+        if site_filter is not None and imps not in site_filter:
+            # measurement aid (bench.py): pass over this site with the QR alone
+            mps.push_cano(imps)
+            if site_done is not None:
+                site_done(imps, None)
+            continue
         qnbigl, qnbigr, qnmat = mps.big_qn(cidx)
         mask = get_qn_mask(qnmat, mps.qntot)
         cshape = mask.shape
@@ -423,6 +430,8 @@ def dmrg_single_sweep(mps, mpo, environ, method, m_max, percent, last_opt_idx, s
                 for r, ci in zip(res_mps, cstruct):
                     update_mps(r, ci, cidx, qnbigl, qnbigr, m_max, percent)
         averaged_ms = update_mps(mps, cstruct, cidx, qnbigl, qnbigr, m_max, percent)
+        if site_done is not None:
+            site_done(imps, e)
     mps.switch_direction()
     return micro, res_mps
 

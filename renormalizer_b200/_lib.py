@@ -51,6 +51,9 @@ SIGNATURES = {
     "rn_launch_count": (_l, []),
     "rn_profile_begin": (_i, []),
     "rn_profile_end": (_i, [POINTER(c_double), POINTER(c_double), POINTER(c_long)]),
+    "rn_davidson": (_i, [POINTER(_vp), _i, _vp, _i, _l, _vp, _vp, _vp, c_double, c_double, _i, _i, c_double,
+                        _vp, POINTER(c_double), POINTER(_i), POINTER(_i)]),
+    "rn_int8_peak": (_i, [_vp, _i, POINTER(c_double)]),
     "rn_env_update_host": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i,
                                 _vp, _i, _i, _vp, _i]),
 }

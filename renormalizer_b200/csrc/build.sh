@@ -4,7 +4,7 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../librn_b200.so"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-SRCS="api.cu gemm_f64.cu pack.cu wapply.cu vecops.cu krylov.cu qr.cu qr_panel.cu svd_jacobi.cu hop.cu"
+SRCS="api.cu gemm_f64.cu pack.cu wapply.cu vecops.cu krylov.cu qr.cu qr_panel.cu svd_jacobi.cu hop.cu davidson.cu"
 [ -f "$HERE/ozaki_gemm.cu" ] && SRCS="$SRCS ozaki_gemm.cu"
 cd "$HERE"
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \

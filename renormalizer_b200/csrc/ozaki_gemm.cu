@@ -433,6 +433,50 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------ int8 peak probe
+// Dense int8 tensor-pipe rate of this part, measured the way the digit GEMM uses it: one elected
+// thread per CTA issues back-to-back tcgen05.mma kind::i8 (128x128x32) on two resident shared-memory
+// tiles (no TMA traffic, no epilogue), four TMEM accumulators round-robin.  bench.py's roofline
+// denominator (profiles/r02_int8_peak.json) comes from this kernel instead of "2 x bf16".
+__global__ void __launch_bounds__(128, 1)
+int8_peak_kernel(int iters) {
+  extern __shared__ unsigned char pk_smem_raw[];
+  const uint32_t raw = smem_u32(pk_smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;
+  const uint32_t bar = tiles + 2 * OZ_TILE_BYTES, tmem_slot = bar + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(pk_smem_raw + (tmem_slot - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * OZ_TILE_BYTES / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(pk_smem_raw + (tiles - raw))[i] = 0x01010101u * (uint32_t)(i & 3);
+  if (warp == 1 && lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(OZ_ACC * OZ_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy tile writes -> async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  if (warp == 1 && lane == 0) {
+    const uint64_t adesc = make_smem_desc(tiles), bdesc = make_smem_desc(tiles + OZ_TILE_BYTES);
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem_base + (uint32_t)((it & 3) * OZ_BN);
+#pragma unroll
+      for (int k4 = 0; k4 < OZ_BK / 32; ++k4)
+        umma_i8(d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, it >= 4 || k4 > 0 ? 1u : 0u);
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(OZ_ACC * OZ_BN));
+  }
+}
+
 // --------------------------------------------------------------------------------------- split
 // Digit extraction shared by the split kernels: v (already divided by the row scale and
 // multiplied by 64) -> S signed digits, most significant first.  All steps are exact in FP64.
@@ -1005,6 +1049,31 @@ extern "C" int rn_ozaki_gemm_tn(void* stream, int m, int n, int k, const double*
   err = launch_ozaki_gemm(st, m, n, k, nslices, qA, sA, qB, sB, C, ldc);
   if (err) return err;
   cudaFreeAsync(qA, st); cudaFreeAsync(qB, st); cudaFreeAsync(sA, st); cudaFreeAsync(sB, st);
+  return 0;
+}
+
+// Dense int8 tcgen05 rate: `iters` MMAs of 128x128x128 (4 instructions of K = 32) per CTA on one CTA
+// per SM; *tops_out = 1e-12 * ops / s of this launch, timed with CUDA events on `stream`.
+extern "C" int rn_int8_peak(void* stream, int iters, double* tops_out) {
+  using namespace rn;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  RN_CHECK(cudaGetDevice(&dev));
+  RN_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = 2 * OZ_TILE_BYTES + 1024 + 64;
+  RN_CHECK(cudaFuncSetAttribute(int8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  RN_CHECK(cudaEventCreate(&e0));
+  RN_CHECK(cudaEventCreate(&e1));
+  RN_CHECK(cudaEventRecord(e0, st));
+  int8_peak_kernel<<<sms, 128, smem, st>>>(iters);
+  RN_CHECK(cudaEventRecord(e1, st));
+  RN_CHECK(cudaEventSynchronize(e1));
+  RN_LAUNCH_CHECK();
+  float ms = 0.f;
+  RN_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (tops_out) *tops_out = (double)sms * iters * 2.0 * OZ_BM * OZ_BN * OZ_BK / (ms * 1e-3) * 1e-12;
   return 0;
 }
 

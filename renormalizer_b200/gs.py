@@ -75,8 +75,11 @@ def optimize_mps(mps, mpo, omega: float = None):
     return macro_iteration_result, res_mps
 
 
-def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
-    """gs.py:174-304."""
+def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx, site_filter=None, site_hook=None):
+    """gs.py:174-304.  Measurement aids (not in the reference, used by bench.py only): `site_filter`, a
+    set of site indices -- the sweep optimises only those and moves the canonical centre over the
+    others with a QR and the environment update; `site_hook(stage, imps, info)` is called before
+    ("pre": cidx, ltensor, rtensor, mps) and after ("done": e, nhop) every optimised site update."""
     method = mps.optimize_config.method
     nroots = mps.optimize_config.nroots
     # in a state-averaged calculation: the rotated centre tensors of every state (better guesses)
@@ -109,6 +112,11 @@ def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
             ltensor = environ.GetLR("L", lidx, mps, mpo, itensor=None, method=lmethod)
             rtensor = environ.GetLR("R", ridx, mps, mpo, itensor=None, method=rmethod)
             cmo = [mpo[idx] for idx in cidx]
+        if site_filter is not None and imps not in site_filter:
+            mps._push_cano(imps)
+            continue
+        if site_hook is not None:
+            site_hook("pre", imps, dict(cidx=cidx, ltensor=ltensor, rtensor=rtensor, mps=mps, cmo=cmo))
         qnbigl, qnbigr, _ = mps._get_big_qn(cidx, need_mat=False)
         qn_mask = qn_mask_outer(qnbigl, qnbigr, mps.qntot)
         cshape = qn_mask.shape
@@ -145,6 +153,8 @@ def single_sweep(mps, mpo, environ, omega, percent, last_opt_e_idx):
                 for r, ci in zip(res_mps, cstruct):
                     r._update_mps(ci, cidx, qnbigl, qnbigr, percent)
         averaged_ms = mps._update_mps(cstruct, cidx, qnbigl, qnbigr, percent)
+        if site_hook is not None:
+            site_hook("done", imps, dict(e=e, nhop=nhop))
     mps._switch_direction()
     mps.hop_counts = hop_counts
     return micro_iteration_result, res_mps, mpo
@@ -252,6 +262,14 @@ def eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess):
         r = np.zeros(mask.numel())
         r[allowed] = np.random.rand(len(allowed)) - 0.5
         guesses.append(asxp(r).to(dtype))
+    if nroots == 1 and all(getattr(h, "plan", None) is not None and h.plan.dtype == dtype for h in hops):
+        # the whole iteration in one C call (rn_davidson): vectors, inner products and the
+        # preconditioner stay on the device, the host sees two scalar blocks per iteration
+        mask_u8 = mask.to(torch.uint8)
+        e, c, nhop, _ = ops.davidson_plans([h.plan for h in hops], guesses[0], mask_u8, hdiag.to(torch.float64),
+                                           inverse=inverse, max_cycle=100)
+        hop.close()
+        return e, _sign_fix(c).reshape(cshape), nhop
     e, c = davidson(aop, guesses, precond, max_cycle=100, nroots=nroots)
     hop.close()
     if nroots > 1:

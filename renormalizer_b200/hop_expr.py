@@ -58,7 +58,17 @@ def hop_expr(ltensor, rtensor, cmo, cshape, twolayer: bool = False):
 
 
 def hop_expr_dtype(ltensor, rtensor, cmo, cshape, dtype):
-    """hop_expr with an explicit compute dtype (complex centre tensor on real environments)."""
+    """hop_expr with an explicit compute dtype (complex centre tensor on real environments).
+    With parallel.enable_sharded_heff the application is split over the ranks of a process group
+    (rows of L) and its result all-gathered; see parallel.ShardedHop."""
+    from . import parallel
     ltensor, rtensor = asxp(ltensor), asxp(rtensor)
     sites = [ops.as_mpo_site(m) for m in cmo]
+    group = parallel.heff_group()
+    if (group is not None and ltensor.ndim == 3
+            and parallel.heff_flops(ltensor.shape, rtensor.shape, cshape) >= parallel._heff["min_work"]):
+        cshape = tuple(int(x) for x in cshape)
+        return parallel.ShardedHop(
+            ltensor, lambda l_slice: _HopCallable(ops.HopPlan(l_slice, rtensor, sites, cshape, dtype)),
+            cshape[1:-1] + (int(rtensor.shape[0]),), group=group)
     return _HopCallable(ops.HopPlan(ltensor, rtensor, sites, cshape, dtype))

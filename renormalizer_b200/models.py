@@ -9,6 +9,7 @@ Holstein chain (model.py:236-345, HolsteinModel scheme 1/2; renormalizer/tests/p
         + g w sum_i a_i^+ a_i (b_i^+ + b_i)
 """
 import numpy as np
+import scipy.linalg
 
 
 def _boson_ops(d):
@@ -164,40 +165,68 @@ def random_mps_qn(sigmaqn, qntot, m_max, rng):
     qn = [np.zeros((1, qn_size), dtype=int)]
     sites = []
     dim_prev = 1
+    # number of basis states of sites i+1 .. n-1 per quantum number: a bond sector cannot hold more
+    # states than its complement offers
+    right_count = [None] * n
+    acc = {tuple([0] * qn_size): 1}
+    for i in range(n - 1, 0, -1):
+        nxt = {}
+        for t in np.asarray(sigmaqn[i]).reshape(-1, qn_size):
+            for k, c in acc.items():
+                key = tuple(np.array(k) + t)
+                if np.all(np.array(key) <= qntot):
+                    nxt[key] = min(nxt.get(key, 0) + c, 1 << 40)
+        acc = nxt
+        right_count[i - 1] = acc
     for i in range(n - 1):
         sq = np.asarray(sigmaqn[i])
         big = (qn[i][:, None, :] + sq[None, :, :]).reshape(-1, qn_size)
         cols, col_qn = [], []
-        sectors = sorted(set(tuple(t) for t in big))
-        sectors = [s for s in sectors if not np.all(qntot < np.array(s))]
-        blocks = {}
-        for s in sectors:
-            idx = np.where(np.all(big == np.array(s), axis=1))[0]
-            a = rng.standard_normal((len(idx), len(idx)))
-            q, _ = np.linalg.qr(a)
-            blocks[s] = (idx, q)
+        sectors = sorted(set(map(tuple, np.unique(big, axis=0))))
+        sectors = [s for s in sectors if np.all(np.array(s) <= qntot)]
+        # also drop sectors from which qntot cannot be reached by the remaining sites
+        rest_max = np.sum([np.asarray(q).max(axis=0) for q in sigmaqn[i + 1:]], axis=0)
+        sectors = [s for s in sectors if np.all(np.array(s) + rest_max >= qntot)]
+        cap = {s: right_count[i].get(tuple(qntot - np.array(s)), 0) for s in sectors}
+        sectors = [s for s in sectors if cap[s] > 0]
+        members = {s: np.where(np.all(big == np.array(s), axis=1))[0] for s in sectors}
         # spread the retained states evenly over the sectors, then fill up
-        total = sum(len(v[0]) for v in blocks.values())
+        total = sum(len(v) for v in members.values())
         target = min(m_max, total)
-        quota = {s: min(len(blocks[s][0]), target // len(sectors)) for s in sectors}
+        room = {s: min(len(members[s]), cap[s]) for s in sectors}
+        target = min(target, sum(room.values()))
+        quota = {s: min(room[s], target // len(sectors)) for s in sectors}
         left = target - sum(quota.values())
         while left > 0:
             progressed = False
             for s in sectors:
-                if left > 0 and quota[s] < len(blocks[s][0]):
+                if left > 0 and quota[s] < room[s]:
                     quota[s] += 1
                     left -= 1
                     progressed = True
             if not progressed:
                 break
+        blocks = {}
+        for s in sectors:
+            idx = members[s]
+            if quota[s] == 0:
+                blocks[s] = (idx, np.zeros((len(idx), 0)))
+                continue
+            # orthonormal columns; a tall Gaussian block is well conditioned, so two rounds of
+            # Cholesky QR (BLAS-3, on the transposed block so that the products are row-major) are as
+            # good as Householder QR and several times faster
+            qt = rng.standard_normal((quota[s], len(idx)))
+            for _ in range(2):
+                qt = scipy.linalg.solve_triangular(np.linalg.cholesky(qt @ qt.T), qt, lower=True)
+            q = qt.T
+            blocks[s] = (idx, q)
+        mt = np.zeros((len(big), sum(quota.values())))
+        c0 = 0
         for s in sectors:
             idx, q = blocks[s]
-            for c in range(quota[s]):
-                v = np.zeros(len(big))
-                v[idx] = q[:, c]
-                cols.append(v)
-                col_qn.append(s)
-        mt = np.stack(cols, axis=1)
+            mt[idx, c0:c0 + q.shape[1]] = q
+            col_qn += [s] * q.shape[1]
+            c0 += q.shape[1]
         dim = mt.shape[1]
         sites.append(mt.reshape(dim_prev, sq.shape[0], dim))
         qn.append(np.array(col_qn))
@@ -280,21 +309,21 @@ def qc_sigmaqn(norbs):
     return [np.array([[0, 0], [1, 0]]) if i % 2 == 0 else np.array([[0, 0], [0, 1]]) for i in range(norbs)]
 
 
-def operator_sum_mpo(strings, coefs, mats, sym_qn, tol=1e-13):
-    """MPO site tensors W[b, up, down, f] of sum_t coefs[t] prod_l mats[strings[t, l]] (site l).
+def operator_sum_mpo(strings, coefs, site_mats, site_qn, tol=1e-13):
+    """MPO site tensors W[b, up, down, f] of sum_t coefs[t] prod_l site_mats[l][strings[t, l]].
 
-    sym_qn[s, :] is the change of the conserved quantum numbers produced by symbol s; every term
-    must conserve them.  Returns (sites, bond quantum numbers)."""
+    site_mats[l] is the local alphabet of site l (array nsym_l x d_l x d_l), site_qn[l][s, :] the
+    change of the conserved quantum numbers produced by symbol s; every term must conserve them.
+    Returns (sites, bond quantum numbers)."""
     strings = np.asarray(strings)
     nterm, n = strings.shape
-    nsym = len(mats)
-    sym_qn = np.asarray(sym_qn)
-    mats = np.stack(mats)
+    nq = np.asarray(site_qn[0]).shape[1]
     suf, A = strings, np.asarray(coefs, dtype=float)[None, :].copy()
-    state_qn = np.zeros((1, sym_qn.shape[1]), dtype=int)
+    state_qn = np.zeros((1, nq), dtype=int)
     sites, bond_qn = [], [state_qn]
     smax = 0.0
     for i in range(n):
+        mats, sym_qn = np.asarray(site_mats[i]), np.asarray(site_qn[i])
         ops = suf[:, 0].astype(int)
         ns = A.shape[0]
         if i == n - 1:
@@ -302,7 +331,7 @@ def operator_sum_mpo(strings, coefs, mats, sym_qn, tol=1e-13):
             for u, o in enumerate(ops):
                 w[:, :, :, 0] += A[:, u, None, None] * mats[o][None]
             sites.append(w)
-            bond_qn.append(np.zeros((1, sym_qn.shape[1]), dtype=int))
+            bond_qn.append(np.zeros((1, nq), dtype=int))
             break
         urest, inv = np.unique(suf[:, 1:], axis=0, return_inverse=True)
         inv = inv.reshape(-1)
@@ -311,28 +340,32 @@ def operator_sum_mpo(strings, coefs, mats, sym_qn, tol=1e-13):
         groups = {}
         for o in np.unique(ops):
             cols_o = np.nonzero(ops == o)[0]
-            sub = A[:, cols_o]
-            live = np.nonzero(np.abs(sub).max(axis=1) > 0)[0]
+            live = np.nonzero(np.abs(A[:, cols_o]).max(axis=1) > 0)[0]
             for s in live:
                 groups.setdefault(tuple(state_qn[s] + sym_qn[o]), []).append((s, o, cols_o))
         q_cols, q_rows, r_blocks, new_qn = [], [], [], []
         for g in sorted(groups):
             members = groups[g]
             cols = np.unique(np.concatenate([inv[c] for _, _, c in members]))
-            pos = {c: k for k, c in enumerate(cols)}
+            pos = np.full(len(urest), -1)
+            pos[cols] = np.arange(len(cols))
             sub = np.zeros((len(members), len(cols)))
             for r, (s, o, cols_o) in enumerate(members):
-                sub[r, [pos[c] for c in inv[cols_o]]] = A[s, cols_o]
+                sub[r, pos[inv[cols_o]]] = A[s, cols_o]
             # rank factorisation sub = Q R through the LQ factorisation of the (short, wide) block
-            qt, lt = np.linalg.qr(sub.T)                  # sub = lt.T @ qt.T
-            u, sv, vh = np.linalg.svd(lt.T, full_matrices=False)
+            if sub.shape[1] > sub.shape[0]:
+                qt, lt = np.linalg.qr(sub.T)              # sub = lt.T @ qt.T
+                u, sv, vh = np.linalg.svd(lt.T, full_matrices=False)
+                vh = vh @ qt.T
+            else:
+                u, sv, vh = np.linalg.svd(sub, full_matrices=False)
             smax = max(smax, sv[0] if len(sv) else 0.0)
             k = int(np.count_nonzero(sv > tol * smax))
             if k == 0:
                 continue
             q_rows.append(members)
             q_cols.append(u[:, :k])
-            r_blocks.append((cols, (sv[:k, None] * vh[:k]) @ qt.T))
+            r_blocks.append((cols, sv[:k, None] * vh[:k]))
             new_qn += [g] * k
         ktot = len(new_qn)
         w = np.zeros((ns, mats.shape[1], mats.shape[2], ktot))
@@ -356,24 +389,67 @@ def qc_mpo(h1e, h2e, tol=1e-13):
     quantum numbers; the nuclear repulsion is not included (as in the reference's model)."""
     n = h1e.shape[0]
     strings, coefs = qc_operator_strings(np.asarray(h1e), np.asarray(h2e))
-    # quantum-number change per symbol depends on the spin of the orbital: build per-site tables
-    # by giving sigma- (creation) +1 and sigma+ (annihilation) -1 in the orbital's spin component
-    sites, bond_qn = _qc_operator_sum(strings, coefs, n, tol)
-    return sites, bond_qn
+    mats = np.stack(_JW_MATS)
+    qn_a = np.zeros((len(_JW_MATS), 2), dtype=int)
+    qn_a[_JW_M], qn_a[_JW_P] = (1, 0), (-1, 0)         # sigma- creates, sigma+ annihilates
+    qn_b = qn_a[:, ::-1].copy()
+    return operator_sum_mpo(strings, coefs, [mats] * n, [qn_a if i % 2 == 0 else qn_b for i in range(n)], tol)
 
 
-def _qc_operator_sum(strings, coefs, n, tol):
-    # operator_sum_mpo takes one symbol table for all sites; spin alternates between sites, so the
-    # alphabet is doubled: symbols 0-5 on alpha (even) orbitals, 6-11 on beta (odd) orbitals
-    strings = strings.astype(np.int16).copy()
-    strings[:, 1::2] += len(_JW_MATS)
-    mats = _JW_MATS + _JW_MATS
-    qn = np.zeros((2 * len(_JW_MATS), 2), dtype=int)
-    qn[_JW_M] = (1, 0)
-    qn[_JW_P] = (-1, 0)
-    qn[len(_JW_MATS) + _JW_M] = (0, 1)
-    qn[len(_JW_MATS) + _JW_P] = (0, -1)
-    return operator_sum_mpo(strings, coefs, mats, qn, tol)
+def exciton_phonon_mpo(energies, jmat, omegas, couplings, nlevels, tol=1e-13):
+    """Frenkel-Holstein Hamiltonian with long-range excitonic couplings (example/fmo.py:45-52,
+    model.py:236-345, HolsteinModel scheme 3-like: any J_ij):
+        H = sum_i e_i a+_i a_i + sum_{i!=j} J_ij a+_i a_j
+            + sum_{i,k} w_k b+_ik b_ik + sum_{i,k} g_k w_k a+_i a_i (b+_ik + b_ik)
+    sites [e_1, ph_11 .. ph_1K, e_2, ...]; one conserved exciton number.  Returns (sites, bond qn)."""
+    nmol, nmode = len(energies), len(omegas)
+    adag = np.array([[0.0, 0.0], [1.0, 0.0]])
+    e_mats = np.stack([np.eye(2), adag, adag.T, adag @ adag.T])           # I, a+, a, n
+    e_qn = np.array([[0], [1], [-1], [0]])
+    idn, num, x = _boson_ops(nlevels)
+    p_mats = np.stack([idn, num, x])
+    p_qn = np.zeros((3, 1), dtype=int)
+    n = nmol * (1 + nmode)
+    pos_e = [i * (1 + nmode) for i in range(nmol)]
+    terms, coefs = [], []
+
+    def add(c, ops):
+        if c == 0:
+            return
+        row = np.zeros(n, dtype=np.int8)
+        for site, sym in ops:
+            row[site] = sym
+        terms.append(row)
+        coefs.append(c)
+    for i in range(nmol):
+        add(energies[i], [(pos_e[i], 3)])
+        for j in range(nmol):
+            if i != j:
+                add(jmat[i][j], [(pos_e[i], 1), (pos_e[j], 2)])
+        for k in range(nmode):
+            add(omegas[k], [(pos_e[i] + 1 + k, 1)])
+            add(couplings[k] * omegas[k], [(pos_e[i], 3), (pos_e[i] + 1 + k, 2)])
+    site_mats = [e_mats if l in pos_e else p_mats for l in range(n)]
+    site_qn = [e_qn if l in pos_e else p_qn for l in range(n)]
+    return operator_sum_mpo(np.stack(terms), np.array(coefs), site_mats, site_qn, tol)
+
+
+def exciton_phonon_sigmaqn(nmol, nmode, nlevels):
+    out = []
+    for _ in range(nmol):
+        out.append(np.array([[0], [1]]))
+        out += [np.zeros((nlevels, 1), dtype=int)] * nmode
+    return out
+
+
+def random_mpdm_qn(sigmaqn, qntot, m_max, rng):
+    """Random left-canonical density-operator MPS (sites (l, up, ancilla, r)) with the quantum
+    numbers of MpDm: the ancilla index carries none (mpdm.py: _get_sigmaqn = add_outer(sigmaqn, 0)).
+    Returns (sites, qn, sigmaqn of the (up, ancilla) pairs)."""
+    pair = [np.repeat(np.asarray(sq)[:, None, :], len(sq), axis=1) for sq in sigmaqn]
+    flat, qn = random_mps_qn([p.reshape(-1, p.shape[-1]) for p in pair], qntot, m_max, rng)
+    sites = [s.reshape(s.shape[0], len(sq), len(sq), s.shape[-1]) for s, sq in zip(flat, sigmaqn)]
+    return sites, qn, pair
 
 
 def random_qc_integrals(nspatial, rng, decay=0.35):
@@ -397,3 +473,36 @@ def random_qc_integrals(nspatial, rng, decay=0.35):
     seri = np.where((P % 2 == S % 2) & (Q % 2 == R % 2), eri[P // 2, S // 2, Q // 2, R // 2], 0.0)
     aseri = np.where((P < Q) & (R < S), seri - seri.transpose(0, 1, 3, 2), 0.0)
     return sh, aseri
+
+
+def seeded_mps_qn(sigmaqn, qntot, m_max, rng, occupation, noise=1e-3):
+    """A product state (physical index occupation[i] on site i) plus `noise` times a random state
+    of bond dimension m_max - 1 -- the direct sum of the two bond spaces, as the reference seeds
+    its ab initio runs (mps/tests/test_gs.py:131-134: `mps.scale(1e-8) + hf`).  The first sweep then
+    starts from a sensible guess instead of a random vector.  Not canonical; returns (sites, qn)."""
+    qntot = np.asarray(qntot)
+    n, nq = len(sigmaqn), len(qntot)
+    rs, rqn = random_mps_qn(sigmaqn, qntot, m_max - 1, rng)
+    acc = np.zeros(nq, dtype=int)
+    pqn = [acc.copy().reshape(1, nq)]
+    for i in range(n):
+        acc = acc + np.asarray(sigmaqn[i])[occupation[i]]
+        pqn.append(acc.copy().reshape(1, nq))
+    assert np.array_equal(acc, qntot), "occupation does not give qntot"
+    pqn[-1] = np.zeros((1, nq), dtype=int)
+    sites, qn = [], [np.zeros((1, nq), dtype=int)]
+    for i in range(n):
+        r = rs[i] * (noise if i == 0 else 1.0)
+        dl, d, dr = r.shape
+        first, last = i == 0, i == n - 1
+        t = np.zeros((1 if first else dl + 1, d, 1 if last else dr + 1))
+        t[(0 if first else dl), occupation[i], (0 if last else dr)] = 1.0
+        if first:
+            t[0, :, :dr] = r[0]
+        elif last:
+            t[:dl, :, 0] = r[:, :, 0]
+        else:
+            t[:dl, :, :dr] = r
+        sites.append(t)
+        qn.append(pqn[i + 1] if last else np.concatenate([rqn[i + 1], pqn[i + 1]]))
+    return sites, qn

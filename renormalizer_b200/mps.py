@@ -795,10 +795,17 @@ class Mps:
             config.guess_dt *= p
             cur = half2
 
-    def _evolve_tdvp_ps(self, mpo, evolve_dt):
+    def _evolve_tdvp_ps(self, mpo, evolve_dt, site_filter=None, site_probe=None, half_sweeps=2, site_hook=None):
         """One-site projector-splitting TDVP step (mps.py:1268-1404, Krylov local solver):
         forward half sweep and backward half sweep, each site evolved by dt/2 with H_eff and each
-        bond matrix evolved backwards with the zero-site H_eff."""
+        bond matrix evolved backwards with the zero-site H_eff.
+
+        Measurement aids (not in the reference, used by bench.py only): `site_filter`, a set of site
+        indices -- the other sites are passed over with the QR and the environment update alone;
+        `site_probe(imps, energy)` receives Re <C|H_eff|C> of every evolved centre tensor, a gauge
+        invariant the CPU oracle is compared with; `half_sweeps` stops after the first half;
+        `site_hook(stage, imps, info)` is called before ("pre": l_array, r_array, mps) and after
+        ("done") every evolved site."""
         # mps.py:1272-1279: imaginary time keeps the state's dtype.  A step with both a real and an
         # imaginary part makes exp(-i dt H_eff) complex, so a real state is promoted (the reference's
         # NumPy arithmetic promotes implicitly).
@@ -814,16 +821,25 @@ class Mps:
         environ = Environ(mps, mpo, "R" if mps.to_right else "L")
         local_steps = []
         n = len(mps)
-        for _ in range(2):
+        for _ in range(half_sweeps):
             for imps in mps.iter_idx_list(full=True):
                 system = "L" if mps.to_right else "R"
                 l_array = environ.read("L", imps - 1)
                 r_array = environ.read("R", imps + 1)
                 shape = list(mps[imps].shape)
-                hop = hop_expr_dtype(l_array, r_array, [mpo[imps]], shape, cdtype)
-                mps_t, j = expm_krylov(hop, -1j * evolve_dt / 2, mps[imps].reshape(-1))
-                hop.close()
-                local_steps.append(j)
+                evolve_site = site_filter is None or imps in site_filter
+                if evolve_site and site_hook is not None:
+                    site_hook("pre", imps, dict(l_array=l_array, r_array=r_array, mps=mps))
+                if evolve_site:
+                    hop = hop_expr_dtype(l_array, r_array, [mpo[imps]], shape, cdtype)
+                    mps_t, j = expm_krylov(hop, -1j * evolve_dt / 2, mps[imps].reshape(-1))
+                    if site_probe is not None:
+                        hc = hop(mps_t.reshape(shape)).reshape(-1)
+                        site_probe(imps, float(torch.vdot(mps_t.reshape(-1), hc).real))
+                    hop.close()
+                    local_steps.append(j)
+                else:
+                    mps_t = mps[imps]
                 mps_t = mps_t.reshape(shape)
                 qnbigl, qnbigr, _ = mps._get_big_qn([imps], need_mat=False)
                 u, qnlset, v, qnrset = svd_qn(mps_t, qnbigl, qnbigr, mps.qntot, QR=True,
@@ -836,10 +852,13 @@ class Mps:
                     r_array = environ.GetLR("R", imps, mps, mpo, itensor=r_array, method="System")
                     u = u.contiguous()
                     shape_u = list(u.shape)
-                    hop_u = hop_expr_dtype(l_array, r_array, [], shape_u, cdtype)
-                    back, j = expm_krylov(hop_u, 1j * evolve_dt / 2, u.reshape(-1))
-                    hop_u.close()
-                    local_steps.append(j)
+                    if evolve_site:
+                        hop_u = hop_expr_dtype(l_array, r_array, [], shape_u, cdtype)
+                        back, j = expm_krylov(hop_u, 1j * evolve_dt / 2, u.reshape(-1))
+                        hop_u.close()
+                        local_steps.append(j)
+                    else:
+                        back = u
                     mps[imps - 1] = ops.tensordot1(mps[imps - 1], back.reshape(shape_u))
                 elif mps.to_right and imps != n - 1:
                     mps[imps] = u.contiguous().reshape(shape[:-1] + [-1])
@@ -847,13 +866,18 @@ class Mps:
                     mps.qnidx = imps + 1
                     l_array = environ.GetLR("L", imps, mps, mpo, itensor=l_array, method="System")
                     shape_svt = list(vt.shape)
-                    hop_svt = hop_expr_dtype(l_array, r_array, [], shape_svt, cdtype)
-                    back, j = expm_krylov(hop_svt, 1j * evolve_dt / 2, vt.reshape(-1))
-                    hop_svt.close()
-                    local_steps.append(j)
+                    if evolve_site:
+                        hop_svt = hop_expr_dtype(l_array, r_array, [], shape_svt, cdtype)
+                        back, j = expm_krylov(hop_svt, 1j * evolve_dt / 2, vt.reshape(-1))
+                        hop_svt.close()
+                        local_steps.append(j)
+                    else:
+                        back = vt
                     mps[imps + 1] = ops.tensordot1(back.reshape(shape_svt), mps[imps + 1])
                 else:
                     mps[imps] = mps_t
+                if evolve_site and site_hook is not None:
+                    site_hook("done", imps, {})
             mps._switch_direction()
         mps.evolve_config.stat = local_steps
         return mps

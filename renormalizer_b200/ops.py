@@ -429,3 +429,23 @@ def allclose(a, b, rtol=1e-5, atol=1e-8, flag=None):
     check(lib.rn_allclose(stream_ptr(), _is_cplx(a), a.numel(), _ptr(a), _ptr(b), rtol, atol, _ptr(flag)),
           "rn_allclose")
     return int(flag.item()) == 0
+
+
+def davidson_plans(plans, x0, mask_u8, hdiag, inverse=1.0, tol=1e-12, max_cycle=100, max_space=12, lindep=1e-14):
+    """Lowest eigenpair of inverse * sum_p H_eff[p] in the masked subspace through rn_davidson (the
+    whole Davidson iteration in one C call).  Returns (e, c, H_eff applications, converged)."""
+    lib = _lib.get()
+    x0 = _dense(x0.reshape(-1))
+    hdiag = _dense(hdiag.reshape(-1))
+    _check_dev(x0, hdiag)
+    if hdiag.dtype != torch.float64:
+        raise ValueError("hdiag must be real")
+    n = x0.numel()
+    handles = (ctypes.c_void_p * len(plans))(*[p.handle for p in plans])
+    out = torch.empty_like(x0)
+    e, nhop, conv = ctypes.c_double(0), ctypes.c_int(0), ctypes.c_int(0)
+    check(lib.rn_davidson(handles, len(plans), stream_ptr(), _is_cplx(x0), n, _ptr(x0),
+                          _ptr(mask_u8) if mask_u8 is not None else None, _ptr(hdiag), float(inverse), tol,
+                          max_cycle, max_space, lindep, _ptr(out), ctypes.byref(e), ctypes.byref(nhop),
+                          ctypes.byref(conv)), "rn_davidson")
+    return e.value, out, nhop.value, bool(conv.value)

@@ -81,3 +81,56 @@ def test_run_sharded_two_ranks_gloo(tmp_path):
     a, b = np.load(out1), np.load(out2)
     assert a.shape == (5, 2) and b.shape == (5, 2)
     assert np.abs(a - b).max() < 1e-12
+
+
+@pytest.mark.parametrize("la", [8, 7])
+def test_sharded_heff_two_ranks_gloo(tmp_path, la):
+    """ShardedHop on two gloo ranks: each rank applies H_eff with its own rows of L (the oracle's
+    contraction stands in for the rank-local CUDA plan), the slices are all-gathered, and every rank
+    holds the single-rank result -- for an even split and for a ragged one (7 rows on 2 ranks)."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch
+        import torch.distributed as dist
+        from renormalizer_b200 import parallel
+        from oracle.contract import hop_apply
+        rank, world = parallel.init_process_group("gloo")
+        rng = np.random.default_rng(5)                       # same operands on every rank
+        la, w, m, d = {la}, 3, 6, 4
+        L = rng.standard_normal((la, w, m)) + 1j * rng.standard_normal((la, w, m))
+        R = rng.standard_normal((m, w, m)) + 1j * rng.standard_normal((m, w, m))
+        W = rng.standard_normal((w, d, d, w))
+        C = rng.standard_normal((m, d, m)) + 1j * rng.standard_normal((m, d, m))
+        parallel.enable_sharded_heff(True, min_work=0.0)
+        assert parallel.heff_group() is not None
+        make_local = lambda l_slice: (lambda c: torch.from_numpy(hop_apply(l_slice.numpy(), R, [W], c.numpy())))
+        hop = parallel.ShardedHop(torch.from_numpy(L), make_local, (d, m), group=parallel.heff_group())
+        lo, hi = hop.lo, hop.hi
+        assert (hi - lo) in (la // 2, la - la // 2, -(-la // 2))
+        out = hop(torch.from_numpy(C)).numpy()
+        ref = hop_apply(L, R, [W], C)
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() < 1e-13, np.abs(out - ref).max()
+        st = parallel.sharded_heff_stats()
+        assert st["applications"] == 1 and st["gathered_bytes"] >= ref.nbytes
+        # every rank holds the same bits
+        t = torch.from_numpy(np.ascontiguousarray(out)).view(torch.float64).clone()
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mn = t.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        assert torch.equal(mx, mn)
+        if rank == 0:
+            np.save(sys.argv[1], out)
+        dist.destroy_process_group()
+    """))
+    port = _free_port()
+    out = tmp_path / "out.npy"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(out)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    assert out.exists()
