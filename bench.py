@@ -42,7 +42,7 @@ UNIT = "sites/s"
 PARITY_TOL = 1e-10
 
 # name -> (default bond dimension, steps, warmup, CPU-sampled site updates) for the sub-results
-SUB_WORKLOADS = {"holstein_dmrg": (512, 2, 1, 3), "qc_dmrg": (1024, 1, 1, 2), "fmo_thermal": (512, 1, 1, 2)}
+SUB_WORKLOADS = {"holstein_dmrg": (512, 2, 1, 3), "qc_dmrg": (1024, 1, 1, 1), "fmo_thermal": (512, 1, 1, 1)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -68,8 +68,7 @@ def make_workload(name, bond, args, seed):
         nmol, d = args.mols, args.levels
         w = models.holstein_mpo(nmol, d, e0=0.0, j=-0.1, omega=0.2, g=1.0)
         sq = models.holstein_sigmaqn(nmol, d)
-        # exciton on the first molecule, phonon vacuum, plus 1e-3 x a random state of bond dimension M - 1
-        sites, qn = models.seeded_mps_qn(sq, [1], bond, rng, [1, 0] + [0, 0] * (nmol - 1))
+        sites, qn = models.random_mps_qn(sq, [1], bond, rng)
         n = len(sites)
         meta = dict(qn=qn, sigmaqn=sq, qntot=np.array([1]), qnidx=n - 1, to_right=False)
         return dict(key=name, kind="dmrg", mpo=w, sites=sites, meta=meta, nsite=n, sites_per_step=n - 1,
@@ -401,7 +400,7 @@ def gpu_capture(work, mpo, mps, chosen):
     return caps
 
 
-def cpu_replay(work, cap, hops_timed=2):
+def cpu_replay(work, cap):
     """One captured site update on the CPU oracle: (seconds, scalars, note).  The oracle statements are
     those of oracle/sweep.py (dmrg_single_sweep / evolve_tdvp_ps) for a single site."""
     from oracle import sweep as osw
@@ -465,13 +464,16 @@ def cpu_replay(work, cap, hops_timed=2):
         cstruct = osw._scatter(osw._sign_fix(c), mask)
         t_solve = time.perf_counter() - t0
     else:
-        for _ in range(hops_timed):
-            hc = hop_apply(lt, rt, cmo, guess)
-        t_solve = (time.perf_counter() - t0) / hops_timed * cap["nhop"]
+        # a whole Davidson run and the reference's full-matrices block SVD of a site this size take
+        # minutes on the host: one H_eff application is timed and multiplied by the CUDA path's
+        # application count at this site; the SVD update is left out of the oracle's time (which makes
+        # the reported CPU figure an upper bound of the reference's speed)
+        hc = hop_apply(lt, rt, cmo, guess)
+        t_solve = (time.perf_counter() - t0) * cap["nhop"]
         scalars = [float(np.vdot(guess, hc).real), float(np.linalg.norm(hc))]
-        cstruct = guess
-        note = (f"{hops_timed} H_eff applications timed and multiplied by the CUDA path's {cap['nhop']} "
-                f"applications at this site")
+        note = (f"1 H_eff application timed and multiplied by the CUDA path's {cap['nhop']} applications at this "
+                f"site, SVD update not timed")
+        return t_solve, scalars, note
     t1 = time.perf_counter()
     osw.update_mps(om, cstruct, cidx, qnbigl, qnbigr, work["bond"], 0.0)
     return t_solve + time.perf_counter() - t1, scalars, note
@@ -665,7 +667,7 @@ def measure(gpu, args, name, bond, steps, warmup, nsample, do_cpu, do_parity):
             t_cpu.append(tc)
             ratios.append(tc / cap["t_gpu"])
             if note:
-                notes.add(note.split(" at this site")[0].split(" and multiplied")[0])
+                notes.add(note)
             for x, y in zip(scal, cap["scalars"]):
                 worst = max(worst, abs(x - y) / max(1.0, abs(x)))
                 count += 1
@@ -682,7 +684,7 @@ def measure(gpu, args, name, bond, steps, warmup, nsample, do_cpu, do_parity):
         how = (f"{len(caps)} full-size site updates ({what}) of the state after the timed steps, sites {sites}, inputs "
                f"captured from the CUDA run, {sum(t_cpu):.1f} s of oracle time; {est}; NumPy/BLAS threads = {threads}")
         if notes:
-            how += "; eigensolver: " + "; ".join(sorted(notes)) + " and multiplied by the CUDA path's application count"
+            how += "; eigensolver: " + "; ".join(sorted(notes))
         out["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count(), "threads": threads,
                                "kind": "port", "sample": how}
         out["parity_check"].update({

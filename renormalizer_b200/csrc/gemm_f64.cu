@@ -145,14 +145,14 @@ int launch_gemm_tn_f64(cudaStream_t st, int m, int n, int k, const double* A, lo
                      (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0);
   dim3 grid((unsigned)ceil_div(n, G_BN), (unsigned)ceil_div(m, G_BM), (unsigned)batch);
   const bool prof = gemm_profile_on();
-  if (prof) gemm_profile_mark(st, 0, 0.0);
+  cudaEvent_t prof_begin = prof ? gemm_profile_begin(st) : nullptr;
   if (vec16)
     { RN_LAUNCH(gemm_tn_f64_kernel<true>, grid, G_THREADS, G_SMEM_BYTES, st, A, B, C, m, n, k, lda, ldb, ldc,
                                                                     sA, sB, sC, accumulate); rn::g_launches++; }
   else
     { RN_LAUNCH(gemm_tn_f64_kernel<false>, grid, G_THREADS, G_SMEM_BYTES, st, A, B, C, m, n, k, lda, ldb,
                                                                      ldc, sA, sB, sC, accumulate); rn::g_launches++; }
-  if (prof) gemm_profile_mark(st, 0, 2.0 * m * n * k * batch);
+  if (prof_begin) gemm_profile_end(st, 0, prof_begin, 2.0 * m * n * k * batch);
   RN_LAUNCH_CHECK();
   return 0;
 }

@@ -289,6 +289,12 @@ extern "C" int rn_env_update(void* stream, int cplx, int domain, const void* env
   const int es = cplx ? 2 : 1;
   int err;
   double *B1 = nullptr, *X1 = nullptr, *Y = nullptr, *A3 = nullptr, *B3 = nullptr;
+  // scratch is released on every exit path (a failed launch must not leak pool memory)
+  struct Scratch {
+    cudaStream_t st;
+    double **p[5];
+    ~Scratch() { for (double** q : p) if (*q) cudaFreeAsync(*q, st); }
+  } guard{st, {&B1, &X1, &Y, &A3, &B3}};
   const long dg = (long)d * g;
   if (domain == 0) {
     // G1: X1[(a,b),(e,l,h)] = env[(a,b),c] . ket[c,(e,l,h)]
@@ -364,11 +370,6 @@ extern "C" int rn_env_update(void* stream, int cplx, int domain, const void* env
                         (double*)out, (long)F * Mh * es);
     if (err) return err;
   }
-  if (B1) cudaFreeAsync(B1, st);
-  if (X1) cudaFreeAsync(X1, st);
-  if (Y) cudaFreeAsync(Y, st);
-  if (A3) cudaFreeAsync(A3, st);
-  if (B3) cudaFreeAsync(B3, st);
   return 0;
 }
 
@@ -386,11 +387,11 @@ extern "C" int rn_matmul(void* stream, int cplx, int M, int K, int N, const void
   int err;
   if (use_ozaki(path, (double)M, (double)N * es, (double)K * es)) {
     OzOperand oa, ob;
-    if ((err = oz_alloc(st, oa, M, K * es, g_ozaki_slices))) return err;
-    if ((err = oz_alloc(st, ob, N * es, K * es, g_ozaki_slices))) return err;
-    if ((err = launch_ozaki_split(st, (const double*)a, (long)K * es, M, K * es, oa.nslices, oa.q, oa.scale))) return err;
-    if ((err = launch_ozaki_split_t(st, cplx, b, N, N, K, ob.nslices, ob.q, ob.scale))) return err;
-    err = oz_gemm(st, oa, nullptr, 0, ob, nullptr, 0, (double*)out, (long)N * es);
+    err = oz_alloc(st, oa, M, K * es, g_ozaki_slices);
+    if (!err) err = oz_alloc(st, ob, N * es, K * es, g_ozaki_slices);
+    if (!err) err = launch_ozaki_split(st, (const double*)a, (long)K * es, M, K * es, oa.nslices, oa.q, oa.scale);
+    if (!err) err = launch_ozaki_split_t(st, cplx, b, N, N, K, ob.nslices, ob.q, ob.scale);
+    if (!err) err = oz_gemm(st, oa, nullptr, 0, ob, nullptr, 0, (double*)out, (long)N * es);
     oz_free(st, oa); oz_free(st, ob);
     return err;
   }

@@ -41,7 +41,8 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
                            double* C, long ldc, const double* dotv = nullptr, double* dot_partial = nullptr);
 int ozaki_gemm_tiles(int m, int n);
 bool gemm_profile_on();
-void gemm_profile_mark(cudaStream_t st, int kind, double flops_if_end);
+cudaEvent_t gemm_profile_begin(cudaStream_t st);
+void gemm_profile_end(cudaStream_t st, int kind, cudaEvent_t begin, double flops);
 int launch_ozaki_gemm(cudaStream_t st, int m, int n, int K, int nslices, const signed char* qA,
                       const double* sA, const signed char* qB, const double* sB, double* C, long ldc);
 

@@ -15,6 +15,15 @@
 
 namespace rn {
 
+// cudaFreeAsync of every registered pointer when the scope is left, on success and on error alike
+struct ScratchGuard {
+  cudaStream_t st;
+  std::vector<void**> ptrs;
+  explicit ScratchGuard(cudaStream_t s) : st(s) {}
+  void add(void** p) { ptrs.push_back(p); }
+  ~ScratchGuard() { for (void** p : ptrs) if (*p) cudaFreeAsync(*p, st); }
+};
+
 constexpr int J_THREADS = 256;
 
 template <bool CPLX>
@@ -392,6 +401,8 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
                        double* S, int max_sweeps, int* sweeps_out) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   int* flag = nullptr;
+  ScratchGuard guard(st);
+  guard.add((void**)&flag);
   RN_CHECK(cudaMallocAsync((void**)&flag, sizeof(int), st));
   int nbe = (int)ceil_div((long)nt * nt, 256);
   if (nbe > 1184) nbe = 1184;
@@ -420,6 +431,7 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
   const int ns_x = slices(mt, rps_x), ns_v = slices(nt, rps_v);
   T *Gp = nullptr, *Jg = nullptr;
   int* pair_rot = nullptr;
+  guard.add((void**)&Gp); guard.add((void**)&Jg); guard.add((void**)&pair_rot);
   if (blocked) {
     RN_CHECK(cudaMallocAsync((void**)&Gp, sizeof(T) * (size_t)(NB / 2) * ns_x * JK * JK, st));
     RN_CHECK(cudaMallocAsync((void**)&Jg, sizeof(T) * (size_t)(NB / 2) * JK * JK, st));
@@ -452,10 +464,6 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
   if (sweeps_out) *sweeps_out = converged ? sweeps : -sweeps;
   { RN_LAUNCH(jacobi_finalize_kernel<CPLX>, nt, J_THREADS, 0, st, At, mt, ldt, S); rn::g_launches++; }
   RN_LAUNCH_CHECK();
-  RN_CHECK(cudaFreeAsync(flag, st));
-  if (Gp) RN_CHECK(cudaFreeAsync(Gp, st));
-  if (Jg) RN_CHECK(cudaFreeAsync(Jg, st));
-  if (pair_rot) RN_CHECK(cudaFreeAsync(pair_rot, st));
   return 0;
 }
 
@@ -471,6 +479,8 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
   const int nt = wide ? m : n;
   const long ldt = mt, ldv = nt;
   T *At = nullptr, *Vw = nullptr;
+  ScratchGuard guard(st);
+  guard.add((void**)&At); guard.add((void**)&Vw);
   RN_CHECK(cudaMallocAsync((void**)&At, sizeof(T) * (size_t)nt * ldt, st));
   RN_CHECK(cudaMallocAsync((void**)&Vw, sizeof(T) * (size_t)nt * ldv, st));
   int err;
@@ -489,10 +499,7 @@ static int svd_driver(cudaStream_t st, int m, int n, const void* A, long lda, vo
     if (err) return err;
     err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, nt, n, At, ldt, 1, (double*)Vh, ldvh * es);
   }
-  if (err) return err;
-  RN_CHECK(cudaFreeAsync(At, st));
-  RN_CHECK(cudaFreeAsync(Vw, st));
-  return 0;
+  return err;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -577,6 +584,10 @@ static int svd_precond_driver(cudaStream_t st, int m, int n, const void* A, long
     *Vw = nullptr, *W = nullptr, *UT = nullptr;
   double* nrm = nullptr;
   int* perm = nullptr;
+  ScratchGuard guard(st);
+  for (void** q : {(void**)&Tt, (void**)&Ts, (void**)&Q1, (void**)&UT, (void**)&R1, (void**)&B, (void**)&Q2, (void**)&R2,
+                   (void**)&Vw, (void**)&W, (void**)&nrm, (void**)&perm})
+    guard.add(q);
   const size_t tall = sizeof(T) * (size_t)mt * k, sq = sizeof(T) * (size_t)k * k;
   RN_CHECK(cudaMallocAsync((void**)&Tt, tall, st));
   RN_CHECK(cudaMallocAsync((void**)&Ts, tall, st));
@@ -650,9 +661,6 @@ static int svd_precond_driver(cudaStream_t st, int m, int n, const void* A, long
     if ((err = launch_pack(st, CPLX, 0, CPLX ? 1 : 0, k, mt, UT, 1, k, (double*)Vh, ldvh * es))) return err;
   }
   RN_LAUNCH_CHECK();
-  for (void* ptr : {(void*)Tt, (void*)Ts, (void*)Q1, (void*)UT, (void*)R1, (void*)B, (void*)Q2, (void*)R2, (void*)Vw,
-                    (void*)W, (void*)nrm, (void*)perm})
-    RN_CHECK(cudaFreeAsync(ptr, st));
   return 0;
 }
 

@@ -347,8 +347,11 @@ class Mps:
             need_full = percent != 0 or (
                 self.compress_config.criteria is not CompressCriteria.threshold
                 and int(self.compress_config.max_dims[bond]) > economic_rank(qnbigl, qnbigr, self.qntot))
+            keep = None
+            if percent == 0 and self.compress_config.criteria is CompressCriteria.fixed:
+                keep = int(self.compress_config.max_dims[bond])
             Uset, SUset, qnlnew, Vset, SVset, qnrnew = svd_qn(cstruct, qnbigl, qnbigr, self.qntot, system=system,
-                                                              full_matrices=need_full)
+                                                              full_matrices=need_full, keep_hint=keep)
             if self.to_right:
                 m_trunc = self.compress_config.compute_m_trunc(SUset, cidx[0], self.to_right)
                 ms, msdim, msqn, compms = select_basis(Uset, SUset, qnlnew, Vset, m_trunc, percent=percent)

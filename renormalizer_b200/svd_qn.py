@@ -77,7 +77,16 @@ def _complete(q, extra):
     return torch.cat([q, qa], dim=1)
 
 
-def _orthonormal_null_vectors(u, s, vh):
+def _numerical_rank(sh, shape):
+    """Singular values above the cutoff of numpy.linalg.matrix_rank (with a margin for the round-off
+    of the two QR factorisations in front of the Jacobi iteration); sh sorted descending (host)."""
+    if len(sh) == 0:
+        return 0
+    tol = sh.max() * max(shape) * np.finfo(float).eps * 8
+    return int(np.count_nonzero(sh > tol))
+
+
+def _orthonormal_null_vectors(u, s, vh, sh=None):
     """One-sided Jacobi delivers the left vectors as (A V)_j / sigma_j: for a (numerically) zero
     singular value that column is zero or normalised round-off, not a unit vector orthogonal to the
     others as LAPACK's would be.  The sweeps do keep such vectors (bond dimension larger than the
@@ -86,11 +95,9 @@ def _orthonormal_null_vectors(u, s, vh):
     k = s.numel()
     if k == 0:
         return u, vh
-    sh = s.cpu().numpy()
-    # numerical rank as numpy.linalg.matrix_rank, with a margin for the round-off of the two QR
-    # factorisations in front of the Jacobi iteration
-    tol = sh.max() * max(u.shape[0], vh.shape[1]) * np.finfo(float).eps * 8
-    ngood = int(np.count_nonzero(sh > tol))          # s is sorted: the null vectors come last
+    if sh is None:
+        sh = s.cpu().numpy()
+    ngood = _numerical_rank(sh, (u.shape[0], vh.shape[1]))          # s is sorted: the null vectors come last
     if ngood == k:
         return u, vh
     u = _complete(u[:, :ngood].contiguous(), k - ngood)
@@ -98,16 +105,70 @@ def _orthonormal_null_vectors(u, s, vh):
     return u, vh
 
 
-def _block_svd(block, full_matrices, opt_full_matrices):
+# The quantum-number blocks of one bond are independent (svd_qn.py:140-200 loops over them).  One
+# block's Jacobi iteration is a chain of small launches that leaves most of the SMs idle and it
+# synchronises with the host once per sweep, so the economic SVDs of the larger blocks run
+# concurrently: one host thread and one CUDA stream per block (ctypes releases the GIL during the C
+# call).  Everything that draws random numbers (null-space completion) stays on the calling thread,
+# in block order, so results do not depend on the scheduling.
+SVD_CONCURRENT_MIN = 64          # blocks with min(m, n) below this are not worth a thread
+_svd_pool = {"executor": None, "streams": {}}
+
+
+def _economic_svds(blocks):
+    """ops.svd of every block; blocks with min(shape) >= SVD_CONCURRENT_MIN run concurrently."""
+    big = [i for i, b in enumerate(blocks) if min(b.shape) >= SVD_CONCURRENT_MIN]
+    if len(big) < 2:
+        return [ops.svd(b) for b in blocks]
+    from concurrent.futures import ThreadPoolExecutor
+    nworker = min(len(big), 4)
+    if _svd_pool["executor"] is None:
+        _svd_pool["executor"] = ThreadPoolExecutor(max_workers=4, thread_name_prefix="rn_svd")
+    dev = blocks[0].device
+    streams = _svd_pool["streams"].setdefault(dev.index, [torch.cuda.Stream(device=dev) for _ in range(4)])
+    main = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    results = [None] * len(blocks)
+
+    def work(slot, idxs):
+        torch.cuda.set_device(dev)
+        st = streams[slot]
+        with torch.cuda.stream(st):
+            st.wait_event(ready)
+            for i in idxs:
+                results[i] = ops.svd(blocks[i])
+        done = torch.cuda.Event()
+        done.record(st)
+        return done
+
+    # largest blocks first, dealt round-robin to the workers
+    order = sorted(big, key=lambda i: -blocks[i].shape[0] * blocks[i].shape[1] * min(blocks[i].shape))
+    futures = [_svd_pool["executor"].submit(work, w, order[w::nworker]) for w in range(nworker)]
+    for i, b in enumerate(blocks):
+        if i not in big:
+            results[i] = ops.svd(b)
+    for f in futures:
+        main.wait_event(f.result())
+    for i in big:
+        for t in results[i]:
+            t.record_stream(main)
+    return results
+
+
+def _block_svd(block, full_matrices, opt_full_matrices, economic=None, sh=None, fix_null=True):
     """optimized_svd (svd_qn.py:13-49): economic Jacobi SVD, completed to the sizes the reference
     returns under full_matrices (all of the null space, or min(m,n) extra vectors when very
-    unbalanced)."""
+    unbalanced).  `economic`: the block's (u, s, vh) when it has been computed already, `sh` its
+    singular values on the host; fix_null=False leaves the vectors of (numerically) zero singular
+    values as the Jacobi iteration returned them (the caller knows they cannot be selected)."""
     m, n = block.shape
     if not full_matrices:
         opt_full_matrices = False
     opt = opt_full_matrices and not (1 / 3 < m / n < 3)
-    u, s, vh = ops.svd(block)
-    u, vh = _orthonormal_null_vectors(u, s, vh)
+    u, s, vh = ops.svd(block) if economic is None else economic
+    if fix_null or full_matrices:
+        u, vh = _orthonormal_null_vectors(u, s, vh, sh)
     if full_matrices:
         k = min(m, n)
         if opt:
@@ -130,7 +191,7 @@ def _scatter_rows(indices, block, nrows, trivial):
 
 
 def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray, QR: bool = False,
-           system: str = None, full_matrices: bool = True, opt_full_matrices: bool = True):
+           system: str = None, full_matrices: bool = True, opt_full_matrices: bool = True, keep_hint: int = None):
     """Block decompose the coefficient tensor by SVD / QR according to the quantum numbers.
 
     Returns (U, S_u, qnl, V, S_v, qnr) -- or (U, qnl, V, qnr) with QR=True -- exactly like the
@@ -138,6 +199,11 @@ def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray
     (V = Vh.T, not conjugated), S_* are NumPy arrays.  With QR=True and system "R" the factor
     returned in U is lower instead of upper triangular (an LQ factorisation); the orthonormal
     factor and the product U @ V.T are the same gauge class as the reference's RQ.
+
+    keep_hint (not in the reference): the largest number of vectors the caller will retain, ranked by
+    singular value.  When the blocks hold at least that many vectors with non-zero singular values, the
+    vectors of the zero singular values can never be selected and their orthonormal completion
+    (random vectors, two projections and a QR per block) is skipped.
     """
     coef_array = asxp(coef_array)
     nl = int(np.prod(qnbigl.shape[:-1]))
@@ -165,6 +231,7 @@ def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray
         zero = (0,) * qn_size
         dim = min(nl, nr)
         return bu, [zero] * dim, bv, [zero] * dim
+    todo = []
     for ql in _distinct_qn(lqn):
         qr_ = qntot - ql
         rset = np.where(get_qn_mask(rqn, qr_))[0]
@@ -178,10 +245,17 @@ def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray
         else:
             li, ri = _idx(lset, dev), _idx(rset, dev)
             block = mat.index_select(0, li).index_select(1, ri).contiguous()
+        todo.append((ql, qr_, li, ri, trivial, block))
+    economic = _economic_svds([t[-1] for t in todo]) if not QR else [None] * len(todo)
+    s_host = [eco[1].cpu().numpy() for eco in economic] if not QR else [None] * len(todo)
+    fix_null = True
+    if not QR and keep_hint is not None and not full_matrices:
+        fix_null = sum(_numerical_rank(sh, t[-1].shape) for sh, t in zip(s_host, todo)) < keep_hint
+    for (ql, qr_, li, ri, trivial, block), eco, sh in zip(todo, economic, s_host):
         dim = min(block.shape)
         if not QR:
-            bu, bs, bvh = _block_svd(block, full_matrices, opt_full_matrices)
-            s_nz.append(bs.cpu().numpy())
+            bu, bs, bvh = _block_svd(block, full_matrices, opt_full_matrices, economic=eco, sh=sh, fix_null=fix_null)
+            s_nz.append(sh)
             bv = bvh.transpose(0, 1)
         else:
             if full_matrices:
