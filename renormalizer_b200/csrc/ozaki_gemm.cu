@@ -433,267 +433,6 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-// ------------------------------------------------------------------------ persistent variant
-// One CTA per SM walks a static list of work units (whole tiles first, then the K-split units of a
-// ragged last wave): barriers, the TMEM allocation and the tensor-map prefetch are paid once per CTA,
-// the TMA ring and the four TMEM accumulators keep rotating across units, so the loads of unit i+1 are
-// in flight while unit i's last products retire and the epilogue of unit i (TMEM -> FP64 registers ->
-// C through a 32-column shared-memory stage) overlaps the MMAs of unit i+1.  Same arithmetic, same
-// order of accumulation and the same outputs (C, split-K partials, fused dot partials) as
-// ozaki_gemm_kernel<false>; at M = 256 a tile has only four K blocks and the per-CTA prologue and the
-// un-overlapped last epilogue were a third of a tile's time.
-constexpr int OZP_STAGES = 6;
-constexpr int OZP_CSTAGE_COLS = 32;
-constexpr int OZP_CSTAGE_BYTES = OZP_CSTAGE_COLS * (OZ_BM + 1) * 8;
-constexpr int OZP_SMEM = OZP_STAGES * 2 * OZ_TILE_BYTES + OZP_CSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-struct OzUnit {
-  int row0, col0, kb0, kb1, ksplit, split, tile_id, ptile;
-};
-
-__device__ __forceinline__ OzUnit oz_decode_unit(int unit_idx, int n_full, int ksplit_tail, int kb_per_split,
-                                                 int kblocks, int tiles_m, int tiles_n) {
-  OzUnit u;
-  int tile;
-  if (unit_idx < n_full) { tile = unit_idx; u.split = 0; u.ksplit = 1; }
-  else {
-    const int t = unit_idx - n_full;
-    tile = n_full + t / ksplit_tail; u.split = t % ksplit_tail; u.ksplit = ksplit_tail;
-  }
-  u.tile_id = tile;
-  u.ptile = tile - n_full;
-  const int per_group = OZ_GROUP_M * tiles_n;
-  const int first_m = (tile / per_group) * OZ_GROUP_M;
-  const int gsize = (tiles_m - first_m) < OZ_GROUP_M ? (tiles_m - first_m) : OZ_GROUP_M;
-  const int in_group = tile % per_group;
-  u.row0 = (first_m + in_group % gsize) * OZ_BM;
-  u.col0 = (in_group / gsize) * OZ_BN;
-  u.kb0 = u.ksplit > 1 ? u.split * kb_per_split : 0;
-  u.kb1 = u.ksplit > 1 ? ((u.kb0 + kb_per_split) < kblocks ? (u.kb0 + kb_per_split) : kblocks) : kblocks;
-  return u;
-}
-
-__global__ void __launch_bounds__(OZ_THREADS, 1)
-ozaki_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const double* __restrict__ sA, const double* __restrict__ sB,
-                          double* __restrict__ C, int m, int n, long ldc, int rowsA, int rowsB, int kblocks,
-                          int nslices, int tiles_m, int tiles_n, int n_full, int ksplit_tail, int kb_per_split,
-                          int total_units, double* __restrict__ partial, int* __restrict__ counters,
-                          const double* __restrict__ dotv, double* __restrict__ dot_partial) {
-  pdl_trigger();
-  extern __shared__ unsigned char oz_smem_raw[];
-  const uint32_t raw = smem_u32(oz_smem_raw);
-  const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-B aligned operand ring
-  const uint32_t cstage = tiles + OZP_STAGES * 2 * OZ_TILE_BYTES;
-  const uint32_t bars = cstage + OZP_CSTAGE_BYTES;
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * OZP_STAGES;
-  const uint32_t tfull_bar = bars + 16 * OZP_STAGES, tempty_bar = tfull_bar + 8 * OZ_ACC;
-  const uint32_t tmem_slot = tempty_bar + 8 * OZ_ACC, last_slot = tmem_slot + 4;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(oz_smem_raw + (tmem_slot - raw));
-  volatile uint32_t* last_ptr = reinterpret_cast<volatile uint32_t*>(oz_smem_raw + (last_slot - raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < OZP_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int a = 0; a < OZ_ACC; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(OZ_ACC * OZ_BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int first_g = (nslices & 1) ? -1 : 0;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0;
-      for (int ui = blockIdx.x; ui < total_units; ui += gridDim.x) {
-        const OzUnit u = oz_decode_unit(ui, n_full, ksplit_tail, kb_per_split, kblocks, tiles_m, tiles_n);
-        for (int g = first_g; g < nslices; g += 2) {
-          const int hi = g + 1;
-          for (int kb = u.kb0; kb < u.kb1; ++kb)
-            for (int s = 0; s <= hi; ++s, ++it) {
-              const int st = it % OZP_STAGES;
-              const uint32_t ph = (uint32_t)(it / OZP_STAGES) & 1u;
-              mbar_wait(empty_bar + 8 * st, ph ^ 1u);
-              mbar_expect_tx(full_bar + 8 * st, 2 * OZ_TILE_BYTES);
-              tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES, &tmA, full_bar + 8 * st, kb * OZ_BK, s * rowsA + u.row0);
-              tma_load_2d(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES, &tmB, full_bar + 8 * st, kb * OZ_BK,
-                          (hi - s) * rowsB + u.col0);
-            }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      int it = 0;
-      uint32_t lv = 0;                               // running level index: accumulator slot = lv & 3
-      for (int ui = blockIdx.x; ui < total_units; ui += gridDim.x) {
-        const OzUnit u = oz_decode_unit(ui, n_full, ksplit_tail, kb_per_split, kblocks, tiles_m, tiles_n);
-        for (int g = first_g; g < nslices; g += 2) {
-          const int lo = g, hi = g + 1;
-          const uint32_t lv_lo = lv + (uint32_t)lo, lv_hi = lv + (uint32_t)hi;   // lv_lo unused when lo < 0
-          if (lo >= 0) mbar_wait(tempty_bar + 8 * (lv_lo & 3), ((lv_lo >> 2) & 1u) ^ 1u);
-          mbar_wait(tempty_bar + 8 * (lv_hi & 3), ((lv_hi >> 2) & 1u) ^ 1u);
-          tc_fence_after();
-          const uint32_t d_lo = tmem_base + (uint32_t)((lv_lo & 3) * OZ_BN), d_hi = tmem_base + (uint32_t)((lv_hi & 3) * OZ_BN);
-          uint32_t acc_lo = 0, acc_hi = 0;
-          for (int kb = u.kb0; kb < u.kb1; ++kb) {
-            int prev = -1;
-            for (int s = 0; s <= hi; ++s, ++it) {
-              const int st = it % OZP_STAGES;
-              const uint32_t ph = (uint32_t)(it / OZP_STAGES) & 1u;
-              mbar_wait(full_bar + 8 * st, ph);
-              tc_fence_after();
-              const uint64_t adesc = make_smem_desc(tiles + st * 2 * OZ_TILE_BYTES);
-              const uint64_t bdesc = make_smem_desc(tiles + st * 2 * OZ_TILE_BYTES + OZ_TILE_BYTES);
-#pragma unroll
-              for (int k4 = 0; k4 < OZ_BK / 32; ++k4) {
-                umma_i8(d_hi, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_hi);
-                acc_hi = 1;
-              }
-              if (s >= 1) {
-                const uint64_t pdesc = make_smem_desc(tiles + prev * 2 * OZ_TILE_BYTES);
-#pragma unroll
-                for (int k4 = 0; k4 < OZ_BK / 32; ++k4) {
-                  umma_i8(d_lo, pdesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), OZ_IDESC, acc_lo);
-                  acc_lo = 1;
-                }
-                umma_commit(empty_bar + 8 * prev);
-              }
-              prev = st;
-            }
-            umma_commit(empty_bar + 8 * prev);
-          }
-          if (lo >= 0) umma_commit(tfull_bar + 8 * (lv_lo & 3));
-          umma_commit(tfull_bar + 8 * (lv_hi & 3));
-        }
-        lv += (uint32_t)nslices;
-      }
-    }
-  } else {
-    // ===== epilogue: 8 warps, thread = (row, 64-column half) =====
-    const int ew = warp - 2;
-    const int lane_quarter = warp & 3;
-    const int half = ew >> 2;
-    const int r = lane_quarter * 32 + lane;
-    double* stage = reinterpret_cast<double*>(oz_smem_raw + (cstage - raw));       // [32 cols][129]
-    uint32_t lv = 0;
-    for (int ui = blockIdx.x; ui < total_units; ui += gridDim.x) {
-      const OzUnit u = oz_decode_unit(ui, n_full, ksplit_tail, kb_per_split, kblocks, tiles_m, tiles_n);
-      double sum[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) sum[i] = 0.0;
-      for (int g = 0; g < nslices; ++g, ++lv) {
-        const int acc = (int)(lv & 3);
-        mbar_wait(tfull_bar + 8 * acc, (lv >> 2) & 1u);
-        tc_fence_after();
-        const double wg = scalbn(1.0, -12 - 7 * g);
-        const uint32_t taddr = tmem_base + ((uint32_t)(lane_quarter * 32) << 16) + acc * OZ_BN + half * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const double x = __hiloint2double(0x43300000, (int)(v[i] ^ 0x80000000u)) - 4503601774854144.0;
-            sum[c * 32 + i] = fma(x, wg, sum[c * 32 + i]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-      }
-      bool store = true;
-      if (u.ksplit > 1) {
-        double2* mine = reinterpret_cast<double2*>(partial + ((long)u.ptile * u.ksplit + u.split) * (OZ_BM * OZ_BN)) +
-                        (half * 32) * OZ_BM + r;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mine[i * OZ_BM] = make_double2(sum[2 * i], sum[2 * i + 1]);
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (ew == 0 && lane == 0) {
-          const int old = atomicAdd(counters + u.ptile, 1);
-          const int last = old == u.ksplit - 1;
-          if (last) counters[u.ptile] = 0;            // self-resetting: ready for the next launch
-          *last_ptr = (uint32_t)last;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        store = *last_ptr != 0u;
-        if (store) {
-          __threadfence();
-          const double2* p0 = reinterpret_cast<const double2*>(partial + (long)u.ptile * u.ksplit * (OZ_BM * OZ_BN)) +
-                              (half * 32) * OZ_BM + r;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) sum[i] = 0.0;
-          for (int sp = 0; sp < u.ksplit; ++sp) {
-            const double2* ps = p0 + (long)sp * (OZ_BM * OZ_BN / 2);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const double2 v = __ldcg(ps + i * OZ_BM);
-              sum[2 * i] += v.x; sum[2 * i + 1] += v.y;
-            }
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");              // last_ptr may be rewritten by the next unit
-      }
-      if (store) {
-        // C tile through the 32-column stage: thread-per-row results are transposed so that every
-        // global store of a warp writes 256 contiguous bytes of one row
-        const int grow = u.row0 + r;
-        const double sa = grow < m ? sA[grow] : 0.0;
-        double dacc = 0.0;
-#pragma unroll
-        for (int ch = 0; ch < OZ_BN / OZP_CSTAGE_COLS; ++ch) {
-          if (half == (ch >> 1)) {
-#pragma unroll
-            for (int i = 0; i < OZP_CSTAGE_COLS; ++i) stage[i * (OZ_BM + 1) + r] = sum[(ch & 1) * 32 + i] * sa;
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const int col = u.col0 + ch * OZP_CSTAGE_COLS + lane;
-          const double sb = col < n ? sB[col] : 0.0;
-          for (int rr = ew; rr < OZ_BM; rr += 8) {
-            const int gr = u.row0 + rr;
-            if (gr >= m) break;
-            if (col < n) {
-              const double val = stage[lane * (OZ_BM + 1) + rr] * sb;
-              C[(long)gr * ldc + col] = val;
-              if (dotv) dacc = fma(val, dotv[(long)gr * ldc + col], dacc);
-            }
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");            // stage free for the next chunk / unit
-        }
-        if (dotv) {
-          dacc = warp_sum(dacc);
-          if (lane == 0) stage[ew] = dacc;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (ew == 0 && lane == 0) {
-            double t = 0.0;
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) t += stage[w8];
-            dot_partial[2 * u.tile_id] = t;
-            dot_partial[2 * u.tile_id + 1] = 0.0;
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(OZ_ACC * OZ_BN));
-  }
-}
-
 // ------------------------------------------------------------------------------ int8 peak probe
 // Dense int8 tensor-pipe rate of this part, measured the way the digit GEMM uses it: one elected
 // thread per CTA issues back-to-back tcgen05.mma kind::i8 (128x128x32) on two resident shared-memory
@@ -1179,11 +918,9 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
   if (!attr_set) {
     RN_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
     RN_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-    RN_CHECK(cudaFuncSetAttribute(ozaki_gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZP_SMEM));
     attr_set = true;
   }
-  static int persist_on = -1;               // RN_OZ_PERSIST=0: one CTA per tile (the round-1 kernel)
-  if (persist_on < 0) { const char* e = getenv("RN_OZ_PERSIST"); persist_on = (e && e[0] == '0') ? 0 : 1; }
+
   const bool pair = tmB64 != nullptr && oz_use_pair(m);
   const int Kp = (K + 15) & ~15;
   const int kblocks = (Kp + OZ_BK - 1) / OZ_BK;
@@ -1262,12 +999,7 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
   const unsigned units_launched = (unsigned)(n_full + split_units * ksplit);
   cudaEvent_t prof_begin = g_prof.on ? gemm_profile_begin(st) : nullptr;
   const int ks_arg = ksplit > 1 ? ksplit : 1;
-  if (!pair && persist_on) {
-    const unsigned grid = units_launched < (unsigned)g_oz_sms ? units_launched : (unsigned)g_oz_sms;
-    { RN_LAUNCH(ozaki_gemm_persist_kernel, grid, OZ_THREADS, OZP_SMEM, st,
-        *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, n_full, ks_arg, kb_per,
-        (int)units_launched, partial, counters, dotv, dot_partial); rn::g_launches++; }
-  } else if (!pair) {
+  if (!pair) {
     { RN_LAUNCH(ozaki_gemm_kernel<false>, units_launched, OZ_THREADS, OZ_SMEM, st,
         *tmA, *tmB, sA, sB, C, m, n, ldc, m, n, kblocks, nslices, tiles_m, tiles_n, n_full, ks_arg, kb_per,
         partial, counters, dotv, dot_partial); rn::g_launches++; }
