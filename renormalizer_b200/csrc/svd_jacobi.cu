@@ -12,6 +12,8 @@
 #include "internal.cuh"
 #include <algorithm>
 #include <vector>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace rn {
 
@@ -358,6 +360,176 @@ jb_apply_kernel(typename std::conditional<CPLX, double2, double>::type* __restri
   }
 }
 
+// ---- one block round as ONE cluster launch -------------------------------------------------------
+// The three kernels above exchange the partial Gram matrices and the rotation J through global
+// memory and pay two launch boundaries per round; a round is ~35 us of which ~4 us are arithmetic.
+// Here a cluster of S CTAs owns one block pair: CTA s keeps its row slice of the 32 columns of X and
+// of V resident in shared memory, forms its partial Gram matrix, every CTA sums the S partials
+// through DSMEM in a fixed order (so all CTAs hold the same G bit for bit), runs the same Jacobi
+// sweep on it redundantly, and applies J to its own resident slices.  Columns are read once and
+// written once per round, G and J never leave the SMs.
+constexpr int JF_MAXROWS_BYTES = 160 * 1024;     // resident X + V slices per CTA
+
+template <bool CPLX>
+__global__ void __launch_bounds__(JBT)
+jb_fused_round_kernel(typename std::conditional<CPLX, double2, double>::type* __restrict__ At,
+                      typename std::conditional<CPLX, double2, double>::type* __restrict__ Vw,
+                      int m, int n, int nv, long ldt, long ldv, int round, int NB, int nb, int rps_x, int rps_v,
+                      double tol, int full, int* __restrict__ rotated) {
+  pdl_wait();
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = (int)cluster.num_blocks();
+  const int slice = (int)cluster.block_rank();
+  const int pair = blockIdx.x / S;
+  extern __shared__ __align__(16) unsigned char jf_smem[];
+  T* Gp = reinterpret_cast<T*>(jf_smem);                 // my partial Gram matrix (read by the siblings)
+  T* G = Gp + JK * JK;
+  T* J = G + JK * JK;
+  T* tx = J + JK * JK;                                   // X slice: [JK][rps_x + 1]
+  const int ldx = rps_x + 1, ldvs = rps_v + 1;
+  T* tv = tx + (long)JK * ldx;                           // V slice: [JK][rps_v + 1]
+  __shared__ int col[JK];
+  __shared__ int rp[JB], rq[JB];
+  __shared__ double rc[JB];
+  __shared__ T rs[JB];
+  __shared__ int any_rot;
+  const int tid = threadIdx.x;
+  int P, Q;
+  jb_pair(pair, round, NB, P, Q);
+  const bool live = P < nb;                              // bye pair of an odd tournament: nothing to do
+  if (tid < JK) col[tid] = live ? jb_col(tid, P, Q, nb, n) : -1;
+  if (tid == 0) any_rot = 0;
+  __syncthreads();
+  const int xbeg = slice * rps_x, xend = min(m, xbeg + rps_x);
+  const int vbeg = slice * rps_v, vend = min(nv, vbeg + rps_v);
+  if (live) {
+    for (int e = tid; e < JK * rps_x; e += JBT) {
+      const int c = e / rps_x, r = e % rps_x, gr = xbeg + r;
+      const int cc = col[c];
+      tx[c * ldx + r] = (cc >= 0 && gr < xend) ? At[(long)cc * ldt + gr] : jb_zero<T>();
+    }
+    for (int e = tid; e < JK * rps_v; e += JBT) {
+      const int c = e / rps_v, r = e % rps_v, gr = vbeg + r;
+      const int cc = col[c];
+      tv[c * ldvs + r] = (cc >= 0 && gr < vend) ? Vw[(long)cc * ldv + gr] : jb_zero<T>();
+    }
+  }
+  __syncthreads();
+  {
+    // partial Gram matrix of my rows: thread -> row gi of G, 4 consecutive columns
+    const int gi = tid >> 3, gj = (tid & 7) * 4;
+    T acc[4] = {jb_zero<T>(), jb_zero<T>(), jb_zero<T>(), jb_zero<T>()};
+    if (live) {
+      const int rows = xend - xbeg;
+      for (int r = 0; r < rows; ++r) {
+        const T xi = tx[gi * ldx + r];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) jb_cfma(acc[jj], xi, tx[(gj + jj) * ldx + r]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) Gp[gi * JK + gj + jj] = acc[jj];
+  }
+  cluster.sync();
+  // G = sum of the partials in slice order (identical in every CTA) ; J = I
+  for (int e = tid; e < JK * JK; e += JBT) {
+    T g = jb_zero<T>();
+    for (int sl = 0; sl < S; ++sl) {
+      const T* remote = cluster.map_shared_rank(Gp, sl);
+      g = jb_add(g, remote[e]);
+    }
+    G[e] = g;
+    T one = jb_zero<T>();
+    if ((e / JK) == (e % JK)) { if constexpr (CPLX) one.x = 1.0; else one = 1.0; }
+    J[e] = one;
+  }
+  __syncthreads();
+  if (live) {
+    const int ti = tid >> 4, tj = tid & 15;
+    const int nrounds = full ? JK - 1 : JB;
+    for (int lr = 0; lr < nrounds; ++lr) {
+      if (tid < JB) {
+        int p, q;
+        if (!full) { p = tid; q = JB + ((tid + lr) & (JB - 1)); }
+        else if (tid == 0) { p = JK - 1; q = lr; }
+        else { p = (lr + tid) % (JK - 1); q = (lr - tid + (JK - 1)) % (JK - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double a = jb_real(G[p * JK + p]), b = jb_real(G[q * JK + q]);
+        const T g = G[p * JK + q];
+        const double g2 = jb_abs2(g);
+        double c = 1.0;
+        T sph = jb_zero<T>();
+        if (a > 0.0 && b > 0.0 && g2 > 0.0 && g2 > tol * tol * a * b) {
+          const double d = b - a;
+          const double w = 1.0 / (fabs(d) + sqrt(fma(d, d, 4.0 * g2)));
+          const double tg = (d >= 0.0 ? 2.0 : -2.0) * w;
+          const double t2 = tg * tg * g2;
+          c = rsqrt(1.0 + t2);
+          sph = jb_scale(c * tg, g);
+          any_rot = 1;
+        }
+        rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = sph;
+      }
+      __syncthreads();
+      {
+        const int p = rp[ti], q = rq[ti], u = rp[tj], v = rq[tj];
+        const double ci = rc[ti], cj = rc[tj];
+        const T si = rs[ti], sj = rs[tj];
+        const T gpu = G[p * JK + u], gpv = G[p * JK + v], gqu = G[q * JK + u], gqv = G[q * JK + v];
+        const T pu = jb_sub(jb_scale(cj, gpu), jb_cmul(sj, gpv)), pv = jb_add(jb_mul(sj, gpu), jb_scale(cj, gpv));
+        const T qu = jb_sub(jb_scale(cj, gqu), jb_cmul(sj, gqv)), qv = jb_add(jb_mul(sj, gqu), jb_scale(cj, gqv));
+        T npu = jb_sub(jb_scale(ci, pu), jb_mul(si, qu)), npv = jb_sub(jb_scale(ci, pv), jb_mul(si, qv));
+        T nqu = jb_add(jb_cmul(si, pu), jb_scale(ci, qu)), nqv = jb_add(jb_cmul(si, pv), jb_scale(ci, qv));
+        if (ti == tj) {
+          npv = jb_zero<T>(); nqu = jb_zero<T>();
+          if constexpr (CPLX) { npu.y = 0.0; nqv.y = 0.0; }
+        }
+        G[p * JK + u] = npu; G[p * JK + v] = npv; G[q * JK + u] = nqu; G[q * JK + v] = nqv;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int rr = ti + h * JB;
+          const T ju = J[rr * JK + u], jv = J[rr * JK + v];
+          J[rr * JK + u] = jb_sub(jb_scale(cj, ju), jb_cmul(sj, jv));
+          J[rr * JK + v] = jb_add(jb_mul(sj, ju), jb_scale(cj, jv));
+        }
+      }
+      __syncthreads();
+    }
+    if (any_rot) {
+      if (tid == 0 && slice == 0) *rotated = 1;
+      // my slices <- slices . J : thread -> row r (of X, then of V), NC columns at a time from registers
+      for (int which = 0; which < 2; ++which) {
+        T* tile = which == 0 ? tx : tv;
+        const int ld = which == 0 ? ldx : ldvs;
+        const int rows = which == 0 ? xend - xbeg : vend - vbeg;
+        T* M = which == 0 ? At : Vw;
+        const long ldg = which == 0 ? ldt : ldv;
+        const int rbeg = which == 0 ? xbeg : vbeg;
+        // item = (row r, group of 8 output columns): consecutive threads -> consecutive rows
+        for (int item = tid; item < rows * (JK / 8); item += JBT) {
+          const int r = item % rows, j0 = (item / rows) * 8;
+          T acc[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) acc[jj] = jb_zero<T>();
+#pragma unroll 4
+          for (int c = 0; c < JK; ++c) {
+            const T x = tile[c * ld + r];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) jb_fma(acc[jj], x, J[c * JK + j0 + jj]);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int cc = col[j0 + jj];
+            if (cc >= 0) M[(long)cc * ldg + rbeg + r] = acc[jj];
+          }
+        }
+      }
+    }
+  }
+  cluster.sync();          // no CTA may exit while a sibling can still read its partial Gram matrix
+}
+
 // S[c] = |At[c]|, At[c] /= S[c]
 template <bool CPLX>
 __global__ void __launch_bounds__(J_THREADS)
@@ -429,10 +601,26 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
   };
   int rps_x = 0, rps_v = 0;
   const int ns_x = slices(mt, rps_x), ns_v = slices(nt, rps_v);
+  // fused cluster round: S CTAs per block pair, X and V row slices resident in shared memory
+  static int fused_on = -1;                 // RN_SVD_FUSED=0 keeps the three-kernel round (diagnostics)
+  if (fused_on < 0) { const char* e = getenv("RN_SVD_FUSED"); fused_on = (e && e[0] == '0') ? 0 : 1; }
+  int fS = 8;
+  while (fS > 1 && ((mt + fS - 1) / fS < 16)) fS >>= 1;
+  const int frps_x = (int)ceil_div(mt, fS), frps_v = (int)ceil_div(nt, fS);
+  const size_t fsmem = sizeof(T) * ((size_t)3 * JK * JK + (size_t)JK * (frps_x + 1) + (size_t)JK * (frps_v + 1));
+  bool fused_ok = blocked && fused_on && fsmem <= (size_t)JF_MAXROWS_BYTES + sizeof(T) * 3 * JK * JK;
+  if (fused_ok) {
+    static size_t attr_bytes[2] = {0, 0};
+    if (fsmem > 48 * 1024 && fsmem > attr_bytes[CPLX ? 1 : 0]) {
+      RN_CHECK(cudaFuncSetAttribute(jb_fused_round_kernel<CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(JF_MAXROWS_BYTES + sizeof(T) * 3 * JK * JK)));
+      attr_bytes[CPLX ? 1 : 0] = JF_MAXROWS_BYTES + sizeof(T) * 3 * JK * JK;
+    }
+  }
   T *Gp = nullptr, *Jg = nullptr;
   int* pair_rot = nullptr;
   guard.add((void**)&Gp); guard.add((void**)&Jg); guard.add((void**)&pair_rot);
-  if (blocked) {
+  if (blocked && !fused_ok) {
     RN_CHECK(cudaMallocAsync((void**)&Gp, sizeof(T) * (size_t)(NB / 2) * ns_x * JK * JK, st));
     RN_CHECK(cudaMallocAsync((void**)&Jg, sizeof(T) * (size_t)(NB / 2) * JK * JK, st));
     RN_CHECK(cudaMallocAsync((void**)&pair_rot, sizeof(int) * (size_t)(NB / 2), st));
@@ -440,7 +628,22 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
   if (nt > 1) {
     for (; sweeps < max_sweeps; ++sweeps) {
       RN_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
-      if (blocked) {
+      if (blocked && fused_ok) {
+        for (int round = 0; round < NB - 1; ++round) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3((unsigned)((NB / 2) * fS)); cfg.blockDim = dim3(JBT);
+          cfg.dynamicSmemBytes = fsmem; cfg.stream = st;
+          cudaLaunchAttribute attr[2];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = (unsigned)fS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[1].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr; cfg.numAttrs = 2;
+          RN_CHECK(cudaLaunchKernelEx(&cfg, jb_fused_round_kernel<CPLX>, At, Vw, mt, nt, nt, ldt, ldv, round, NB, nb,
+                                      frps_x, frps_v, tol, round == 0 ? 1 : 0, flag));
+          rn::g_launches++;
+        }
+      } else if (blocked) {
         for (int round = 0; round < NB - 1; ++round) {
           RN_LAUNCH(jb_gram_kernel<CPLX>, dim3(NB / 2, ns_x), JBT, 0, st, At, mt, nt, ldt, round, NB, nb, rps_x, Gp);
           RN_LAUNCH(jb_rotate_kernel<CPLX>, NB / 2, JBT, 0, st, Gp, ns_x, round, NB, nb, tol, round == 0 ? 1 : 0, Jg,

@@ -120,6 +120,10 @@ def _economic_svds(blocks):
     big = [i for i, b in enumerate(blocks) if min(b.shape) >= SVD_CONCURRENT_MIN]
     if len(big) < 2:
         return [ops.svd(b) for b in blocks]
+    from . import parallel
+    group = parallel.heff_group()
+    if group is not None:
+        return _economic_svds_distributed(blocks, big, group)
     from concurrent.futures import ThreadPoolExecutor
     nworker = min(len(big), 4)
     if _svd_pool["executor"] is None:
@@ -153,6 +157,39 @@ def _economic_svds(blocks):
     for i in big:
         for t in results[i]:
             t.record_stream(main)
+    return results
+
+
+def _economic_svds_distributed(blocks, big, group):
+    """One sweep on several GPUs (parallel.enable_sharded_heff): the larger blocks are dealt to the ranks
+    of the group (largest first, to the least loaded rank), every rank factorises its own and the
+    factors are broadcast, so that all ranks continue with the same bits."""
+    import torch.distributed as dist
+    grp = None if group is True else group
+    rank, world = dist.get_rank(grp), dist.get_world_size(grp)
+    cost = {i: float(blocks[i].shape[0]) * blocks[i].shape[1] * min(blocks[i].shape) for i in big}
+    load, owner = [0.0] * world, {}
+    for i in sorted(big, key=lambda i: -cost[i]):
+        r = min(range(world), key=lambda q: load[q])
+        owner[i] = r
+        load[r] += cost[i]
+    results = [None] * len(blocks)
+    for i, b in enumerate(blocks):
+        if i not in owner or owner[i] == rank:
+            results[i] = ops.svd(b)
+    for i in big:                                           # fixed order on every rank
+        m, n = blocks[i].shape
+        k = min(m, n)
+        if owner[i] == rank:
+            u, sv, vh = (t.contiguous() for t in results[i])
+        else:
+            u = torch.empty((m, k), dtype=blocks[i].dtype, device=blocks[i].device)
+            sv = torch.empty((k,), dtype=torch.float64, device=blocks[i].device)
+            vh = torch.empty((k, n), dtype=blocks[i].dtype, device=blocks[i].device)
+        src = owner[i] if grp is None else dist.get_global_rank(grp, owner[i])
+        for t in (u, sv, vh):
+            dist.broadcast(torch.view_as_real(t) if t.is_complex() else t, src=src, group=grp)
+        results[i] = (u, sv, vh)
     return results
 
 

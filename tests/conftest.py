@@ -12,6 +12,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run with -m gpu on a B200)")
+    config.addinivalue_line("markers", "slow: full-size parity case (tens of seconds: one oracle site update at the benchmarked size)")
 
 
 @pytest.fixture(scope="session")

@@ -134,3 +134,45 @@ def test_sharded_heff_two_ranks_gloo(tmp_path, la):
     for p in procs:
         assert p.wait(timeout=300) == 0
     assert out.exists()
+
+
+def test_distributed_block_svds_two_ranks_gloo(tmp_path):
+    """One sweep on several GPUs: the quantum-number blocks of a bond are dealt to the ranks, each rank
+    factorises its own and the factors are broadcast (svd_qn._economic_svds_distributed).  Host logic
+    only: the kernels are replaced by the CPU test double of tests/_host_logic_stub.py."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+        import numpy as np, torch
+        import torch.distributed as dist
+        import _host_logic_stub                                  # ops.svd -> torch.linalg.svd on the CPU
+        from renormalizer_b200 import parallel, svd_qn
+        rank, world = parallel.init_process_group("gloo")
+        parallel.enable_sharded_heff(True, min_work=0.0)
+        rng = np.random.default_rng(3)
+        blocks = [torch.from_numpy(rng.standard_normal(s)) for s in [(90, 70), (8, 5), (64, 130), (100, 100)]]
+        blocks.append(torch.from_numpy(rng.standard_normal((70, 66)) + 1j * rng.standard_normal((70, 66))))
+        out = svd_qn._economic_svds(blocks)
+        assert len(out) == len(blocks)
+        for b, (u, s, vh) in zip(blocks, out):
+            assert torch.allclose((u * s.to(u.dtype)) @ vh, b, atol=1e-12)
+            for t in (u, s, vh):                                 # the same bits on every rank
+                r = torch.view_as_real(t) if t.is_complex() else t
+                mx = r.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                mn = r.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+                assert torch.equal(mx, mn)
+        if rank == 0:
+            open(sys.argv[1], "w").write("ok")
+        dist.destroy_process_group()
+    """))
+    port = _free_port()
+    out = tmp_path / "out.txt"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(out)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    assert out.read_text() == "ok"

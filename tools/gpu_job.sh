@@ -1,2 +1,9 @@
-for p in 1 0; do RN_OZ_PERSIST=$p ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 2 -c 2 -o gpurun_out/r2_gemm256_p$p -f python tools/hop_roofline.py 256 > gpurun_out/r2_ncu_p$p.log 2>&1; tail -1 gpurun_out/r2_ncu_p$p.log; done
-RN_OZ_PERSIST=1 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 2 -c 2 -o gpurun_out/r2_gemm1024_p1 -f python tools/hop_roofline.py 1024 real > gpurun_out/r2_ncu_p1b.log 2>&1; tail -1 gpurun_out/r2_ncu_p1b.log
+N=${1:-8}
+timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/r2_scale$N.json 2> gpurun_out/r2_scale$N.err; tail -c 600 gpurun_out/r2_scale$N.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r2_scale$N.json").read().strip().splitlines()[-1])
+print("value", d["value"], "n_gpus", d["n_gpus"], "e2e", d["e2e"])
+for s in d["strong_scaling"]:
+    print({k:v for k,v in s.items() if k not in ("sharding","collective")})
+PY
