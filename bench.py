@@ -756,7 +756,7 @@ def gemm_roofline(args, step_fn, work, raw=None):
 
 
 def strong_scaling(gpu, args, name, bond, steps, warmup):
-    """ONE chain on all N GPUs: the same DMRG sweeps run (a) on every rank alone and (b) with H_eff split
+    """ONE chain on all N GPUs: the same DMRG sweeps / TDVP steps run (a) on rank 0 alone and (b) with H_eff split
     over the bra-bond rows of L across the ranks and all-gathered over NVLink (parallel.ShardedHop);
     sites/s of both, max over ranks, and the sweep energies of both (they must agree)."""
     from renormalizer_b200 import parallel
@@ -764,7 +764,7 @@ def strong_scaling(gpu, args, name, bond, steps, warmup):
     from renormalizer_b200.mps import Mps
     from renormalizer_b200.gs import single_sweep
     from renormalizer_b200.lib import Environ
-    from renormalizer_b200.configs import CompressConfig, CompressCriteria
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig, EvolveMethod
     work = make_workload(name, bond, args, seed=1234)            # the SAME chain on every rank
     meta = work["meta"]
     mpo = Mpo(work["mpo"])
@@ -777,16 +777,23 @@ def strong_scaling(gpu, args, name, bond, steps, warmup):
         m = Mps(work["sites"], meta["qn"], meta["sigmaqn"], meta["qntot"], meta["qnidx"], meta["to_right"])
         m.optimize_config.method = "2site"
         m.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=bond)
-        m.ensure_right_canonical()
-        env = Environ(m, mpo, "R")
+        m.evolve_config = EvolveConfig(EvolveMethod.tdvp_ps)
+        st = {"m": m}
+        if work["kind"] == "dmrg":
+            m.ensure_right_canonical()
+            env = Environ(m, mpo, "R")
         energies = []
 
         def step():
             # the single-GPU reference runs on rank 0 alone (the other ranks wait at the barrier), so
             # that it is not slowed by N processes sharing the host
             if mode == "sharded" or gpu.rank == 0:
-                micro, _, _ = single_sweep(m, mpo, env, None, 0.0, None)
-                energies.append(float(min(e for e, _ in micro)))
+                if work["kind"] == "dmrg":
+                    micro, _, _ = single_sweep(m, mpo, env, None, 0.0, None)
+                    energies.append(float(min(e for e, _ in micro)))
+                else:
+                    st["m"] = st["m"].evolve(mpo, work["dt"])
+                    energies.append(float(np.real(st["m"].expectation(mpo))))
         for _ in range(warmup):
             step()
         ms = gpu.timed(step, steps)
@@ -805,7 +812,7 @@ def strong_scaling(gpu, args, name, bond, steps, warmup):
             "collective": "one NCCL all-gather of the H_eff result per application",
             "heff_applications_sharded": res["stats"]["applications"],
             "gathered_bytes_per_step": res["stats"]["gathered_bytes"] // nsweeps,
-            "sweep_energy_max_abs_diff_vs_1gpu": de, "sweep_energies": res["sharded"]["energies"]}
+            "energy_max_abs_diff_vs_1gpu": de, "energies": res["sharded"]["energies"]}
 
 
 def run_ours(args):
@@ -905,7 +912,7 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the M=512 / M=1024 sub-results")
     ap.add_argument("--only-sub", default="", help="comma-separated subset of the sub-results")
-    ap.add_argument("--strong", default="holstein_dmrg,qc_dmrg",
+    ap.add_argument("--strong", default="holstein_dmrg,fmo_thermal,qc_dmrg",
                     help="N > 1: workloads whose single chain is also run with H_eff split over all GPUs")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--shard-min-work", type=float, default=5.0e8,

@@ -445,7 +445,21 @@ jb_fused_round_kernel(typename std::conditional<CPLX, double2, double>::type* __
     J[e] = one;
   }
   __syncthreads();
+  // pairs this visit would rotate (all 496, or the 256 that join the two blocks): when none of them
+  // exceeds the threshold -- most block pairs of the last sweeps -- the rotation rounds are skipped
+  int need = 0;
   if (live) {
+    for (int e = tid; e < JK * JK; e += JBT) {
+      const int i = e / JK, j = e % JK;
+      if (i < j && (full || (i < JB && j >= JB))) {
+        const double a = jb_real(G[i * JK + i]), b = jb_real(G[j * JK + j]);
+        const double g2 = jb_abs2(G[e]);
+        if (a > 0.0 && b > 0.0 && g2 > 0.0 && g2 > tol * tol * a * b) need = 1;
+      }
+    }
+  }
+  need = __syncthreads_or(need);
+  if (live && need) {
     const int ti = tid >> 4, tj = tid & 15;
     const int nrounds = full ? JK - 1 : JB;
     for (int lr = 0; lr < nrounds; ++lr) {
@@ -608,7 +622,12 @@ static int jacobi_core(cudaStream_t st, int mt, int nt, typename std::conditiona
   while (fS > 1 && ((mt + fS - 1) / fS < 16)) fS >>= 1;
   const int frps_x = (int)ceil_div(mt, fS), frps_v = (int)ceil_div(nt, fS);
   const size_t fsmem = sizeof(T) * ((size_t)3 * JK * JK + (size_t)JK * (frps_x + 1) + (size_t)JK * (frps_v + 1));
-  bool fused_ok = blocked && fused_on && fsmem <= (size_t)JF_MAXROWS_BYTES + sizeof(T) * 3 * JK * JK;
+  // worth it only while every cluster of a round is resident at once (large blocks need most of an
+  // SM's shared memory per CTA and would run in several waves: 2048 x 2048 measured 403 vs 234 ms)
+  const long fused_ctas = (long)(NB / 2) * fS;
+  const long per_sm = (long)(227 * 1024) / (long)(fsmem + 1024);
+  bool fused_ok = blocked && fused_on && fsmem <= (size_t)JF_MAXROWS_BYTES + sizeof(T) * 3 * JK * JK &&
+                  per_sm >= 1 && fused_ctas <= 148 * per_sm;
   if (fused_ok) {
     static size_t attr_bytes[2] = {0, 0};
     if (fsmem > 48 * 1024 && fsmem > attr_bytes[CPLX ? 1 : 0]) {

@@ -17,7 +17,51 @@ def contract_one_site(environ, ms, mo, domain, ms_conj=None):
     if ms.ndim not in (3, 4):
         raise ValueError(f"MPS ndim is not 3 or 4, got {ms.ndim}")
     bra = ms if ms_conj is None else asxp(ms_conj).conj().resolve_conj()
-    return ops.env_update(environ, bra, ms, ops.as_mpo_site(mo), domain)
+    site = ops.as_mpo_site(mo)
+    from . import parallel
+    group = parallel.heff_group()
+    if group is not None:
+        out = _contract_one_site_sharded(environ, bra, ms, site, domain, group)
+        if out is not None:
+            return out
+    return ops.env_update(environ, bra, ms, site, domain)
+
+
+def _contract_one_site_sharded(environ, bra, ket, site, domain, group):
+    """One sweep on several GPUs (parallel.enable_sharded_heff): the environment update costs as much as
+    one H_eff application, so it is split the same way -- over the ket's NEW bond h of
+    "abc, adf, bdeg, ceh -> fgh" (lib.py:214-258), which every step of the contraction chain carries:
+    rank r absorbs ket[..., h_r] and the slices out[:, :, h_r] are all-gathered.  Returns None when the
+    update is too small to be worth a collective."""
+    import torch.distributed as dist
+    from . import parallel
+    grp = None if group is True else group
+    rank, world = dist.get_rank(grp), dist.get_world_size(grp)
+    mh = ket.shape[-1] if domain == "L" else ket.shape[0]
+    ea, eb, ec = environ.shape
+    inner = 1
+    for x in ket.shape[1:-1]:
+        inner *= int(x)
+    mf = bra.shape[-1] if domain == "L" else bra.shape[0]
+    flops = 2.0 * ea * eb * ec * inner * mh + 2.0 * ea * inner * mf * site.shape[0 if domain == "R" else 3] * mh
+    if flops < parallel._heff["min_work"] or mh % world != 0:
+        return None
+    w = mh // world
+    if domain == "L":
+        part = ket[..., rank * w:(rank + 1) * w].contiguous()
+    else:
+        part = ket[rank * w:(rank + 1) * w].contiguous()
+    local = ops.env_update(environ, bra, part, site, domain)            # (Mf, F, w)
+    # gathered along the first axis: (world * Mf, F, w), read below as (world, Mf, F, w)
+    buf = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    local = local.contiguous()
+    if local.is_complex():                      # collectives see the interleaved real view
+        dist.all_gather_into_tensor(torch.view_as_real(buf), torch.view_as_real(local), group=grp)
+    else:
+        dist.all_gather_into_tensor(buf, local, group=grp)
+    parallel._heff["gathered_bytes"] += buf.numel() * buf.element_size()
+    buf = buf.reshape((world,) + tuple(local.shape))
+    return buf.permute(1, 2, 0, 3).reshape(local.shape[0], local.shape[1], world * w).contiguous()
 
 
 class Environ:

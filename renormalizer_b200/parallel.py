@@ -158,7 +158,10 @@ class ShardedHop:
             send = torch.zeros((self.width,) + self.inner, dtype=ref.dtype, device=ref.device)
             if part is not None:
                 send[:self.hi - self.lo] = part
-        self.dist.all_gather_into_tensor(full, send, group=self.group)
+        if full.is_complex():                   # collectives see the interleaved real view
+            self.dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(send), group=self.group)
+        else:
+            self.dist.all_gather_into_tensor(full, send, group=self.group)
         _heff["applications"] += 1
         _heff["gathered_bytes"] += full.numel() * full.element_size()
         return full if self.even else full[:self.la].contiguous()

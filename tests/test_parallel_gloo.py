@@ -176,3 +176,50 @@ def test_distributed_block_svds_two_ranks_gloo(tmp_path):
     for p in procs:
         assert p.wait(timeout=300) == 0
     assert out.read_text() == "ok"
+
+
+@pytest.mark.parametrize("domain", ["L", "R"])
+def test_sharded_environment_update_two_ranks_gloo(tmp_path, domain):
+    """contract_one_site split over the ket's new bond across two gloo ranks (host logic with the CPU
+    test double for the kernel) equals the single-rank environment update."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+        import numpy as np, torch
+        import torch.distributed as dist
+        import _host_logic_stub
+        from renormalizer_b200 import parallel
+        from renormalizer_b200.lib import contract_one_site
+        from oracle.contract import env_update
+        rank, world = parallel.init_process_group("gloo")
+        rng = np.random.default_rng(9)
+        ea, w, ec, d, mf, mh = 5, 3, 6, 4, 7, 8
+        env = rng.standard_normal((ea, w, ec)) + 1j * rng.standard_normal((ea, w, ec))
+        mo = rng.standard_normal((w, d, d, w))
+        if {domain!r} == "L":
+            ket = rng.standard_normal((ec, d, mh)) + 1j * rng.standard_normal((ec, d, mh))
+            bra = rng.standard_normal((ea, d, mf)) + 1j * rng.standard_normal((ea, d, mf))
+        else:
+            ket = rng.standard_normal((mh, d, ec)) + 1j * rng.standard_normal((mh, d, ec))
+            bra = rng.standard_normal((mf, d, ea)) + 1j * rng.standard_normal((mf, d, ea))
+        ref = env_update(env, ket, mo, {domain!r}, ms_conj=bra.conj())
+        parallel.enable_sharded_heff(True, min_work=0.0)
+        got = contract_one_site(torch.from_numpy(env), torch.from_numpy(ket), mo, {domain!r},
+                                ms_conj=torch.from_numpy(bra).conj()).numpy()
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-12
+        assert parallel.sharded_heff_stats()["gathered_bytes"] >= ref.nbytes
+        if rank == 0:
+            open(sys.argv[1], "w").write("ok")
+        dist.destroy_process_group()
+    """))
+    port = _free_port()
+    out = tmp_path / "out.txt"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(out)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    assert out.read_text() == "ok"
