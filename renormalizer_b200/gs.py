@@ -257,8 +257,8 @@ def eigh_iterative(mps, qn_mask, ltensor, rtensor, cmo, raw_cguess):
     nroots = mps.optimize_config.nroots
     guesses = [g.reshape(-1).to(dtype) * maskf for g in raw_cguess]
     # missing guesses are random in the allowed subspace (gs.py:268-271, same np.random stream)
-    allowed = np.nonzero(qn_mask.reshape(-1))[0]
     for _ in range(len(guesses), nroots):
+        allowed = np.nonzero(qn_mask.reshape(-1))[0]
         r = np.zeros(mask.numel())
         r[allowed] = np.random.rand(len(allowed)) - 0.5
         guesses.append(asxp(r).to(dtype))

@@ -69,7 +69,12 @@ def _complete(q, extra):
     m, n = q.shape
     if extra <= 0:
         return q
-    a = torch.from_numpy(np.random.rand(m, extra)).to(q.device).to(q.dtype)
+    # uniform random vectors as in the reference; drawn on the device from a generator seeded by numpy's
+    # global stream, so that np.random.seed still fixes the result (and every rank of a multi-GPU sweep
+    # draws the same vectors) without generating and uploading m x extra numbers on the host
+    gen = torch.Generator(device=q.device)
+    gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))
+    a = torch.rand((m, extra), generator=gen, dtype=torch.float64, device=q.device).to(q.dtype)
     for _ in range(2):
         if n > 0:
             a = a - ops.matmul(q, ops.matmul(q.conj().transpose(0, 1).contiguous(), a))
