@@ -102,16 +102,13 @@ struct rn_hop_plan {
   long launches;
 };
 
-extern "C" int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int nsite,
+static int hop_plan_fill(rn_hop_plan* p, void* stream, int cplx, int nsite,
                                   const void* L, int La, int Lb, int Lc, const void* R, int Rl,
                                   int Rf, int Rk, int d1, int g1, int d2, int g2, int w1_F,
                                   const int* w1_rowptr, const int* w1_pq, const double* w1_val,
                                   int w2_F, const int* w2_rowptr, const int* w2_pq,
                                   const double* w2_val, int path) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (nsite < 0 || nsite > 2) return (int)cudaErrorInvalidValue;
-  rn_hop_plan* p = new (std::nothrow) rn_hop_plan();
-  if (!p) return (int)cudaErrorMemoryAllocation;
   p->cplx = cplx; p->es = cplx ? 2 : 1; p->nsite = nsite; p->path = path;
   p->La = La; p->Lb = Lb; p->Lc = Lc; p->Rl = Rl; p->Rf = Rf; p->Rk = Rk;
   p->d1 = nsite >= 1 ? d1 : 1; p->g1 = nsite >= 1 ? g1 : 1;
@@ -128,7 +125,7 @@ extern "C" int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int
     p->w2.rowptr = w2_rowptr; p->w2.pq = w2_pq; p->w2.val = w2_val;
   }
   const int wlast = nsite == 0 ? Lb : (nsite == 1 ? w1_F : w2_F);
-  if (wlast != Rf) { delete p; return (int)cudaErrorInvalidValue; }
+  if (wlast != Rf) return (int)cudaErrorInvalidValue;
   p->rest = (long)p->d1 * p->g1 * p->d2 * p->g2;
   const long n1 = p->rest * Rk;  // columns of T1 (elements)
   p->Cb = p->T1 = p->T2 = p->T3 = nullptr; p->Rb = nullptr; p->own_Rb = false;
@@ -170,6 +167,24 @@ extern "C" int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int
       err = launch_ozaki_split(st, (const double*)R, K3, Rl, (int)K3, g_ozaki_slices, p->ozR.q, p->ozR.scale);
     if (err) return err;
   }
+  return 0;
+}
+
+// A plan that fails half way (allocation, tensor-map encoding, a split launch) is destroyed before the
+// error is returned: nothing it allocated from the stream-ordered pool is leaked.
+extern "C" int rn_hop_plan_create(rn_hop_plan** out, void* stream, int cplx, int nsite,
+                                  const void* L, int La, int Lb, int Lc, const void* R, int Rl,
+                                  int Rf, int Rk, int d1, int g1, int d2, int g2, int w1_F,
+                                  const int* w1_rowptr, const int* w1_pq, const double* w1_val,
+                                  int w2_F, const int* w2_rowptr, const int* w2_pq,
+                                  const double* w2_val, int path) {
+  if (out == nullptr || nsite < 0 || nsite > 2) return (int)cudaErrorInvalidValue;
+  rn_hop_plan* p = new (std::nothrow) rn_hop_plan();
+  if (!p) return (int)cudaErrorMemoryAllocation;
+  p->Cb = p->T1 = p->T2 = p->T3 = nullptr; p->Rb = nullptr; p->own_Rb = false;
+  const int err = hop_plan_fill(p, stream, cplx, nsite, L, La, Lb, Lc, R, Rl, Rf, Rk, d1, g1, d2, g2, w1_F,
+                                w1_rowptr, w1_pq, w1_val, w2_F, w2_rowptr, w2_pq, w2_val, path);
+  if (err) { rn_hop_plan_destroy(p, stream); return err; }
   *out = p;
   return 0;
 }

@@ -392,6 +392,9 @@ def gen_qc():
     basis, ham_terms = h_qc.qc_model(h1e, h2e)
     model = Model(basis, ham_terms)
     mpo = Mpo(model)
+    # the spin-orbital integrals read_fcidump returns (h_qc.py:15-72): input of the numeric MPO builder
+    # renormalizer_b200.models.qc_mpo, whose MPO must equal the reference's symbolic one as an operator
+    out["h1e"], out["h2e"] = h1e, h2e
     nelec = [3, 3]
     M = 30
     procedure = [[M, 0.4], [M, 0.2], [M, 0.1], [M, 0], [M, 0], [M, 0], [M, 0]]
