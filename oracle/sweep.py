@@ -783,6 +783,72 @@ def evolve_prop_and_compress(mps, mpo, dt, spec, order=4, normalize=True):
     return new
 
 
+def _contract(mpo, mps, spec):
+    """Mpo.contract, mpo.py:415-419: apply + canonicalise + compress with the state's configuration."""
+    return compress(mpo_apply(mpo, mps).canonicalise(), spec)
+
+
+def evolve_pc_tdrk4(mps, mpo_t, dt, spec):
+    """Classical RK4 propagate-and-compress step, mps.py:664-698; mpo_t(t) -> Mpo."""
+    def stage(state, t):
+        return mps_scale(_contract(mpo_t(t), state, spec), -1j)
+
+    def shifted(k, f):
+        return compress(mps_add(mps, mps_scale(k, f)).canonicalise(), spec)
+    k1 = stage(mps, 0)
+    k2 = stage(shifted(k1, 0.5 * dt), 0.5 * dt)
+    k3 = stage(shifted(k2, 0.5 * dt), 0.5 * dt)
+    k4 = stage(shifted(k3, dt), dt)
+    return compressed_sum([mps, mps_scale(k1, dt / 6), mps_scale(k2, 2 * dt / 6), mps_scale(k3, 2 * dt / 6),
+                           mps_scale(k4, dt / 6)], spec)
+
+
+def evolve_pc_tdrk(mps, mpo_t, dt, spec, tableau, order, adaptive=False, guess_dt=None, rtol=5e-4):
+    """General explicit Runge-Kutta propagate-and-compress step with the embedded-pair step control,
+    mps.py:700-793.  tableau = (a, b, c) of utils/rk.py.  Returns (new state, guess_dt)."""
+    a, b, c = tableau
+    nstage = len(c)
+
+    def norm(m):
+        return abs(m.coeff) * m.mp_norm
+
+    def sub_step(y, tau, t0):
+        ks = []
+        for i in range(nstage):
+            k = compressed_sum([y] + [mps_scale(ks[j], a[i, j] * tau) for j in range(i) if a[i, j] != 0], spec,
+                               batchsize=6)
+            ks.append(mps_scale(_contract(mpo_t(c[i] * tau + t0), k, spec), -1j))
+        new = compressed_sum([y] + [mps_scale(ks[i], b[0, i] * tau) for i in range(nstage) if b[0, i] != 0], spec,
+                             batchsize=6)
+        if not adaptive:
+            return new, 0
+        err = None
+        for i in range(nstage):
+            if not np.allclose(b[0, i], b[1, i]):
+                term = mps_scale(ks[i], (b[0, i] - b[1, i]) * tau)
+                err = term if err is None else mps_add(err, term)
+        return new, norm(err) / norm(new)
+
+    if not adaptive:
+        return sub_step(mps, dt, 0)[0], guess_dt
+    p_restart, p_min, p_max = 0.5, 0.1, 2.0
+    evolved, new = 0, mps
+
+    def min_abs(x, y):
+        return x if abs(x) < abs(y) else y
+    while True:
+        tau = min_abs(guess_dt, dt - evolved)
+        new, error = sub_step(new, tau, evolved)       # mps.py:757-759: kept even when judged inaccurate
+        p = (rtol / (error + 1e-30)) ** (1 / order[0])
+        if p < p_restart:
+            guess_dt = tau * max(p_min, p)
+        elif np.allclose(tau + evolved, dt):
+            return new, min_abs(tau * p, guess_dt)
+        else:
+            guess_dt *= min(p, p_max)
+            evolved += tau
+
+
 def normalize(mps, kind):
     """mps.py:619-642 / 2025-2058, in place."""
     nrm = mps.mp_norm

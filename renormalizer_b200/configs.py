@@ -17,6 +17,8 @@ class EvolveMethod(Enum):
     tdvp_ps = "TDVP_PS"
     tdvp_ps2 = "TDVP_PS2"
     prop_and_compress = "P&C"
+    prop_and_compress_tdrk4 = "P&C TD RK4"        # configs.py:309-311: Runge-Kutta propagators, the
+    prop_and_compress_tdrk = "P&C TD RK"          # Hamiltonian may depend on time
     tdvp_mu_vmf = "TDVP_MU_VMF"
     tdvp_vmf = "TDVP_VMF"
     tdvp_mu_cmf = "TDVP_MU_CMF"
@@ -117,11 +119,13 @@ class OptimizeConfig:
 
 class EvolveConfig:
     def __init__(self, method=EvolveMethod.prop_and_compress, adaptive=False, guess_dt=1e-1,
-                 adaptive_rtol=5e-4, taylor_order=None, ivp_solver="krylov"):
+                 adaptive_rtol=5e-4, taylor_order=None, ivp_solver="krylov", rk_solver="C_RK4"):
         if isinstance(method, str):
             method = EvolveMethod[method]
         self.method = method
         self.adaptive = adaptive
+        from .rk import RungeKutta
+        self.rk_config = RungeKutta(rk_solver)      # configs.py:363
         if taylor_order is None:                    # configs.py:364-368
             taylor_order = 5 if adaptive else 4
         self.taylor_order = taylor_order
@@ -132,7 +136,8 @@ class EvolveConfig:
 
     @property
     def is_tdvp(self):
-        return self.method is not EvolveMethod.prop_and_compress
+        return self.method not in (EvolveMethod.prop_and_compress, EvolveMethod.prop_and_compress_tdrk4,
+                                   EvolveMethod.prop_and_compress_tdrk)
 
     def check_valid_dt(self, evolve_dt):
         """configs.py:394-402."""

@@ -746,8 +746,11 @@ class Mps:
         integrators TDVP-PS / TDVP-PS2; the variational mean-field TDVP variants are not sweeps over
         H_eff and stay outside the accelerated path."""
         method = self.evolve_config.method
-        if method is EvolveMethod.prop_and_compress:
-            new_mps = self._evolve_prop_and_compress(mpo, evolve_dt)
+        if method in (EvolveMethod.prop_and_compress, EvolveMethod.prop_and_compress_tdrk4,
+                      EvolveMethod.prop_and_compress_tdrk):
+            new_mps = {EvolveMethod.prop_and_compress: self._evolve_prop_and_compress,
+                       EvolveMethod.prop_and_compress_tdrk4: self._evolve_prop_and_compress_tdrk4,
+                       EvolveMethod.prop_and_compress_tdrk: self._evolve_prop_and_compress_tdrk}[method](mpo, evolve_dt)
             if normalize:
                 new_mps.normalize("mps_and_coeff" if np.iscomplex(evolve_dt) else "mps_only")
             return new_mps
@@ -771,6 +774,85 @@ class Mps:
             else:
                 new_mps.normalize("mps_only")
         return new_mps
+
+    @staticmethod
+    def _mpo_of_time(mpo):
+        """mps.py:669-676: a fixed MPO, or a callable t -> MPO over 0 .. evolve_dt."""
+        if callable(mpo) and not hasattr(mpo, "contract"):
+            return mpo
+        if not hasattr(mpo, "contract"):
+            raise TypeError(f"unsupported mpo type: {mpo}")
+        return lambda t, *args, **kwargs: mpo
+
+    def _evolve_prop_and_compress_tdrk4(self, mpo, evolve_dt):
+        """Classical 4th-order Runge-Kutta step for a (possibly time-dependent) Hamiltonian,
+        mps.py:664-698: every stage is Mpo.contract (apply + canonicalise + compress), the stage
+        states and the final sum are canonicalised and compressed with the state's own configuration."""
+        from .lib import compressed_sum
+        mpo_t = self._mpo_of_time(mpo)
+        k1 = mpo_t(0).contract(self).scale(-1j)
+        tmp = self + k1.scale(0.5 * evolve_dt)
+        tmp.canonicalise().compress()
+        k2 = mpo_t(0.5 * evolve_dt).contract(tmp).scale(-1j)
+        tmp = self + k2.scale(0.5 * evolve_dt)
+        tmp.canonicalise().compress()
+        k3 = mpo_t(0.5 * evolve_dt).contract(tmp).scale(-1j)
+        tmp = self + k3.scale(evolve_dt)
+        tmp.canonicalise().compress()
+        k4 = mpo_t(evolve_dt).contract(tmp).scale(-1j)
+        return compressed_sum([self, k1.scale(1 / 6 * evolve_dt), k2.scale(2 / 6 * evolve_dt),
+                               k3.scale(2 / 6 * evolve_dt), k4.scale(1 / 6 * evolve_dt)])
+
+    def _evolve_prop_and_compress_tdrk(self, mpo, evolve_dt):
+        """General explicit Runge-Kutta step from the tableau of evolve_config.rk_config, with the
+        embedded-pair step-size control when evolve_config.adaptive, mps.py:700-793."""
+        from functools import reduce
+        from .lib import compressed_sum
+        mpo_t = self._mpo_of_time(mpo)
+        rk = self.evolve_config.rk_config
+        a, b, c = rk.tableau
+
+        def sub_step(y, tau, t0):
+            ks = []
+            for istage in range(rk.stage):
+                k = compressed_sum([y] + [ks[i].scale(a[istage, i] * tau) for i in range(istage) if a[istage, i] != 0],
+                                   batchsize=6)
+                k = mpo_t(c[istage] * tau + t0, mps=k).contract(k).scale(-1j)
+                ks.append(k)
+            new = compressed_sum([y] + [ks[i].scale(b[0, i] * tau) for i in range(rk.stage) if b[0, i] != 0],
+                                 batchsize=6)
+            if not self.evolve_config.adaptive:
+                assert len(rk.order) == 1
+                return new, 0
+            assert len(rk.order) == 2 and rk.order[0] - rk.order[1] == 1
+            err = reduce(lambda m1, m2: m1.add(m2),
+                         [ks[i].scale((b[0, i] - b[1, i]) * tau) for i in range(rk.stage)
+                          if not np.allclose(b[0, i], b[1, i])])
+            return new, err.norm / new.norm
+
+        self.evolve_config.check_valid_dt(evolve_dt)
+        if not self.evolve_config.adaptive:
+            return sub_step(self, evolve_dt, 0)[0]
+        p_restart, p_min, p_max = 0.5, 0.1, 2.0
+        evolved = 0
+        new = self
+
+        def min_abs(x, y):
+            return x if abs(x) < abs(y) else y
+        while True:
+            dt = min_abs(new.evolve_config.guess_dt, evolve_dt - evolved)
+            # as in the reference (mps.py:757-759) the trial state replaces the current one even when the
+            # step is then judged inaccurate and repeated with a smaller guess
+            new, error = sub_step(new, dt, evolved)
+            p = (new.evolve_config.adaptive_rtol / (error + 1e-30)) ** (1 / rk.order[0])
+            if p < p_restart:
+                new.evolve_config.guess_dt = dt * max(p_min, p)
+            elif np.allclose(dt + evolved, evolve_dt):
+                new.evolve_config.guess_dt = min_abs(dt * p, new.evolve_config.guess_dt)
+                return new
+            else:
+                new.evolve_config.guess_dt *= min(p, p_max)
+                evolved += dt
 
     def _evolve_adaptive(self, mpo, evolve_target_t):
         """mps.py:46-115 (adaptive_tdvp): step-doubling error control around _evolve_tdvp_ps."""

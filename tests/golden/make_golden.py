@@ -626,6 +626,28 @@ def gen_pc():
     out["ada_occ"] = np.array(occ)
     out["ada_guess_dt"] = np.array(guess)
     out["ada_bond_dims"] = np.array(dims)
+    # Runge-Kutta propagators (mps.py:664-793): classical RK4 with the MPO given as a function of time,
+    # and the tableau integrator with the embedded Fehlberg pair and adaptive step control
+    for tag, kw in (("rk4", dict(method=EvolveMethod.prop_and_compress_tdrk4)),
+                    ("rkf", dict(method=EvolveMethod.prop_and_compress_tdrk, adaptive=True, guess_dt=0.3,
+                                 adaptive_rtol=1e-4, rk_solver="RKF45")),
+                    ("rk3", dict(method=EvolveMethod.prop_and_compress_tdrk, rk_solver="Kutta_RK3"))):
+        np.random.seed(777)
+        gs = Mps.ground_state(model, False)
+        mps = Mpo.onsite(model, r"a^\dagger", dof_set={0}) @ gs
+        mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+        mps.evolve_config = EvolveConfig(**kw)
+        occ, guess, dims = [], [], []
+        for i in range(3):
+            mps = mps.evolve((lambda t, *a, **k: mpo) if tag == "rk4" else mpo, 0.5)
+            occ.append([mps.expectation(o) for o in occ_ops])
+            guess.append(mps.evolve_config.guess_dt)
+            dims.append(mps.bond_dims)
+        out[f"{tag}_occ"] = np.array(occ)
+        out[f"{tag}_energy"] = np.array(mps.expectation(mpo))
+        out[f"{tag}_guess_dt"] = np.array(guess)
+        out[f"{tag}_bond_dims"] = np.array(dims)
+        dump_mp(f"{tag}_mpsT", mps, out)
     np.savez_compressed(os.path.join(HERE, "pc.npz"), **out)
 
 

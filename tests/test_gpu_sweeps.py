@@ -778,3 +778,36 @@ def test_variational_compress_golden(golden, method):
     ref = to_device_mps(load_oracle_mps(g, f"{method}_new", meta=f"{method}_new"))
     assert abs(abs(ref.conj().dot(new)) / (ref.mp_norm * new.mp_norm) - 1) < T_TOL
     assert abs(new.conj().dot(exact)) / (new.mp_norm * exact.mp_norm) > 1 - 1e-6
+
+
+@pytest.mark.parametrize("tag", ["rk4", "rkf", "rk3"])
+def test_prop_and_compress_runge_kutta_golden(golden, tag):
+    """Mps.evolve with the Runge-Kutta propagate-and-compress integrators (mps.py:664-793): classical
+    RK4 with the MPO given as a function of time, the tableau integrator with the embedded Fehlberg pair
+    and adaptive step control, and a fixed-step third-order tableau; Mpo.contract, Mps.add and the SVD
+    compression run on the device."""
+    from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig
+    g = golden("pc")
+    mpo = _device_mpo_with_qn(g)
+    from renormalizer_b200.mpo import Mpo
+    occ = [Mpo(load_mpo(g, f"occ{i}")) for i in range(int(g["nmol"]))]
+    mps = _device_mps_with_coeff(g, "mps0")
+    mps.compress_config = CompressConfig(CompressCriteria.fixed, max_bonddim=10)
+    mps.evolve_config = {
+        "rk4": EvolveConfig(EvolveMethod.prop_and_compress_tdrk4),
+        "rkf": EvolveConfig(EvolveMethod.prop_and_compress_tdrk, adaptive=True, guess_dt=0.3, adaptive_rtol=1e-4,
+                            rk_solver="RKF45"),
+        "rk3": EvolveConfig(EvolveMethod.prop_and_compress_tdrk, rk_solver="Kutta_RK3")}[tag]
+    assert not mps.evolve_config.is_tdvp
+    occs, guesses, dims = [], [], []
+    for _ in range(3):
+        mps = mps.evolve((lambda t, *a, **k: mpo) if tag == "rk4" else mpo, 0.5)
+        occs.append([mps.expectation(o) for o in occ])
+        guesses.append(mps.evolve_config.guess_dt)
+        dims.append(mps.bond_dims)
+    assert np.array_equal(np.array(dims), g[f"{tag}_bond_dims"])
+    assert np.abs(np.array(occs) - g[f"{tag}_occ"]).max() < E_TOL
+    assert abs(mps.expectation(mpo) - float(g[f"{tag}_energy"])) < E_TOL
+    assert np.allclose(guesses, g[f"{tag}_guess_dt"], rtol=1e-6)
+    ref = to_device_mps(load_oracle_mps(g, f"{tag}_mpsT", meta="mps0"))
+    assert abs(abs(ref.conj().dot(mps)) - 1) < T_TOL

@@ -461,3 +461,38 @@ def test_variational_compress(golden, method):
     assert abs(abs(ref.dot_conj(new)) / (ref.mp_norm * new.mp_norm) - 1) < 1e-8
     # a compression: close to the exact product
     assert abs(new.dot_conj(exact)) / (new.mp_norm * exact.mp_norm) > 1 - 1e-6
+
+
+@pytest.mark.parametrize("tag", ["rk4", "rkf", "rk3"])
+def test_prop_and_compress_runge_kutta(golden, tag):
+    """The Runge-Kutta propagate-and-compress integrators (mps.py:664-793): classical RK4 with the MPO
+    given as a function of time, the tableau integrator with the embedded Fehlberg pair and adaptive
+    step control, and a fixed-step third-order tableau -- occupations, bond dimensions, guess_dt and
+    the final state follow the reference (evolve's "mps_only" normalisation included)."""
+    from helpers import load_oracle_mpo
+    from oracle.sweep import evolve_pc_tdrk4, evolve_pc_tdrk, CompressSpec, normalize
+    from renormalizer_b200.rk import RungeKutta
+    g = golden("pc")
+    mpo = load_oracle_mpo(g)
+    occ = [load_mpo(g, f"occ{i}") for i in range(int(g["nmol"]))]
+    mps = _load_with_coeff(g, "mps0")
+    spec = CompressSpec("fixed", max_bonddim=10)
+    guess = 0.3 if tag == "rkf" else 0.1
+    occs, guesses, dims = [], [], []
+    for _ in range(3):
+        if tag == "rk4":
+            mps = evolve_pc_tdrk4(mps, lambda t: mpo, 0.5, spec)
+        else:
+            rk = RungeKutta("RKF45" if tag == "rkf" else "Kutta_RK3")
+            mps, guess = evolve_pc_tdrk(mps, lambda t: mpo, 0.5, spec, rk.tableau, rk.order, adaptive=tag == "rkf",
+                                        guess_dt=guess, rtol=1e-4)
+        normalize(mps, "mps_only")
+        occs.append([mps.expectation(o) for o in occ])
+        guesses.append(guess)
+        dims.append(mps.bond_dims)
+    assert np.array_equal(np.array(dims), g[f"{tag}_bond_dims"])
+    assert np.abs(np.array(occs) - g[f"{tag}_occ"]).max() < 1e-10
+    assert abs(mps.expectation(mpo.sites) - float(g[f"{tag}_energy"])) < 1e-10
+    assert np.allclose(guesses, g[f"{tag}_guess_dt"], rtol=1e-6)
+    ref = load_oracle_mps(g, f"{tag}_mpsT", meta="mps0")
+    assert abs(abs(ref.dot_conj(mps)) - 1) < 1e-10
