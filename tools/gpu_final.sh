@@ -15,6 +15,5 @@ cat gpurun_out/r2f_hop.log
 timeout 1200 ncu --profile-from-start off --cache-control none --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2f_bench_launches.csv python bench.py --steps 1 --warmup 1 --no-sub --no-e2e --no-roofline --no-cpu-baseline --profiler-range > gpurun_out/r2f_ncu2.log 2>&1
 python tools/launch_summary.py gpurun_out/r2f_bench_launches.csv > gpurun_out/r2f_launch_summary.md
 head -24 gpurun_out/r2f_launch_summary.md
-timeout 1200 ncu --profile-from-start off --cache-control none --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2f_dmrg_launches.csv python bench.py --workload holstein_dmrg --steps 1 --warmup 3 --no-e2e --no-roofline --no-cpu-baseline --profiler-range > gpurun_out/r2f_ncu3.log 2>&1
-python tools/launch_summary.py gpurun_out/r2f_dmrg_launches.csv > gpurun_out/r2f_dmrg_launch_summary.md
-head -24 gpurun_out/r2f_dmrg_launch_summary.md
+# (a launch list of a Holstein sweep takes > 20 min under ncu: ~50 k launches; tools/pyprof_dmrg.py gives the breakdown instead)
+timeout 240 python tools/pyprof_dmrg.py 512 20 holstein_dmrg 3 > gpurun_out/r2f_dmrg_pyprof.txt 2>&1; head -24 gpurun_out/r2f_dmrg_pyprof.txt

@@ -1,3 +1,5 @@
+#!/bin/bash
+# N-GPU run of bench.py on one box (weak-scaling headline + single-chain strong-scaling legs): bash tools/gpu_scale.sh 8
 N=${1:-8}
 timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/r2_scale$N.json 2> gpurun_out/r2_scale$N.err; tail -c 600 gpurun_out/r2_scale$N.err
 python - <<PY
