@@ -39,9 +39,21 @@ def qn_mask_outer(qnbigl: np.ndarray, qnbigr: np.ndarray, qntot):
     return mask.reshape(sl + sr)
 
 
+_rank_cache = {}
+
+
 def economic_rank(qnbigl: np.ndarray, qnbigr: np.ndarray, qntot):
     """Number of singular vectors svd_qn returns with full_matrices=False: the sum over the
-    quantum-number blocks of min(rows, columns)."""
+    quantum-number blocks of min(rows, columns).  Cached on the labels (same bond, sweep after sweep)."""
+    key = (qnbigl.tobytes(), qnbigr.tobytes(), np.asarray(qntot).tobytes(), qnbigl.shape, qnbigr.shape)
+    if key not in _rank_cache:
+        if len(_rank_cache) > 512:
+            _rank_cache.clear()
+        _rank_cache[key] = _economic_rank(qnbigl, qnbigr, qntot)
+    return _rank_cache[key]
+
+
+def _economic_rank(qnbigl, qnbigr, qntot):
     nq = qnbigl.shape[-1]
     lq, lc = np.unique(qnbigl.reshape(-1, nq), axis=0, return_counts=True)
     rq, rc = np.unique(np.asarray(qntot).reshape(1, -1) - qnbigr.reshape(-1, nq), axis=0, return_counts=True)
@@ -224,6 +236,34 @@ def _block_svd(block, full_matrices, opt_full_matrices, economic=None, sh=None, 
     return u, s, vh
 
 
+_structure_cache = {}
+
+
+def _block_structure(lqn, rqn, qntot, nl, nr, dev):
+    """The quantum-number blocks of a bond matrix: [(ql, qr, row indices, column indices, trivial)] in
+    the reference's iteration order (svd_qn.py:176-186), the index arrays already on the device.  The
+    structure of a bond repeats whenever its labels do (fixed-basis sweeps, repeated H_eff set-ups), so
+    it is cached on the quantum-number labels."""
+    key = (lqn.tobytes(), rqn.tobytes(), np.asarray(qntot).tobytes(), lqn.shape, rqn.shape, str(dev))
+    hit = _structure_cache.get(key)
+    if hit is not None:
+        return hit
+    out = []
+    for ql in _distinct_qn(lqn):
+        qr_ = qntot - ql
+        rset = np.where(get_qn_mask(rqn, qr_))[0]
+        if len(rset) == 0:
+            continue
+        lset = np.where(get_qn_mask(lqn, ql))[0]
+        trivial = len(lset) == nl and len(rset) == nr
+        li, ri = (None, None) if trivial else (_idx(lset, dev), _idx(rset, dev))
+        out.append((ql, qr_, li, ri, trivial))
+    if len(_structure_cache) > 512:
+        _structure_cache.clear()
+    _structure_cache[key] = out
+    return out
+
+
 def _scatter_rows(indices, block, nrows, trivial):
     if trivial:
         return block
@@ -274,19 +314,8 @@ def svd_qn(coef_array, qnbigl: np.ndarray, qnbigr: np.ndarray, qntot: np.ndarray
         dim = min(nl, nr)
         return bu, [zero] * dim, bv, [zero] * dim
     todo = []
-    for ql in _distinct_qn(lqn):
-        qr_ = qntot - ql
-        rset = np.where(get_qn_mask(rqn, qr_))[0]
-        if len(rset) == 0:
-            continue
-        lset = np.where(get_qn_mask(lqn, ql))[0]
-        trivial = len(lset) == nl and len(rset) == nr
-        if trivial:
-            block = mat
-            li = ri = None
-        else:
-            li, ri = _idx(lset, dev), _idx(rset, dev)
-            block = mat.index_select(0, li).index_select(1, ri).contiguous()
+    for ql, qr_, li, ri, trivial in _block_structure(lqn, rqn, qntot, nl, nr, dev):
+        block = mat if trivial else mat.index_select(0, li).index_select(1, ri).contiguous()
         todo.append((ql, qr_, li, ri, trivial, block))
     economic = _economic_svds([t[-1] for t in todo]) if not QR else [None] * len(todo)
     s_host = [eco[1].cpu().numpy() for eco in economic] if not QR else [None] * len(todo)
