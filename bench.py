@@ -766,6 +766,19 @@ def strong_scaling(gpu, args, name, bond, steps, warmup):
     from renormalizer_b200.lib import Environ
     from renormalizer_b200.configs import CompressConfig, CompressCriteria, EvolveConfig, EvolveMethod
     work = make_workload(name, bond, args, seed=1234)            # the SAME chain on every rank
+    # ... bit for bit: the MPO builder and the state generator go through LAPACK on the host, so rank 0's
+    # arrays are broadcast (all ranks must take identical decisions, see parallel.ShardedHop)
+    torch, dist = gpu.torch, gpu.dist
+    for arrs in (work["mpo"], work["sites"]):
+        shapes = torch.tensor([x for a in arrs for x in a.shape], dtype=torch.int64, device="cuda")
+        ref_shapes = shapes.clone()
+        dist.broadcast(ref_shapes, 0)
+        if not torch.equal(shapes, ref_shapes):
+            raise RuntimeError("workload shapes differ between ranks")
+        for i, a in enumerate(arrs):
+            t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            dist.broadcast(torch.view_as_real(t) if t.is_complex() else t, 0)
+            arrs[i] = t.cpu().numpy()
     meta = work["meta"]
     mpo = Mpo(work["mpo"])
     res = {}
