@@ -31,6 +31,10 @@ struct WCsr {
   const double* val = nullptr;
 };
 
+// The int32 accumulators of a digit level hold K (g + 1) 2^12 < 2^31, i.e. K <= 65536 per CTA; longer
+// contractions (the G3 of a wide MPO bond: K = w M) run split-K with at least K / 65536 splits, whose
+// partial tiles are summed in FP64 (launch_ozaki_gemm_maps), up to 16 splits.
+constexpr double OZ_MAX_K = 16.0 * 65536.0;
 static int g_ozaki_slices = 7;
 static double g_ozaki_min_work = 4.0e6;
 
@@ -38,7 +42,7 @@ static int gemm_dispatch(cudaStream_t st, int path, int m, int n, int k, const d
                          const double* B, long ldb, double* C, long ldc) {
   // tensor-core path for contractions large enough to fill 128x128 tiles; boundary sites stay on
   // the exact DMMA kernel
-  if (path == 1 && (double)m * n * k >= g_ozaki_min_work && k <= 65536)
+  if (path == 1 && (double)m * n * k >= g_ozaki_min_work && k <= OZ_MAX_K)
     return rn_ozaki_gemm_tn(st, m, n, k, A, lda, B, ldb, C, ldc, g_ozaki_slices);
   return launch_gemm_tn_f64(st, m, n, k, A, lda, B, ldb, C, ldc, 0, 1, 0, 0, 0);
 }
@@ -68,7 +72,7 @@ static void oz_free(cudaStream_t st, OzOperand& o) {
 }
 
 static bool use_ozaki(int path, double m, double n, double k) {
-  return path == 1 && m * n * k >= g_ozaki_min_work && k <= 65536;
+  return path == 1 && m * n * k >= g_ozaki_min_work && k <= OZ_MAX_K;
 }
 
 // GEMM with pre-split operands (either may be split on the fly from X when `fresh` is given)

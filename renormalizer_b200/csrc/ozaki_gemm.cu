@@ -938,23 +938,29 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
     if (const char* e = getenv("RN_OZ_KSPLIT")) g_oz_force_ksplit = atoi(e);
   }
   const int slots = g_oz_sms / per_unit;
+  // a CTA's int32 level accumulators overflow beyond 65536 contraction elements (512 K blocks): longer
+  // contractions MUST be split along K, the partial tiles are summed in FP64
+  constexpr int OZ_KB_MAX = 65536 / OZ_BK;
+  const int min_split = (kblocks + OZ_KB_MAX - 1) / OZ_KB_MAX;
+  if (min_split > 16) return (int)cudaErrorInvalidValue;
   {
     const double t_kb = 256.0 * (nslices * (nslices + 1) / 2), t_fixed = 9000.0, t_red = 1200.0;
     double best = 1e300;
     const int smax = kblocks < 16 ? kblocks : 16;
     // (a) every unit split the same way
-    for (int s = 1; s <= smax; ++s) {
+    for (int s = min_split; s <= smax; ++s) {
       const int per = (kblocks + s - 1) / s;
       const int seff = (kblocks + per - 1) / per;
       if (seff != s) continue;
-      if ((double)tiles * per_unit * seff * OZ_BM * OZ_BN * 8.0 > 192e6) continue;   // partial tiles stay L2 resident
+      // partial tiles stay L2 resident -- unless the split is forced by the accumulator range
+      if (min_split == 1 && (double)tiles * per_unit * seff * OZ_BM * OZ_BN * 8.0 > 192e6) continue;
       const long waves = ceil_div((long)tiles * seff, slots);
       const double cost = waves * (per * t_kb + t_fixed) + (seff > 1 ? t_red * seff + 2000.0 : 0.0);
       if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; n_full = 0; }
     }
     // (b) whole waves unsplit, the ragged last wave split along K
     const int tail = tiles % slots, full = tiles - tail;
-    if (full > 0 && tail > 0) {
+    if (full > 0 && tail > 0 && min_split == 1) {
       const int st_max = slots / tail < smax ? slots / tail : smax;
       for (int s = 2; s <= st_max; ++s) {
         const int per = (kblocks + s - 1) / s;
@@ -964,11 +970,16 @@ int launch_ozaki_gemm_maps(cudaStream_t st, int m, int n, int K, int nslices, co
         if (cost < best * 0.97) { best = cost; ksplit = seff; kb_per = per; n_full = full; }
       }
     }
-    if (g_oz_force_ksplit > 0 && g_oz_force_ksplit <= kblocks) {
+    if (g_oz_force_ksplit >= min_split && g_oz_force_ksplit <= kblocks) {
       kb_per = (kblocks + g_oz_force_ksplit - 1) / g_oz_force_ksplit;
       ksplit = (kblocks + kb_per - 1) / kb_per;
       n_full = 0;
     }
+  }
+  if (ksplit < min_split) {                 // no balanced partition qualified: the plain forced split
+    kb_per = (kblocks + min_split - 1) / min_split;
+    ksplit = (kblocks + kb_per - 1) / kb_per;
+    n_full = 0;
   }
   if (ksplit == 1) n_full = tiles;
   const int split_units = tiles - n_full;

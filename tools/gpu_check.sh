@@ -1,4 +1,5 @@
 #!/bin/bash
-# Quick GPU check (about 2 min): the parity suite and the host profile of a converged Holstein sweep.
-( time timeout 600 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -6
-timeout 240 python tools/pyprof_dmrg.py 512 20 holstein_dmrg 3 > gpurun_out/r2f_dmrg_pyprof.txt 2>&1; head -22 gpurun_out/r2f_dmrg_pyprof.txt | cut -c1-220
+# Quick GPU check: the parity suite, then the ab initio DMRG workload as the headline of a short bench run.
+( time timeout 400 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -5
+timeout 200 python tools/hop_qc_shape.py 2>&1 | tail -1
+timeout 400 python bench.py --workload qc_dmrg --steps 1 --warmup 1 --no-e2e --no-roofline > gpurun_out/r2f_bench_qc.json 2> gpurun_out/r2f_bench_qc.err; tail -2 gpurun_out/r2f_bench_qc.err; python tools/show_bench.py gpurun_out/r2f_bench_qc.json | cut -c1-400
