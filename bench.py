@@ -839,8 +839,13 @@ def run_ours(args):
             if args.only_sub and name not in args.only_sub.split(","):
                 continue
             gpu.torch.cuda.empty_cache()
-            sub, _ = measure(gpu, args, name, bond, steps, warmup, nsample,
-                             do_cpu=not args.no_cpu_baseline, do_parity=not args.no_parity)
+            try:
+                sub, _ = measure(gpu, args, name, bond, steps, warmup, nsample,
+                                 do_cpu=not args.no_cpu_baseline, do_parity=not args.no_parity)
+            except Exception as exc:                     # a failing sub-result must not take the headline line with it
+                import traceback
+                traceback.print_exc()
+                sub = {"workload": name, "error": f"{type(exc).__name__}: {exc}"}
             subs.append(sub)
     strong = []
     if gpu.world > 1 and args.workload == "sbm_tdvp" and not args.no_strong:

@@ -3,6 +3,9 @@ import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 def show(r):
     print(r.get("workload", r.get("config", {}).get("workload")))
+    if "error" in r:
+        print("  ERROR", r["error"])
+        return
     print("  value", round(r["value"], 3), "ms/step", round(r["ms_per_step"], 1), "e2e", r["e2e"] and round(r["e2e"]["value"], 3),
           "launches", r["gpu_launches"])
     rf = r.get("roofline")
