@@ -42,7 +42,7 @@ UNIT = "sites/s"
 PARITY_TOL = 1e-10
 
 # name -> (default bond dimension, steps, warmup, CPU-sampled site updates) for the sub-results
-SUB_WORKLOADS = {"holstein_dmrg": (512, 3, 3, 3), "qc_dmrg": (1024, 1, 1, 1), "fmo_thermal": (512, 1, 1, 1)}
+SUB_WORKLOADS = {"holstein_dmrg": (512, 3, 3, 3), "qc_dmrg": (1024, 1, 2, 1), "fmo_thermal": (512, 1, 1, 1)}
 
 
 # --------------------------------------------------------------------------------------------
